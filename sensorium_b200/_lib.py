@@ -1,0 +1,93 @@
+"""ctypes binding of libdwn_b200.so (include/dwn_b200.h).  Fails loudly: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "libdwn_b200.so"
+_lib = None
+
+
+class DwnError(RuntimeError):
+    pass
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int), ("A", C.c_void_p), ("B", C.c_void_p), ("a_mn", C.c_int), ("b_mn", C.c_int),
+        ("lda", C.c_long), ("ldb", C.c_long), ("a_zstride", C.c_long), ("b_zstride", C.c_long),
+        ("a_zmode", C.c_int), ("b_zmode", C.c_int), ("b_batch_rows", C.c_int),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("Z", C.c_int),
+        ("epi", C.c_int), ("D", C.c_void_p), ("d_dtype", C.c_int), ("ldd", C.c_long), ("d_zstride", C.c_long),
+        ("m_limit", C.c_int), ("n_limit", C.c_int), ("bias", C.c_void_p), ("beta", C.c_float), ("Tn", C.c_int),
+        ("n_out_total", C.c_int), ("row_offset_per_z", C.c_int), ("block_n", C.c_int),
+        ("dbg_lbo_a", C.c_uint), ("dbg_sbo_a", C.c_uint), ("dbg_lbo_b", C.c_uint), ("dbg_sbo_b", C.c_uint),
+    ]
+
+
+_T = {"p": C.c_void_p, "i": C.c_int, "l": C.c_long, "f": C.c_float, "d": C.c_double}
+
+# name -> argument type string (p pointer, i int, l long, f float, d double); mirrors include/dwn_b200.h
+SIGNATURES = {
+    "dwn_input_moments": "piilpipp",
+    "dwn_stem_coef": "pidppppppffpip",
+    "dwn_stem_fwd": "ppppppppp" + "iiiiiiii" + "p",
+    "dwn_bn_finalize": "pidpppppffipiip",
+    "dwn_colstats": "pliipiip",
+    "dwn_sdw_fwd": "ppppp" + "iiiiiii" + "p",
+    "dwn_tdw_fwd": "ppppp" + "iiiiii" + "p",
+    "dwn_se_pool": "pppp" + "iiiii" + "p",
+    "dwn_se_mlp": "pii" + "ppppppp" + "iii" + "p",
+    "dwn_fold_gate": "ppp" + "iiii" + "p",
+    "dwn_block_out": "ppppp" + "ppp" + "ppp" + "iiiiiiiiii" + "p",
+    "dwn_pool_hw": "ppp" + "iii" + "p",
+    "dwn_cortex_out": "ppppppp" + "iiiiii" + "p",
+    "dwn_readout_prep": "pppp" + "iiii" + "p",
+    "dwn_cast_bf16": "pplp",
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise DwnError(
+                f"{_LIB_PATH} is missing: build it with `python -m sensorium_b200.build` "
+                "(sensorium_b200 has no CPU / eager fallback)")
+        _lib = C.CDLL(str(_LIB_PATH))
+        _lib.dwn_last_error.restype = C.c_char_p
+        _lib.dwn_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+        _lib.dwn_gemm.restype = C.c_int
+        for name, sig in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.argtypes = [_T[ch] for ch in sig]
+            fn.restype = C.c_int
+    return _lib
+
+
+def exported_symbols():
+    return ["dwn_last_error", "dwn_abi_version", "dwn_sm_count", "dwn_gemm", *SIGNATURES.keys()]
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    return x
+
+
+def call(name: str, *args):
+    fn = getattr(lib(), name)
+    rc = fn(*[_ptr(a) for a in args])
+    if rc != 0:
+        raise DwnError(f"{name} failed: {lib().dwn_last_error().decode()}")
+
+
+def gemm(stream, **kw):
+    d = GemmDesc()
+    for k, v in kw.items():
+        setattr(d, k, _ptr(v))
+    rc = lib().dwn_gemm(C.byref(d), stream)
+    if rc != 0:
+        raise DwnError(f"dwn_gemm failed: {lib().dwn_last_error().decode()}")

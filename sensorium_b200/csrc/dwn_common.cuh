@@ -1,0 +1,127 @@
+// Common device/host helpers for the DwiseNeuro B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (never throws across the C ABI) -------------------------------------------
+int dwn_fail(const char* fmt, ...);
+int dwn_num_sms();
+#define DWN_LAUNCH_CHECK()                                                                        \
+  do {                                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                                         \
+    if (e__ != cudaSuccess) return dwn_fail("%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+  } while (0)
+#define DWN_REQUIRE(cond, ...)                                                                    \
+  do {                                                                                            \
+    if (!(cond)) return dwn_fail(__VA_ARGS__);                                                    \
+  } while (0)
+
+#define DWN_DT_F32 0
+#define DWN_DT_BF16 1
+
+// ---- vector access: 16-byte vectors of the storage type ----------------------------------------
+template <typename T> struct VecT;
+template <> struct VecT<float> { static constexpr int V = 4; };
+template <> struct VecT<bf16> { static constexpr int V = 8; };
+
+__device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& lo, float& hi) {
+  lo = __uint_as_float(u << 16);
+  hi = __uint_as_float(u & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 16-byte vector load -> floats
+__device__ __forceinline__ void ldv(const float* p, float (&o)[4]) {
+  float4 r = *reinterpret_cast<const float4*>(p);
+  o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
+}
+__device__ __forceinline__ void ldv(const bf16* p, float (&o)[8]) {
+  uint4 r = *reinterpret_cast<const uint4*>(p);
+  unpack_bf16x2(r.x, o[0], o[1]);
+  unpack_bf16x2(r.y, o[2], o[3]);
+  unpack_bf16x2(r.z, o[4], o[5]);
+  unpack_bf16x2(r.w, o[6], o[7]);
+}
+__device__ __forceinline__ void stv(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void stv(bf16* p, const float (&v)[8]) {
+  uint4 r;
+  r.x = pack_bf16x2(v[0], v[1]);
+  r.y = pack_bf16x2(v[2], v[3]);
+  r.z = pack_bf16x2(v[4], v[5]);
+  r.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+// 4-channel access (quad) for both storage types
+__device__ __forceinline__ void ldq(const float* p, float (&o)[4]) { ldv(p, o); }
+__device__ __forceinline__ void ldq(const bf16* p, float (&o)[4]) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  unpack_bf16x2(r.x, o[0], o[1]);
+  unpack_bf16x2(r.y, o[2], o[3]);
+}
+__device__ __forceinline__ void stq(float* p, const float (&v)[4]) { stv(p, v); }
+__device__ __forceinline__ void stq(bf16* p, const float (&v)[4]) {
+  uint2 r;
+  r.x = pack_bf16x2(v[0], v[1]);
+  r.y = pack_bf16x2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+// value as it will be seen by the consumer after storage rounding
+template <typename T> __device__ __forceinline__ float rnd(float x);
+template <> __device__ __forceinline__ float rnd<float>(float x) { return x; }
+template <> __device__ __forceinline__ float rnd<bf16>(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+template <typename T> __device__ __forceinline__ float ld1(const T* p);
+template <> __device__ __forceinline__ float ld1<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld1<bf16>(const bf16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void st1(T* p, float v);
+template <> __device__ __forceinline__ void st1<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st1<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ---- activations: FAST (MUFU ex2+rcp) for the bf16 pipeline, accurate for the fp32 pipeline ---
+template <typename T> struct Act;
+template <> struct Act<float> {
+  static __device__ __forceinline__ float sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+};
+template <> struct Act<bf16> {
+  static __device__ __forceinline__ float sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+};
+template <typename T> __device__ __forceinline__ float silu_t(float x) { return x * Act<T>::sigmoid(x); }
+// d/dx [x*sigmoid(x)] given x
+template <typename T> __device__ __forceinline__ float silu_grad_t(float x) {
+  float s = Act<T>::sigmoid(x);
+  return s * (1.0f + x * (1.0f - s));
+}
+
+// ---- reductions ----------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// BN coefficient table layout: coef[4][C] = {scale, shift, mean, rstd}
+//   y = scale*x + shift ;  xhat = (x-mean)*rstd
+// BN backward coefficient table: bcoef[2][C] = {c1 = sum(dy)/N, c2 = sum(dy*xhat)/N}
+//   dx = gamma*rstd*(dy - c1 - xhat*c2)
+
+static inline int dwn_largest_divisor_le(int n, int cap) {
+  int best = 1;
+  for (int d = 1; d <= cap && d <= n; ++d)
+    if (n % d == 0) best = d;
+  return best;
+}

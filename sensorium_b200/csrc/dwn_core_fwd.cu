@@ -1,0 +1,877 @@
+// Forward kernels of the DwiseNeuro core / cortex glue (channels-last, fused BN+SiLU on load).
+// Reference semantics: /root/reference/src/models/dwiseneuro.py (line numbers cited per kernel).
+#include "dwn_common.cuh"
+#include "dwn_reduce.cuh"
+
+// =================================================================================================
+// input moments: sums and second moments of the 5 input channels (NCDHW fp32 input).
+// Used to derive the stem's train-mode BatchNorm statistics analytically (stem conv is linear):
+//   mean_c = w_c . mu_x ; var_c = w_c^T Cov_x w_c     (dwiseneuro.py:306-309)
+// partial layout: [grid][NM] doubles, NM = CIN + CIN*(CIN+1)/2  (sum_k, then upper-tri sum_jk j<=k)
+// =================================================================================================
+template <int CIN>
+__global__ void __launch_bounds__(256) input_moments_kernel(const float* __restrict__ x, long plane, long total,
+                                                           double* __restrict__ partial) {
+  constexpr int NM = CIN + CIN * (CIN + 1) / 2;
+  float acc[NM];
+  double dacc[NM];
+#pragma unroll
+  for (int i = 0; i < NM; ++i) { acc[i] = 0.f; dacc[i] = 0.0; }
+  int it = 0;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    long b = idx / plane, pos = idx - b * plane;
+    float v[CIN];
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) v[k] = x[(b * CIN + k) * plane + pos];
+    int q = CIN;
+#pragma unroll
+    for (int j = 0; j < CIN; ++j) {
+      acc[j] += v[j];
+#pragma unroll
+      for (int k = j; k < CIN; ++k) acc[q++] += v[j] * v[k];
+    }
+    if (++it == 32) {  // flush to double to keep fp32 partial sums short
+#pragma unroll
+      for (int i = 0; i < NM; ++i) { dacc[i] += (double)acc[i]; acc[i] = 0.f; }
+      it = 0;
+    }
+  }
+  __shared__ double red[8][NM];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NM; ++i) {
+    double s = warp_sum_d(dacc[i] + (double)acc[i]);
+    if (lane == 0) red[wid][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < NM) {
+    double s = 0;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    partial[(long)blockIdx.x * NM + threadIdx.x] = s;
+  }
+}
+
+// moments[NM] = sum over partial rows
+__global__ void moments_finalize_kernel(const double* __restrict__ partial, int P, int NM, double* __restrict__ mom) {
+  int i = threadIdx.x;
+  if (i < NM) {
+    double s = 0;
+    for (int p = 0; p < P; ++p) s += partial[(long)p * NM + i];
+    mom[i] = s;
+  }
+}
+
+extern "C" int dwn_input_moments(const float* x, int B, int cin, long plane, double* partial, int P, double* mom,
+                                 void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  long total = (long)B * plane;
+  int nm = cin + cin * (cin + 1) / 2;
+  switch (cin) {
+#define CASE(N) case N: input_moments_kernel<N><<<P, 256, 0, st>>>(x, plane, total, partial); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    default: return dwn_fail("dwn_input_moments: in_channels=%d unsupported (1..8)", cin);
+  }
+  DWN_LAUNCH_CHECK();
+  moments_finalize_kernel<<<1, 64, 0, st>>>(partial, P, nm, mom);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// stem BN coefficients from the input moments (train) — one thread per output channel.
+// Updates running stats exactly like nn.BatchNorm3d (momentum 0.1, unbiased var) (dwiseneuro.py:9-22).
+__global__ void stem_coef_kernel(const double* __restrict__ mom, int cin, double count, const float* __restrict__ w,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float* __restrict__ rmean, float* __restrict__ rvar, long long* __restrict__ nbt,
+                                 float momentum, float eps, float* __restrict__ coef, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  double mu[8];
+  for (int k = 0; k < cin; ++k) mu[k] = mom[k] / count;
+  double mean = 0;
+  for (int k = 0; k < cin; ++k) mean += (double)w[c * cin + k] * mu[k];
+  double var = 0;
+  int q = cin;
+  for (int j = 0; j < cin; ++j)
+    for (int k = j; k < cin; ++k) {
+      double cov = mom[q++] / count - mu[j] * mu[k];
+      double ww = (double)w[c * cin + j] * (double)w[c * cin + k];
+      var += (j == k ? 1.0 : 2.0) * ww * cov;
+    }
+  if (var < 0) var = 0;
+  double rstd = 1.0 / sqrt(var + (double)eps);
+  float sc = (float)((double)gamma[c] * rstd);
+  coef[c] = sc;
+  coef[C + c] = (float)((double)beta[c] - mean * (double)gamma[c] * rstd);
+  coef[2 * C + c] = (float)mean;
+  coef[3 * C + c] = (float)rstd;
+  if (rmean) {
+    double unb = count > 1 ? var * count / (count - 1.0) : var;
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+  }
+}
+
+extern "C" int dwn_stem_coef(const double* mom, int cin, double count, const float* w, const float* gamma,
+                             const float* beta, float* rmean, float* rvar, long long* nbt, float momentum, float eps,
+                             float* coef, int C, void* stream) {
+  stem_coef_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mom, cin, count, w, gamma, beta, rmean, rvar, nbt,
+                                                                      momentum, eps, coef, C);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// generic BN finalize: partial[P][2][C] (sum, sumsq) -> coef[4][C]; eval mode uses running stats.
+// =================================================================================================
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int P, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   long long* __restrict__ nbt, float momentum, float eps, int training,
+                                   float* __restrict__ coef, int C, int Cp) {
+  // block = (32 channels, 8 slices); partial has Cp channels, channel c reads column c % Cp
+  // (cyclic channel tiling of the shortcut, dwiseneuro.py:130-132)
+  __shared__ double s_sum[8][32], s_sq[8][32];
+  int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  int c = blockIdx.x * 32 + cl;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt && training) *nbt += 1;
+  double mean, var;
+  if (training) {
+    double s = 0, q = 0;
+    if (c < C) {
+      const int cp = c % Cp;
+      for (int p = sl; p < P; p += 8) {
+        s += (double)partial[((long)p * 2) * Cp + cp];
+        q += (double)partial[((long)p * 2 + 1) * Cp + cp];
+      }
+    }
+    s_sum[sl][cl] = s;
+    s_sq[sl][cl] = q;
+    __syncthreads();
+    if (sl != 0 || c >= C) return;
+    s = 0; q = 0;
+    for (int i = 0; i < 8; ++i) { s += s_sum[i][cl]; q += s_sq[i][cl]; }
+    mean = s / count;
+    var = q / count - mean * mean;
+    if (var < 0) var = 0;
+    if (rmean) {
+      double unb = count > 1 ? var * count / (count - 1.0) : var;
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+    }
+  } else {
+    if (sl != 0 || c >= C) return;
+    mean = rmean[c];
+    var = rvar[c];
+  }
+  double rstd = 1.0 / sqrt(var + (double)eps);
+  double g = gamma ? (double)gamma[c] : 1.0, b = beta ? (double)beta[c] : 0.0;
+  coef[c] = (float)(g * rstd);
+  coef[C + c] = (float)(b - mean * g * rstd);
+  coef[2 * C + c] = (float)mean;
+  coef[3 * C + c] = (float)rstd;
+}
+
+extern "C" int dwn_bn_finalize(const float* partial, int P, double count, const float* gamma, const float* beta,
+                               float* rmean, float* rvar, long long* nbt, float momentum, float eps, int training,
+                               float* coef, int C, int Cp, void* stream) {
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partial, P, count, gamma, beta, rmean, rvar, nbt,
+                                                                      momentum, eps, training, coef, C, Cp > 0 ? Cp : C);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// stem: Conv3d(cin -> C0, 1x1x1, no bias) + BN + positional encoding of block 0, writes the
+// channels-last trunk X0[M][C0] (fp32, + optional bf16 copy) and the partial stats of the
+// (strided) shortcut of block 0.       (dwiseneuro.py:306-309, 147-192, 125-134)
+// =================================================================================================
+template <int CIN>
+__global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ coef,
+                                const float* __restrict__ pe_t, const float* __restrict__ pe_h,
+                                const float* __restrict__ pe_w, float* __restrict__ out, bf16* __restrict__ out_bf,
+                                float* __restrict__ partial, int next_stride, int B, int Tn, int H, int W, int C0,
+                                int cqc) {
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
+  const int c = (blockIdx.y * cqc + cq) * 4;
+  float wr[4][CIN], sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = coef[c + j];
+    sh[j] = coef[C0 + c + j];
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) wr[j][k] = w[(c + j) * CIN + k];
+  }
+  float st[2][4] = {};
+  const long plane = (long)Tn * H * W, M = (long)B * plane;
+  for (long m = (long)blockIdx.x * ln + lane; m < M; m += (long)gridDim.x * ln) {
+    long b = m / plane, pos = m - b * plane;
+    int wq = (int)(pos % W), hq = (int)((pos / W) % H), tq = (int)(pos / ((long)W * H));
+    float xv[CIN];
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) xv[k] = __ldg(&x[(b * CIN + k) * plane + pos]);
+    float pt[4], ph[4], pw[4], o[4];
+    ldq(pe_t + (long)tq * C0 + c, pt);
+    ldq(pe_h + (long)hq * C0 + c, ph);
+    ldq(pe_w + (long)wq * C0 + c, pw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < CIN; ++k) a = fmaf(wr[j][k], xv[k], a);
+      o[j] = fmaf(a, sc[j], sh[j]) + ((pt[j] + ph[j]) + pw[j]);
+    }
+    stq(out + m * C0 + c, o);
+    if (out_bf) stq(out_bf + m * C0 + c, o);
+    if (partial && (hq % next_stride == 0) && (wq % next_stride == 0)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { st[0][j] += o[j]; st[1][j] += o[j] * o[j]; }
+    }
+  }
+  if (partial)
+    block_reduce_channels<2, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 2 * C0, C0, blockIdx.y * cqc * 4);
+}
+
+extern "C" int dwn_stem_fwd(const float* x, const float* w, const float* coef, const float* pe_t, const float* pe_h,
+                            const float* pe_w, float* out, void* out_bf, float* partial, int P, int next_stride, int B,
+                            int cin, int Tn, int H, int W, int C0, void* stream) {
+  DWN_REQUIRE(C0 % 4 == 0, "dwn_stem_fwd: C0 %% 4 != 0");
+  int cqc = dwn_largest_divisor_le(C0 / 4, 64);
+  int ln = 256 / cqc;
+  dim3 grid(P, (C0 / 4) / cqc), block(cqc * ln);
+  size_t sm = (size_t)block.x * 2 * 4 * sizeof(float);
+  switch (cin) {
+#define CASE(N)                                                                                                   \
+  case N:                                                                                                         \
+    stem_fwd_kernel<N><<<grid, block, sm, (cudaStream_t)stream>>>(x, w, coef, pe_t, pe_h, pe_w, out, (bf16*)out_bf, \
+                                                                  partial, next_stride, B, Tn, H, W, C0, cqc);     \
+    break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    default: return dwn_fail("dwn_stem_fwd: in_channels=%d unsupported (1..8)", cin);
+  }
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// spatial depth-wise (1,3,3) conv, stride S, pad 1, with BN+SiLU of the producer applied on load.
+//   in  E_raw [NP][H][W][C]   (pre-BN output of conv_pw)          (dwiseneuro.py:90-102)
+//   out S_raw [NP][Ho][Wo][C] (pre-BN), partial[P][2][C] = column sum / sumsq of the stored values
+// CTA tile: one (b,t) plane, THO output rows, all W, CC channels; activated halo tile in smem (fp32).
+// =================================================================================================
+template <typename T, int S, int THO>
+__global__ void sdw_fwd_kernel(const T* __restrict__ in, const float* __restrict__ coef, const float* __restrict__ wgt,
+                               T* __restrict__ out, float* __restrict__ partial, int NP, int H, int W, int C, int CC) {
+  constexpr int V = VecT<T>::V;
+  constexpr int NR = (THO - 1) * S + 3;
+  extern __shared__ float tile[];
+  const int Ho = H / S, Wo = W / S, WP = W + 2;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int c0 = blockIdx.y * CC;
+  // ---- per-thread constants for the load phase
+  const int cvn = CC / V;
+  const int lcv = tid % cvn;
+  float lsc[V], lsh[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    lsc[j] = coef[c0 + lcv * V + j];
+    lsh[j] = coef[C + c0 + lcv * V + j];
+  }
+  // ---- per-thread constants for the compute phase
+  const int cqn = CC / 4;
+  const int cq = tid % cqn, wo = tid / cqn;
+  float wr[9][4];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wr[k][j] = wgt[(c0 + cq * 4 + j) * 9 + k];
+  float st[2][4] = {};
+  // zero halo columns once
+  for (int i = tid; i < NR * 2 * CC; i += nthr) {
+    int r = i / (2 * CC), rem = i % (2 * CC);
+    int col = (rem / CC) ? (W + 1) : 0;
+    tile[(r * WP + col) * CC + (rem % CC)] = 0.f;
+  }
+  const int nb = Ho / THO;
+  const int ntiles = NP * nb;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int p = t / nb, ho0 = (t % nb) * THO;
+    const int hi0 = ho0 * S - 1;
+    __syncthreads();  // previous compute done before overwriting the tile
+    for (int i = tid; i < NR * W * cvn; i += nthr) {
+      int r = i / (W * cvn);
+      int wq = (i / cvn) % W;
+      int hi = hi0 + r;
+      float v[V];
+      if (hi >= 0 && hi < H) {
+        ldv(in + (((long)p * H + hi) * W + wq) * C + c0 + lcv * V, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = silu_t<T>(fmaf(v[j], lsc[j], lsh[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = 0.f;
+      }
+      float* dst = tile + ((r * WP + wq + 1) * CC + lcv * V);
+#pragma unroll
+      for (int j = 0; j < V; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    __syncthreads();
+    float R[3][3][4];
+    auto load_row = [&](int r) {
+      const float* src = tile + ((r * WP + wo * S) * CC + cq * 4);
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        float4 q = *reinterpret_cast<const float4*>(src + kw * CC);
+        R[r % 3][kw][0] = q.x; R[r % 3][kw][1] = q.y; R[r % 3][kw][2] = q.z; R[r % 3][kw][3] = q.w;
+      }
+    };
+    if (S == 1) { load_row(0); load_row(1); } else { load_row(0); }
+#pragma unroll
+    for (int hl = 0; hl < THO; ++hl) {
+      if (S == 1) { load_row(hl + 2); } else { load_row(2 * hl + 1); load_row(2 * hl + 2); }
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = fmaf(R[(hl * S + kh) % 3][kw][j], wr[kh * 3 + kw][j], acc[j]);
+      stq(out + ((((long)p * Ho + ho0 + hl) * Wo + wo) * C + c0 + cq * 4), acc);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float r = rnd<T>(acc[j]);
+        st[0][j] += r;
+        st[1][j] += r * r;
+      }
+    }
+  }
+  __syncthreads();
+  if (partial) block_reduce_channels<2, 4>(st, tile, cqn, Wo, partial + (long)blockIdx.x * 2 * C, C, c0);
+}
+
+template <typename T, int S>
+static int sdw_fwd_launch(const void* in, const float* coef, const float* wgt, void* out, float* partial, int P, int NP,
+                          int H, int W, int C, cudaStream_t st) {
+  const int Ho = H / S, Wo = W / S;
+  int CC = 1024 / Wo;  // (CC/4)*Wo = 256 threads
+  if (CC > 128) CC = 128;
+  while (CC >= 8 && (C % CC != 0)) CC /= 2;
+  DWN_REQUIRE(CC >= 8 && C % CC == 0 && (CC / 4) * Wo <= 1024, "dwn_sdw_fwd: unsupported C=%d W=%d", C, W);
+  int THO = (S == 1 && Ho % 8 == 0) ? 8 : (Ho % 4 == 0 ? 4 : (Ho % 2 == 0 ? 2 : 1));
+  const int NR = (THO - 1) * S + 3;
+  size_t sm = (size_t)NR * (W + 2) * CC * sizeof(float);
+  size_t sm_red = (size_t)(CC / 4) * Wo * 2 * 4 * sizeof(float);
+  if (sm_red > sm) sm = sm_red;
+  dim3 grid(P, C / CC), block((CC / 4) * Wo);
+#define LAUNCH(THO_)                                                                                             \
+  {                                                                                                              \
+    auto k = sdw_fwd_kernel<T, S, THO_>;                                                                         \
+    if (sm > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);           \
+    k<<<grid, block, sm, st>>>((const T*)in, coef, wgt, (T*)out, partial, NP, H, W, C, CC);                      \
+  }
+  switch (THO) {
+    case 8: LAUNCH(8) break;
+    case 4: LAUNCH(4) break;
+    case 2: LAUNCH(2) break;
+    default: LAUNCH(1) break;
+  }
+#undef LAUNCH
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dwn_sdw_fwd(const void* in, const float* coef, const float* wgt, void* out, float* partial, int P, int NP,
+                           int H, int W, int C, int stride, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DWN_REQUIRE(stride == 1 || stride == 2, "dwn_sdw_fwd: stride %d unsupported", stride);
+  DWN_REQUIRE(H % stride == 0 && W % stride == 0, "dwn_sdw_fwd: H,W must be divisible by stride");
+  if (dtype == DWN_DT_F32)
+    return stride == 1 ? sdw_fwd_launch<float, 1>(in, coef, wgt, out, partial, P, NP, H, W, C, st)
+                       : sdw_fwd_launch<float, 2>(in, coef, wgt, out, partial, P, NP, H, W, C, st);
+  return stride == 1 ? sdw_fwd_launch<bf16, 1>(in, coef, wgt, out, partial, P, NP, H, W, C, st)
+                     : sdw_fwd_launch<bf16, 2>(in, coef, wgt, out, partial, P, NP, H, W, C, st);
+}
+
+// =================================================================================================
+// temporal depth-wise (5,1,1) conv, pad 2, BN+SiLU of the producer applied on load.
+//   in S_raw [B][T][HW][C] -> out Tm_raw (same shape), partial[P][2][C]     (dwiseneuro.py:105-111)
+// thread = (channel quad, position); the whole T column lives in registers (TT = compile-time T).
+// =================================================================================================
+template <typename T, int TT>
+__global__ void tdw_fwd_kernel(const T* __restrict__ in, const float* __restrict__ coef, const float* __restrict__ wgt,
+                               T* __restrict__ out, float* __restrict__ partial, int B, int Tn, int HW, int C, int cqc) {
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
+  const int c = (blockIdx.y * cqc + cq) * 4;
+  float sc[4], sh[4], wr[5][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = coef[c + j];
+    sh[j] = coef[C + c + j];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) wr[k][j] = wgt[(c + j) * 5 + k];
+  }
+  float st[2][4] = {};
+  const long npos = (long)B * HW;
+  const long tstride = (long)HW * C;
+  for (long pos = (long)blockIdx.x * ln + lane; pos < npos; pos += (long)gridDim.x * ln) {
+    long b = pos / HW, hw = pos - b * HW;
+    const long base = (b * Tn * HW + hw) * C + c;
+    if (TT > 0) {
+      float a[TT > 0 ? TT : 1][4];
+#pragma unroll
+      for (int t = 0; t < TT; ++t) ldq(in + base + t * tstride, a[t]);
+#pragma unroll
+      for (int t = 0; t < TT; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[t][j] = silu_t<T>(fmaf(a[t][j], sc[j], sh[j]));
+#pragma unroll
+      for (int t = 0; t < TT; ++t) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int ts = t + k - 2;
+          if (ts >= 0 && ts < TT) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = fmaf(a[ts][j], wr[k][j], o[j]);
+          }
+        }
+        stq(out + base + t * tstride, o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float r = rnd<T>(o[j]);
+          st[0][j] += r;
+          st[1][j] += r * r;
+        }
+      }
+    } else {
+      float win[5][4];
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) win[k][j] = 0.f;
+      // preload t=0,1 into slots 3,4 (window covers t-2..t+2 for the *next* output)
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t < Tn) {
+          float v[4];
+          ldq(in + base + t * tstride, v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) win[3 + t][j] = silu_t<T>(fmaf(v[j], sc[j], sh[j]));
+        }
+      }
+      for (int t = 0; t < Tn; ++t) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) win[k][j] = win[k + 1][j];
+        if (t + 2 < Tn) {
+          float v[4];
+          ldq(in + base + (t + 2) * tstride, v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) win[4][j] = silu_t<T>(fmaf(v[j], sc[j], sh[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) win[4][j] = 0.f;
+        }
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = fmaf(win[k][j], wr[k][j], o[j]);
+        stq(out + base + t * tstride, o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float r = rnd<T>(o[j]);
+          st[0][j] += r;
+          st[1][j] += r * r;
+        }
+      }
+    }
+  }
+  if (partial)
+    block_reduce_channels<2, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 2 * C, C, blockIdx.y * cqc * 4);
+}
+
+extern "C" int dwn_tdw_fwd(const void* in, const float* coef, const float* wgt, void* out, float* partial, int P, int B,
+                           int Tn, int HW, int C, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DWN_REQUIRE(C % 4 == 0, "dwn_tdw_fwd: C %% 4 != 0");
+  int cqc = dwn_largest_divisor_le(C / 4, 128);
+  int ln = 256 / cqc;
+  if (ln < 1) ln = 1;
+  dim3 grid(P, (C / 4) / cqc), block(cqc * ln);
+  size_t sm = (size_t)block.x * 2 * 4 * sizeof(float);
+#define GO(TY, TTV) tdw_fwd_kernel<TY, TTV><<<grid, block, sm, st>>>((const TY*)in, coef, wgt, (TY*)out, partial, B, Tn, HW, C, cqc)
+  if (dtype == DWN_DT_F32) {
+    if (Tn == 16) GO(float, 16); else GO(float, 0);
+  } else {
+    if (Tn == 16) GO(bf16, 16); else GO(bf16, 0);
+  }
+#undef GO
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// SE squeeze: a = SiLU(BN3(Tm_raw)) is materialised (the A operand of the projection GEMM) and
+// pooled per (sample, channel).  partial[B][J][C]                        (dwiseneuro.py:38-39)
+// =================================================================================================
+template <typename T>
+__global__ void se_pool_kernel(const T* __restrict__ in, const float* __restrict__ coef, T* __restrict__ act,
+                               float* __restrict__ partial, int Nsp, int C, int cvc) {
+  constexpr int V = VecT<T>::V;
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const int cv = tid % cvc, lane = tid / cvc, ln = blockDim.x / cvc;
+  const int c = (blockIdx.y * cvc + cv) * V;
+  const int b = blockIdx.z;
+  float sc[V], sh[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { sc[j] = coef[c + j]; sh[j] = coef[C + c + j]; }
+  float st[1][V] = {};
+  const long base = (long)b * Nsp * C + c;
+  for (int r = blockIdx.x * ln + lane; r < Nsp; r += gridDim.x * ln) {
+    float v[V];
+    ldv(in + base + (long)r * C, v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = silu_t<T>(fmaf(v[j], sc[j], sh[j]));
+    stv(act + base + (long)r * C, v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) st[0][j] += rnd<T>(v[j]);
+  }
+  block_reduce_channels<1, V>(st, smem, cvc, ln, partial + ((long)b * gridDim.x + blockIdx.x) * C, C,
+                              blockIdx.y * cvc * V);
+}
+
+extern "C" int dwn_se_pool(const void* in, const float* coef, void* act, float* partial, int J, int B, int Nsp, int C,
+                           int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DWN_DT_F32) {
+    int cvc = dwn_largest_divisor_le(C / 4, 64), ln = 256 / cvc;
+    dim3 grid(J, (C / 4) / cvc, B), block(cvc * ln);
+    se_pool_kernel<float><<<grid, block, block.x * 4 * sizeof(float), st>>>((const float*)in, coef, (float*)act, partial,
+                                                                           Nsp, C, cvc);
+  } else {
+    DWN_REQUIRE(C % 8 == 0, "dwn_se_pool: C %% 8 != 0");
+    int cvc = dwn_largest_divisor_le(C / 8, 64), ln = 256 / cvc;
+    dim3 grid(J, (C / 8) / cvc, B), block(cvc * ln);
+    se_pool_kernel<bf16><<<grid, block, block.x * 8 * sizeof(float), st>>>((const bf16*)in, coef, (bf16*)act, partial,
+                                                                          Nsp, C, cvc);
+  }
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// SE excitation MLP, one CTA per sample (dwiseneuro.py:40-43): mean -> reduce(+b) -> SiLU -> expand(+b) -> sigmoid
+__global__ void se_mlp_kernel(const float* __restrict__ partial, int J, float inv_n, const float* __restrict__ w1,
+                              const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                              float* __restrict__ mean_out, float* __restrict__ hpre_out, float* __restrict__ gate_out,
+                              int C, int RD) {
+  extern __shared__ float sm[];  // mean[C], h[RD]
+  float* s_mean = sm;
+  float* s_h = sm + C;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < J; ++j) s += partial[((long)b * J + j) * C + c];
+    s *= inv_n;
+    s_mean[c] = s;
+    mean_out[(long)b * C + c] = s;
+  }
+  __syncthreads();
+  const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  for (int r = wid; r < RD; r += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(w1[(long)r * C + c], s_mean[c], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      s += b1[r];
+      hpre_out[(long)b * RD + r] = s;
+      s_h[r] = s / (1.0f + expf(-s));
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) {
+    float s = b2[c];
+    for (int r = 0; r < RD; ++r) s = fmaf(w2[(long)c * RD + r], s_h[r], s);
+    gate_out[(long)b * C + c] = 1.0f / (1.0f + expf(-s));
+  }
+}
+
+extern "C" int dwn_se_mlp(const float* partial, int J, int Nsp, const float* w1, const float* b1, const float* w2,
+                          const float* b2, float* mean_out, float* hpre_out, float* gate_out, int B, int C, int RD,
+                          void* stream) {
+  se_mlp_kernel<<<B, 256, (C + RD) * sizeof(float), (cudaStream_t)stream>>>(partial, J, 1.0f / (float)Nsp, w1, b1, w2, b2,
+                                                                            mean_out, hpre_out, gate_out, C, RD);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// fold the SE gate into per-sample projection weights: Wb[b][n][k] = W[n][k] * gate[b][k]
+template <typename T>
+__global__ void fold_gate_kernel(const float* __restrict__ w, const float* __restrict__ gate, T* __restrict__ out, long NK,
+                                 int K) {
+  const int b = blockIdx.y;
+  for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < NK; i += (long)gridDim.x * blockDim.x * 4) {
+    int k = (int)(i % K);
+    float wv[4], g[4], o[4];
+    ldq(w + i, wv);
+    ldq(gate + (long)b * K + k, g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = wv[j] * g[j];
+    stq(out + (long)b * NK + i, o);
+  }
+}
+
+extern "C" int dwn_fold_gate(const float* w, const float* gate, void* out, int B, int N, int K, int dtype, void* stream) {
+  DWN_REQUIRE(K % 4 == 0, "dwn_fold_gate: K %% 4 != 0");
+  long NK = (long)N * K;
+  int gx = (int)((NK / 4 + 255) / 256);
+  if (gx > 1024) gx = 1024;
+  dim3 grid(gx, B);
+  if (dtype == DWN_DT_F32)
+    fold_gate_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(w, gate, (float*)out, NK, K);
+  else
+    fold_gate_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(w, gate, (bf16*)out, NK, K);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// residual epilogue of an inverted-residual block (dwiseneuro.py:136-144, 125-134, 46-54):
+//   out = dp[b]*BN4(Y_raw) + BN_sc(shortcut[nearest-strided, channel-tiled]) (+ PE of the next block)
+// writes the fp32 trunk (+bf16 copy) and the partial stats of the next block's (strided) shortcut.
+// =================================================================================================
+template <typename T>
+__global__ void block_out_kernel(const T* __restrict__ y_raw, const float* __restrict__ coef4, const float* __restrict__ dp,
+                                 const float* __restrict__ xin, const float* __restrict__ coef_sc,
+                                 const float* __restrict__ pe_t, const float* __restrict__ pe_h,
+                                 const float* __restrict__ pe_w, float* __restrict__ out, bf16* __restrict__ out_bf,
+                                 float* __restrict__ partial, int next_stride, int B, int Tn, int Ho, int Wo, int Ci,
+                                 int Co, int stride, int cqc) {
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
+  const int c = (blockIdx.y * cqc + cq) * 4;
+  const int ci = c % Ci;  // cyclic channel tile (Ci % 4 == 0 so quads never straddle)
+  float s4[4], h4[4], ss[4], hs[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s4[j] = coef4[c + j];
+    h4[j] = coef4[Co + c + j];
+    ss[j] = coef_sc[c + j];
+    hs[j] = coef_sc[Co + c + j];
+  }
+  float st[2][4] = {};
+  const int Hi = Ho * stride, Wi = Wo * stride;
+  const long Mo = (long)B * Tn * Ho * Wo;
+  for (long m = (long)blockIdx.x * ln + lane; m < Mo; m += (long)gridDim.x * ln) {
+    int wq = (int)(m % Wo), hq = (int)((m / Wo) % Ho);
+    long bt = m / ((long)Wo * Ho);
+    int tq = (int)(bt % Tn), b = (int)(bt / Tn);
+    float y[4], x[4], o[4];
+    ldq(y_raw + m * Co + c, y);
+    ldq(xin + ((bt * Hi + (long)hq * stride) * Wi + (long)wq * stride) * Ci + ci, x);
+    const float d = dp ? dp[b] : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = d * fmaf(y[j], s4[j], h4[j]) + fmaf(x[j], ss[j], hs[j]);
+    if (pe_t) {
+      float pt[4], ph[4], pw[4];
+      ldq(pe_t + (long)tq * Co + c, pt);
+      ldq(pe_h + (long)hq * Co + c, ph);
+      ldq(pe_w + (long)wq * Co + c, pw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] += (pt[j] + ph[j]) + pw[j];
+    }
+    stq(out + m * Co + c, o);
+    if (out_bf) stq(out_bf + m * Co + c, o);
+    if (partial && (hq % next_stride == 0) && (wq % next_stride == 0)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { st[0][j] += o[j]; st[1][j] += o[j] * o[j]; }
+    }
+  }
+  if (partial)
+    block_reduce_channels<2, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 2 * Co, Co, blockIdx.y * cqc * 4);
+}
+
+extern "C" int dwn_block_out(const void* y_raw, const float* coef4, const float* dp, const float* xin,
+                             const float* coef_sc, const float* pe_t, const float* pe_h, const float* pe_w, float* out,
+                             void* out_bf, float* partial, int P, int next_stride, int B, int Tn, int Ho, int Wo, int Ci,
+                             int Co, int stride, int dtype, void* stream) {
+  DWN_REQUIRE(Ci % 4 == 0 && Co % 4 == 0, "dwn_block_out: channels must be multiples of 4");
+  int cqc = dwn_largest_divisor_le(Co / 4, 64), ln = 256 / cqc;
+  dim3 grid(P, (Co / 4) / cqc), block(cqc * ln);
+  size_t sm = (size_t)block.x * 8 * sizeof(float);
+  if (dtype == DWN_DT_F32)
+    block_out_kernel<float><<<grid, block, sm, (cudaStream_t)stream>>>((const float*)y_raw, coef4, dp, xin, coef_sc, pe_t,
+                                                                       pe_h, pe_w, out, (bf16*)out_bf, partial,
+                                                                       next_stride, B, Tn, Ho, Wo, Ci, Co, stride, cqc);
+  else
+    block_out_kernel<bf16><<<grid, block, sm, (cudaStream_t)stream>>>((const bf16*)y_raw, coef4, dp, xin, coef_sc, pe_t,
+                                                                      pe_h, pe_w, out, (bf16*)out_bf, partial,
+                                                                      next_stride, B, Tn, Ho, Wo, Ci, Co, stride, cqc);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// spatial average pool over (H,W) (dwiseneuro.py:374,400): [BT][HW][C] fp32 -> [BT][C] fp32 (+bf16)
+__global__ void pool_hw_kernel(const float* __restrict__ in, float* __restrict__ out, bf16* __restrict__ out_bf, int HW,
+                               int C) {
+  const long bt = blockIdx.x;
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < HW; ++i) {
+      float v[4];
+      ldq(in + (bt * HW + i) * C + c, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[j] += v[j];
+    }
+    const float inv = 1.0f / (float)HW;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] *= inv;
+    stq(out + bt * C + c, a);
+    if (out_bf) stq(out_bf + bt * C + c, a);
+  }
+}
+
+extern "C" int dwn_pool_hw(const float* in, float* out, void* out_bf, int BT, int HW, int C, void* stream) {
+  pool_hw_kernel<<<BT, 64, 0, (cudaStream_t)stream>>>(in, out, (bf16*)out_bf, HW, C);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// column statistics of a row-major [M][ld] matrix (first C columns): partial[J][2][C]
+// =================================================================================================
+template <typename T>
+__global__ void colstats_kernel(const T* __restrict__ x, long M, int ld, int C, float* __restrict__ partial, int cvc) {
+  constexpr int V = VecT<T>::V;
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const int cv = tid % cvc, lane = tid / cvc, ln = blockDim.x / cvc;
+  const int c = (blockIdx.y * cvc + cv) * V;
+  float st[2][V] = {};
+  for (long r = (long)blockIdx.x * ln + lane; r < M; r += (long)gridDim.x * ln) {
+    float v[V];
+    ldv(x + r * ld + c, v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) { st[0][j] += v[j]; st[1][j] += v[j] * v[j]; }
+  }
+  block_reduce_channels<2, V>(st, smem, cvc, ln, partial + (long)blockIdx.x * 2 * C, C, blockIdx.y * cvc * V);
+}
+
+extern "C" int dwn_colstats(const void* x, long M, int ld, int C, float* partial, int J, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DWN_DT_F32) {
+    DWN_REQUIRE(C % 4 == 0 && ld % 4 == 0, "dwn_colstats: C/ld %% 4 != 0");
+    int cvc = dwn_largest_divisor_le(C / 4, 64), ln = 256 / cvc;
+    dim3 grid(J, (C / 4) / cvc), block(cvc * ln);
+    colstats_kernel<float><<<grid, block, block.x * 8 * sizeof(float), st>>>((const float*)x, M, ld, C, partial, cvc);
+  } else {
+    DWN_REQUIRE(C % 8 == 0 && ld % 8 == 0, "dwn_colstats: C/ld %% 8 != 0");
+    int cvc = dwn_largest_divisor_le(C / 8, 64), ln = 256 / cvc;
+    dim3 grid(J, (C / 8) / cvc), block(cvc * ln);
+    colstats_kernel<bf16><<<grid, block, block.x * 16 * sizeof(float), st>>>((const bf16*)x, M, ld, C, partial, cvc);
+  }
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// cortex layer epilogue (dwiseneuro.py:195-234): BN+SiLU of the grouped conv output, channel
+// shuffle folded into the read index, drop-path, + BN_sc(cyclically tiled shortcut).
+//   out[m][j] = dp[b]*SiLU(BN(Y[m][src(j)])) + BN_sc(x[m][j mod I]),  src(j) = (j%g)*(O/g) + j/g
+// =================================================================================================
+template <typename T>
+__global__ void cortex_out_kernel(const T* __restrict__ y, const float* __restrict__ coef, const float* __restrict__ dp,
+                                  const float* __restrict__ xin, const float* __restrict__ coef_sc,
+                                  float* __restrict__ out, bf16* __restrict__ out_bf, int M, int Tn, int I, int O, int G) {
+  const int per = O / G;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)M * O; i += (long)gridDim.x * blockDim.x) {
+    int m = (int)(i / O), j = (int)(i % O);
+    int src = (j % G) * per + j / G;
+    float v = ld1<T>(y + (long)m * O + src);
+    v = silu_t<T>(fmaf(v, coef[src], coef[O + src]));
+    v = rnd<T>(v);
+    float d = dp ? dp[m / Tn] : 1.0f;
+    float s = fmaf(xin[(long)m * I + (j % I)], coef_sc[j], coef_sc[O + j]);
+    float o = d * v + s;
+    out[i] = o;
+    if (out_bf) out_bf[i] = __float2bfloat16_rn(o);
+  }
+}
+
+extern "C" int dwn_cortex_out(const void* y, const float* coef, const float* dp, const float* xin, const float* coef_sc,
+                              float* out, void* out_bf, int M, int Tn, int I, int O, int G, int dtype, void* stream) {
+  long n = (long)M * O;
+  int gx = (int)((n + 255) / 256);
+  if (gx > 2048) gx = 2048;
+  if (dtype == DWN_DT_F32)
+    cortex_out_kernel<float><<<gx, 256, 0, (cudaStream_t)stream>>>((const float*)y, coef, dp, xin, coef_sc, out,
+                                                                   (bf16*)out_bf, M, Tn, I, O, G);
+  else
+    cortex_out_kernel<bf16><<<gx, 256, 0, (cudaStream_t)stream>>>((const bf16*)y, coef, dp, xin, coef_sc, out,
+                                                                  (bf16*)out_bf, M, Tn, I, O, G);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// readout input: Dropout1d mask (per sample, per channel) applied to the cortex output and cast
+// to the GEMM operand type; optional transposed copy for the weight-gradient GEMM.
+//   xm[m][k] = x[m][k] * mask[b][k]      xt[k][m] = xm[m][k]              (dwiseneuro.py:276)
+// =================================================================================================
+template <typename T>
+__global__ void readout_prep_kernel(const float* __restrict__ x, const float* __restrict__ mask, T* __restrict__ xm,
+                                    T* __restrict__ xt, int M, int K, int Tn) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    int m = m0 + r, k = k0 + tx;
+    float v = 0.f;
+    if (m < M && k < K) {
+      v = x[(long)m * K + k];
+      if (mask) v *= mask[(long)(m / Tn) * K + k];
+      if (xm) st1<T>(xm + (long)m * K + k, v);
+    }
+    tile[r][tx] = v;
+  }
+  if (!xt) return;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int k = k0 + r, m = m0 + tx;
+    if (m < M && k < K) st1<T>(xt + (long)k * M + m, tile[tx][r]);
+  }
+}
+
+extern "C" int dwn_readout_prep(const float* x, const float* mask, void* xm, void* xt, int M, int K, int Tn, int dtype,
+                                void* stream) {
+  dim3 grid((K + 31) / 32, (M + 31) / 32), block(32, 8);
+  if (dtype == DWN_DT_F32)
+    readout_prep_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(x, mask, (float*)xm, (float*)xt, M, K, Tn);
+  else
+    readout_prep_kernel<bf16><<<grid, block, 0, (cudaStream_t)stream>>>(x, mask, (bf16*)xm, (bf16*)xt, M, K, Tn);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// fp32 -> storage type cast (weight shadows), n % 4 == 0 not required
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    st1<T>(out + i, in[i]);
+}
+extern "C" int dwn_cast_bf16(const float* in, void* out, long n, void* stream) {
+  int gx = (int)((n + 255) / 256);
+  if (gx > 4096) gx = 4096;
+  if (gx < 1) gx = 1;
+  cast_kernel<bf16><<<gx, 256, 0, (cudaStream_t)stream>>>(in, (bf16*)out, n);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}

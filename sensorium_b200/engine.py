@@ -1,0 +1,297 @@
+"""Kernel orchestration for DwiseNeuro on B200: forward / backward plans over libdwn_b200.so.
+
+Data layout: every activation is channels-last ``[B][T][H][W][C]`` == row-major ``[M][C]``.
+ * trunk (block inputs/outputs) is fp32 (+ a bf16 copy used as tcgen05 A operand in bf16 mode) — this
+   mirrors the autocast dtype map of the reference (the residual trunk is fp32);
+ * branch intermediates E_raw / S_raw / Tm_raw (pre-BatchNorm conv outputs) are stored in the pipeline
+   dtype (bf16 or fp32); BatchNorm + SiLU are applied by the *consumer* on load, batch statistics are
+   produced by the *producer* as deterministic per-CTA partial sums and finalised by a tiny kernel.
+
+Reference call graph: DwiseNeuro.forward (/root/reference/src/models/dwiseneuro.py:397-405).
+"""
+from __future__ import annotations
+
+import math
+import weakref
+from types import SimpleNamespace
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, gemm
+
+F32, BF16 = 0, 1
+BN_MOM, BN_EPS = 0.1, 1e-5
+_P = 592          # partial-stat rows for kernels whose grid.y may be 1 (4 CTAs / SM)
+_P_SDW = 148      # spatial dw kernels have >= 3 channel chunks in grid.y
+_P_MOM = 296
+_J_SE = 16
+
+_plans = weakref.WeakKeyDictionary()
+_shadows = weakref.WeakKeyDictionary()
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _empty(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+def pe_tables(pe_mod, C: int, T: int, H: int, W: int, dev):
+    """Separable lookup tables of PositionalEncoding3d (dwiseneuro.py:147-182).
+
+    PE[c,t,h,w] = pe_t[t][c] + pe_h[h][c] + pe_w[w][c] where exactly one term is non-zero: channels
+    [0,ch) encode T, [ch,2ch) encode H, [2ch,3ch) encode W (truncated to C); inside an axis run the first
+    half is sin(pos*f_k), the second half cos(pos*f_k)."""
+    cache = _plans.setdefault(pe_mod, {})
+    key = (C, T, H, W, str(dev))
+    if key in cache:
+        return cache[key]
+    inv_freq = pe_mod.inv_freq.to(device=dev, dtype=torch.float32)
+    ch = pe_mod.channels
+    tabs = []
+    for axis, n in enumerate((T, H, W)):
+        pos = torch.arange(n, device=dev).type(inv_freq.type())
+        ang = torch.einsum("i,j->ij", inv_freq, pos)           # (ch/2, n)
+        emb = torch.cat((ang.sin(), ang.cos()), dim=0)         # (ch, n)
+        tab = torch.zeros(n, 3 * ch, dtype=torch.float32, device=dev)
+        tab[:, axis * ch:(axis + 1) * ch] = emb.t()
+        tabs.append(tab[:, :C].contiguous())
+    cache[key] = tuple(tabs)
+    return cache[key]
+
+
+def _shadow(p: torch.Tensor) -> torch.Tensor:
+    """bf16 shadow of an fp32 GEMM weight, refreshed when the parameter version changes."""
+    ent = _shadows.get(p)
+    if ent is not None and ent[0] == p._version and ent[1].device == p.device and ent[2] == p.data_ptr():
+        return ent[1]
+    sh = torch.empty(p.shape, dtype=torch.bfloat16, device=p.device)
+    call("dwn_cast_bf16", p.detach(), sh, p.numel(), _stream(p.device))
+    _shadows[p] = (p._version, sh, p.data_ptr())
+    return sh
+
+
+def set_shadow(p: torch.Tensor, sh: torch.Tensor) -> None:
+    """Used by the fused optimizer, which writes the bf16 shadow itself."""
+    _shadows[p] = (p._version, sh, p.data_ptr())
+
+
+def _bn_coef(bn, partial, P, count, C, Cp, training, st, dev):
+    coef = _empty((4, C), torch.float32, dev)
+    if training:
+        call("dwn_bn_finalize", partial, P, float(count), bn.weight, bn.bias, bn.running_mean, bn.running_var,
+             bn.num_batches_tracked, BN_MOM, BN_EPS, 1, coef, C, Cp, st)
+    else:
+        call("dwn_bn_finalize", None, 0, 1.0, bn.weight, bn.bias, bn.running_mean, bn.running_var, None,
+             BN_MOM, BN_EPS, 0, coef, C, 0, st)
+    return coef
+
+
+def _colstats(x, M, ld, C, dcode, st, dev):
+    part = _empty((_P, 2, C), torch.float32, dev)
+    call("dwn_colstats", x, M, ld, C, part, _P, dcode, st)
+    return part
+
+
+def _drop_mask(shape, keep, dtype, dev):
+    # same torch calls (shape, dtype, order) as drop_path (dwiseneuro.py:46-54) so RNG streams agree
+    m = torch.empty(shape, dtype=dtype, device=dev).bernoulli_(keep)
+    if keep > 0.0:
+        m.div_(keep)
+    return m.float().reshape(shape[0]).contiguous()
+
+
+def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training: bool, save: bool):
+    """Returns (list of predictions [B, n_m, T] fp32, saved-state or None)."""
+    cfg = mod.cfg
+    dev = x.device
+    st = _stream(dev)
+    bf = mode == "bf16"
+    adt = torch.bfloat16 if bf else torch.float32
+    dcode = BF16 if bf else F32
+    x = x.detach().contiguous().float()
+    B, Cin, T, H, W = x.shape
+    feats = cfg["core_features"]
+    strides = cfg["spatial_strides"]
+    nb = len(feats)
+    er = cfg["expansion_ratio"]
+    G = cfg["groups"]
+    if cfg["spatial_kernel"] != 3 or cfg["temporal_kernel"] != 5:
+        raise NotImplementedError("sensorium_b200 kernels are specialised for spatial_kernel=3, temporal_kernel=5")
+    sv = SimpleNamespace(blocks=[], cortex=[], readouts=[], mode=mode, B=B, T=T, H=H, W=W, x=x) if save else None
+
+    # ---------------- stem (dwiseneuro.py:306-309) + PE of block 0 -------------------------------
+    stem_conv, stem_bn = mod.core.stem[0], mod.core.stem[1].bn
+    C0 = feats[0]
+    M0 = B * T * H * W
+    coef0 = _empty((4, C0), torch.float32, dev)
+    mom = None
+    if training:
+        nm = Cin + Cin * (Cin + 1) // 2
+        momp = _empty((_P_MOM, nm), torch.float64, dev)
+        mom = _empty((nm,), torch.float64, dev)
+        call("dwn_input_moments", x, B, Cin, T * H * W, momp, _P_MOM, mom, st)
+        call("dwn_stem_coef", mom, Cin, float(M0), stem_conv.weight, stem_bn.weight, stem_bn.bias,
+             stem_bn.running_mean, stem_bn.running_var, stem_bn.num_batches_tracked, BN_MOM, BN_EPS, coef0, C0, st)
+    else:
+        call("dwn_bn_finalize", None, 0, 1.0, stem_bn.weight, stem_bn.bias, stem_bn.running_mean,
+             stem_bn.running_var, None, BN_MOM, BN_EPS, 0, coef0, C0, 0, st)
+    pe = pe_tables(mod.core.blocks[0], C0, T, H, W, dev)
+    X = _empty((M0, C0), torch.float32, dev)
+    Xb = _empty((M0, C0), torch.bfloat16, dev) if bf else None
+    sc_part = _empty((_P, 2, C0), torch.float32, dev) if training else None
+    if H % strides[0] or W % strides[0]:
+        raise NotImplementedError("spatial size must be divisible by the block stride")
+    call("dwn_stem_fwd", x, stem_conv.weight, coef0, pe[0], pe[1], pe[2], X, Xb, sc_part, _P, strides[0], B, Cin, T, H,
+         W, C0, st)
+    if save:
+        sv.stem = SimpleNamespace(coef=coef0, mom=mom)
+
+    # ---------------- inverted-residual blocks (dwiseneuro.py:136-144) ---------------------------
+    Hi, Wi = H, W
+    for i in range(nb):
+        blk = mod.core.blocks[2 * i + 1]
+        ci = feats[i]
+        co = feats[i + 1] if i < nb - 1 else feats[-1]
+        s = strides[i]
+        mid = ci * er
+        if Hi % s or Wi % s:
+            raise NotImplementedError("spatial size must be divisible by the block stride")
+        Ho, Wo = Hi // s, Wi // s
+        Mi, Mo, Nsp = B * T * Hi * Wi, B * T * Ho * Wo, T * Ho * Wo
+        # 1. point-wise expansion (tcgen05 GEMM / SIMT fp32)
+        wpw = blk.conv_pw[0].weight
+        E = _empty((Mi, mid), adt, dev)
+        gemm(st, dtype=dcode, A=Xb if bf else X, B=_shadow(wpw) if bf else wpw, lda=ci, ldb=ci, M=Mi, N=mid, K=ci, Z=1,
+             D=E, d_dtype=dcode, ldd=mid)
+        coef1 = _bn_coef(blk.conv_pw[1].bn, _colstats(E, Mi, mid, mid, dcode, st, dev) if training else None, _P, Mi,
+                         mid, 0, training, st, dev)
+        # 2. spatial depth-wise (BN1+SiLU on load)
+        S = _empty((Mo, mid), adt, dev)
+        part = _empty((_P, 2, mid), torch.float32, dev) if training else None
+        call("dwn_sdw_fwd", E, coef1, blk.spat_covn_dw[0].weight, S, part, _P_SDW, B * T, Hi, Wi, mid, s, dcode, st)
+        coef2 = _bn_coef(blk.spat_covn_dw[1].bn, part, _P_SDW, Mo, mid, 0, training, st, dev)
+        # 3. temporal depth-wise (BN2+SiLU on load)
+        Tm = _empty((Mo, mid), adt, dev)
+        part = _empty((_P, 2, mid), torch.float32, dev) if training else None
+        call("dwn_tdw_fwd", S, coef2, blk.temp_covn_dw[0].weight, Tm, part, _P, B, T, Ho * Wo, mid, dcode, st)
+        coef3 = _bn_coef(blk.temp_covn_dw[1].bn, part, _P, Mo, mid, 0, training, st, dev)
+        # 4. squeeze-excite: a = SiLU(BN3(Tm)), gate folded into per-sample projection weights
+        A = _empty((Mo, mid), adt, dev)
+        rd = blk.se.conv_reduce.weight.shape[0]
+        pool_part = _empty((B, _J_SE, mid), torch.float32, dev)
+        call("dwn_se_pool", Tm, coef3, A, pool_part, _J_SE, B, Nsp, mid, dcode, st)
+        mean = _empty((B, mid), torch.float32, dev)
+        hpre = _empty((B, rd), torch.float32, dev)
+        gate = _empty((B, mid), torch.float32, dev)
+        call("dwn_se_mlp", pool_part, _J_SE, Nsp, blk.se.conv_reduce.weight, blk.se.conv_reduce.bias,
+             blk.se.conv_expand.weight, blk.se.conv_expand.bias, mean, hpre, gate, B, mid, rd, st)
+        Wb = _empty((B, co, mid), adt, dev)
+        call("dwn_fold_gate", blk.conv_pwl[0].weight, gate, Wb, B, co, mid, dcode, st)
+        # 5. point-wise linear projection, batched over samples (B operand = gated weights of the sample)
+        Y = _empty((Mo, co), adt, dev)
+        gemm(st, dtype=dcode, A=A, B=Wb, lda=mid, ldb=mid, a_zstride=Nsp * mid, b_zstride=co * mid, a_zmode=1,
+             b_zmode=1, M=Nsp, N=co, K=mid, Z=B, D=Y, d_dtype=dcode, ldd=co, d_zstride=Nsp * co)
+        coef4 = _bn_coef(blk.conv_pwl[1].bn, _colstats(Y, Mo, co, co, dcode, st, dev) if training else None, _P, Mo, co,
+                         0, training, st, dev)
+        coef_sc = _bn_coef(blk.bn_sc.bn, sc_part, _P, Mo, co, ci, training, st, dev)
+        # 6. residual epilogue (+ drop-path, + PE of the next block, + stats of the next shortcut)
+        dp = None
+        if training and blk.drop_path_rate > 0.0:
+            dp = _drop_mask((B, 1, 1, 1, 1), 1.0 - blk.drop_path_rate, adt, dev)
+        last = i == nb - 1
+        pe = (None, None, None) if last else pe_tables(mod.core.blocks[2 * i + 2], co, T, Ho, Wo, dev)
+        Xn = _empty((Mo, co), torch.float32, dev)
+        Xnb = _empty((Mo, co), torch.bfloat16, dev) if (bf and not last) else None
+        nsc_part = _empty((_P, 2, co), torch.float32, dev) if (training and not last) else None
+        call("dwn_block_out", Y, coef4, dp, X, coef_sc, pe[0], pe[1], pe[2], Xn, Xnb, nsc_part, _P,
+             1 if last else strides[i + 1], B, T, Ho, Wo, ci, co, s, dcode, st)
+        if save:
+            sv.blocks.append(SimpleNamespace(X=X, Xb=Xb, E=E, S=S, Tm=Tm, A=A, Y=Y, Wb=Wb, coef1=coef1, coef2=coef2,
+                                             coef3=coef3, coef4=coef4, coef_sc=coef_sc, gate=gate, hpre=hpre,
+                                             mean=mean, dp=dp, ci=ci, co=co, mid=mid, s=s, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo,
+                                             rd=rd))
+        X, Xb, sc_part, Hi, Wi = Xn, Xnb, nsc_part, Ho, Wo
+
+    # ---------------- pool (dwiseneuro.py:374,400) -----------------------------------------------
+    Mbt = B * T
+    CL = feats[-1]
+    cx = _empty((Mbt, CL), torch.float32, dev)
+    cxb = _empty((Mbt, CL), torch.bfloat16, dev) if bf else None
+    call("dwn_pool_hw", X, cx, cxb, Mbt, Hi * Wi, CL, st)
+    if save:
+        sv.pool = SimpleNamespace(HW=Hi * Wi, C=CL)
+
+    # ---------------- cortex (dwiseneuro.py:195-263) ---------------------------------------------
+    for layer in mod.cortex.layers:
+        I, O = layer.in_features, layer.out_features
+        wc = layer.conv.weight
+        Yc = _empty((Mbt, O), adt, dev)
+        gemm(st, dtype=dcode, A=cxb if bf else cx, B=_shadow(wc) if bf else wc, lda=I, ldb=I // G, a_zstride=I // G,
+             b_zstride=(O // G) * (I // G), a_zmode=1, b_zmode=1, M=Mbt, N=O // G, K=I // G, Z=G, D=Yc, d_dtype=dcode,
+             ldd=O, d_zstride=O // G)
+        coef = _bn_coef(layer.bn.bn, _colstats(Yc, Mbt, O, O, dcode, st, dev) if training else None, _P, Mbt, O, 0,
+                        training, st, dev)
+        coef_sc = _bn_coef(layer.bn_sc.bn, _colstats(cx, Mbt, I, I, F32, st, dev) if training else None, _P, Mbt, O, I,
+                           training, st, dev)
+        dp = None
+        if training and layer.drop_path_rate > 0.0:
+            dp = _drop_mask((B, 1, 1), 1.0 - layer.drop_path_rate, adt, dev)
+        out = _empty((Mbt, O), torch.float32, dev)
+        outb = _empty((Mbt, O), torch.bfloat16, dev) if bf else None
+        call("dwn_cortex_out", Yc, coef, dp, cx, coef_sc, out, outb, Mbt, T, I, O, G, dcode, st)
+        if save:
+            sv.cortex.append(SimpleNamespace(x=cx, xb=cxb, Y=Yc, coef=coef, coef_sc=coef_sc, dp=dp, I=I, O=O))
+        cx, cxb = out, outb
+
+    # ---------------- readouts (dwiseneuro.py:266-287) -------------------------------------------
+    K = cfg["cortex_features"][-1]
+    Kg = K // G
+    outs = cfg["readout_outputs"]
+    mice = range(len(outs)) if index is None else [index]
+    preds: List[torch.Tensor] = []
+    p_drop = cfg["drop_rate"]
+    for m in mice:
+        n_out = outs[m]
+        half = math.ceil(n_out / G)
+        conv = mod.readouts[m].layer[1]
+        mask = None
+        if training and p_drop > 0.0:
+            mask = torch.empty((B, K, 1), dtype=torch.float32, device=dev).bernoulli_(1.0 - p_drop).div_(1.0 - p_drop)
+        if mask is None and not save:
+            xm, xt = (cxb if bf else cx), None
+        else:
+            xm = _empty((Mbt, K), adt, dev)
+            xt = _empty((K, Mbt), adt, dev) if save else None
+            call("dwn_readout_prep", cx, mask, xm, xt, Mbt, K, T, dcode, st)
+        pred = _empty((B, n_out, T), torch.float32, dev)
+        wr = conv.weight
+        gemm(st, dtype=dcode, A=_shadow(wr) if bf else wr, B=xm, lda=Kg, ldb=K, a_zstride=half * Kg, b_zstride=Kg,
+             a_zmode=1, b_zmode=1, M=half, N=Mbt, K=Kg, Z=G, epi=1, D=pred, bias=conv.bias, beta=cfg["softplus_beta"],
+             Tn=T, n_out_total=n_out, row_offset_per_z=half, n_limit=Mbt)
+        preds.append(pred)
+        if save:
+            sv.readouts.append(SimpleNamespace(m=m, mask=mask, xm=xm, xt=xt, pred=pred, n_out=n_out, half=half))
+    if save:
+        sv.cx = cx
+        sv.index = index
+    return preds, sv
+
+
+def forward(mod, x: torch.Tensor, index: Optional[int]):
+    mode = mod._mode()
+    training = mod.training
+    params = [p for p in mod.parameters()]
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    if need_grad:
+        from .autograd import DwiseNeuroFn
+        outs = DwiseNeuroFn.apply(mod, index, mode, x, *params)
+        outs = list(outs)
+    else:
+        with torch.no_grad():
+            outs, _ = run_forward(mod, x, index, mode, training, save=False)
+    return outs if index is None else outs[0]
