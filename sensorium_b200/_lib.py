@@ -44,6 +44,37 @@ SIGNATURES = {
     "dwn_cortex_out": "ppppppp" + "iiiiii" + "p",
     "dwn_readout_prep": "pppp" + "iiii" + "p",
     "dwn_cast_bf16": "pplp",
+    # backward
+    "dwn_bn_bwd_finalize": "piiidpppip",
+    "dwn_block_bwd_reduce": "ppppppp" + "iiiiiiiii" + "p",
+    "dwn_block_bwd_dy": "pppppp" + "llii" + "p",
+    "dwn_block_in_bwd": "pppppp" + "iiiiiii" + "p",
+    "dwn_pool_bwd": "pp" + "lii" + "p",
+    "dwn_se_bwd": "ppppppp" + "pppppppp" + "iiii" + "p",
+    "dwn_tdw_bwd_reduce": "pppp" + "i" + "p" + "i" + "l" + "ii" + "p",
+    "dwn_tdw_bwd": "pppppppp" + "iiiiii" + "p",
+    "dwn_sdw_bwd": "ppppppppp" + "iiiiiii" + "p",
+    "dwn_bn_bwd_apply": "pppp" + "lii" + "p",
+    "dwn_reduce_rows": "pilpp",
+    "dwn_dw_wgrad_finalize": "piiiipip",
+    "dwn_stem_bwd": "ppp" + "i" + "pppppp" + "iili" + "p",
+    "dwn_cortex_bwd_reduce": "ppppppp" + "iiiiiii" + "p",
+    "dwn_cortex_bwd_dy": "pppppp" + "iiiii" + "p",
+    "dwn_cortex_in_bwd": "pppppp" + "iii" + "p",
+    # head / loss / distillation / predictor
+    "dwn_poisson_fwd": "ppp" + "iil" + "f" + "p" + "i" + "p",
+    "dwn_poisson_bwd": "pppi" + "p" + "il" + "f" + "pp",
+    "dwn_readout_bwd_prep": "pp" + "f" + "ppp" + "iiiiiii" + "p",
+    "dwn_readout_dx_combine": "pp" + "i" + "p" + "iii" + "p",
+    "dwn_distill_prepare": "pifppp",
+    "dwn_distill_fill": "ppp" + "iii" + "l" + "p",
+    "dwn_distill_weights": "pppip",
+    "dwn_window_blend": "ppp" + "iiiiii" + "l" + "p",
+    "dwn_window_gather": "pp" + "ii" + "l" + "iiii" + "p",
+    # optimizer / EMA
+    "dwn_adamw": "ppp" + "i" + "pp" + "i" + "ffffff" + "p",
+    "dwn_ema": "ppp" + "i" + "f" + "p",
+    "dwn_scale": "plfp",
 }
 
 

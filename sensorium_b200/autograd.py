@@ -10,6 +10,7 @@ class DwiseNeuroFn(torch.autograd.Function):
     def forward(ctx, mod, index, mode, x, *params):
         from . import engine
         outs, saved = engine.run_forward(mod, x, index, mode, mod.training, save=True)
+        ctx.set_materialize_grads(False)
         ctx.mod = mod
         ctx.saved = saved
         ctx.n_params = len(params)

@@ -1,0 +1,919 @@
+// Backward kernels of the DwiseNeuro core and cortex (channels-last).  Formulas: SURVEY.md §7.4.
+//   BN (train):  dx = gamma*rstd*(dy - c1 - xhat*c2),  c1 = sum(dy)/N, c2 = sum(dy*xhat)/N
+//   SiLU:        s'(u) = sig(u)*(1 + u*(1 - sig(u)))
+// Every kernel that feeds a BatchNorm backward also emits the deterministic per-CTA partial sums
+// (sum dy, sum dy*xhat) of the *next* BN in the chain, so each tensor is read once per stage.
+#include "dwn_common.cuh"
+#include "dwn_reduce.cuh"
+
+// =================================================================================================
+// BN backward finalize: partial[P][NQ][C] (quantities q0, q0+1 = sum dy, sum dy*xhat)
+//   -> dgamma, dbeta (parameter gradients) and bcoef[2][C] = sums / N
+// =================================================================================================
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int P, int NQ, int q0, double count,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ bcoef, int C) {
+  __shared__ double s0[8][32], s1[8][32];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double a = 0, b = 0;
+  if (c < C)
+    for (int p = sl; p < P; p += 8) {
+      a += (double)partial[((long)p * NQ + q0) * C + c];
+      b += (double)partial[((long)p * NQ + q0 + 1) * C + c];
+    }
+  s0[sl][cl] = a;
+  s1[sl][cl] = b;
+  __syncthreads();
+  if (sl != 0 || c >= C) return;
+  a = 0; b = 0;
+  for (int i = 0; i < 8; ++i) { a += s0[i][cl]; b += s1[i][cl]; }
+  if (dbeta) dbeta[c] = (float)a;
+  if (dgamma) dgamma[c] = (float)b;
+  bcoef[c] = (float)(a / count);
+  bcoef[C + c] = (float)(b / count);
+}
+
+extern "C" int dwn_bn_bwd_finalize(const float* partial, int P, int NQ, int q0, double count, float* dgamma,
+                                   float* dbeta, float* bcoef, int C, void* stream) {
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partial, P, NQ, q0, count, dgamma, dbeta, bcoef,
+                                                                          C);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// residual epilogue backward, pass 1 (reductions)          (forward: dwn_block_out)
+//   partial[P][4][Co] = { sum dp*dO, sum dp*dO*yhat4, sum dO, sum dO*xhat_sc }
+// =================================================================================================
+template <typename T>
+__global__ void block_bwd_reduce_kernel(const float* __restrict__ dO, const T* __restrict__ y_raw,
+                                        const float* __restrict__ coef4, const float* __restrict__ dp,
+                                        const float* __restrict__ xin, const float* __restrict__ coef_sc,
+                                        float* __restrict__ partial, int B, int Tn, int Ho, int Wo, int Ci, int Co,
+                                        int stride, int cqc) {
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
+  const int c = (blockIdx.y * cqc + cq) * 4;
+  const int ci = c % Ci;
+  float m4[4], r4[4], ms[4], rs[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m4[j] = coef4[2 * Co + c + j];
+    r4[j] = coef4[3 * Co + c + j];
+    ms[j] = coef_sc[2 * Co + c + j];
+    rs[j] = coef_sc[3 * Co + c + j];
+  }
+  float st[4][4] = {};
+  const int Hi = Ho * stride, Wi = Wo * stride;
+  const long Mo = (long)B * Tn * Ho * Wo;
+  for (long m = (long)blockIdx.x * ln + lane; m < Mo; m += (long)gridDim.x * ln) {
+    int wq = (int)(m % Wo), hq = (int)((m / Wo) % Ho);
+    long bt = m / ((long)Wo * Ho);
+    int b = (int)(bt / Tn);
+    float g[4], y[4], x[4];
+    ldq(dO + m * Co + c, g);
+    ldq(y_raw + m * Co + c, y);
+    ldq(xin + ((bt * Hi + (long)hq * stride) * Wi + (long)wq * stride) * Ci + ci, x);
+    const float d = dp ? dp[b] : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d4 = d * g[j];
+      st[0][j] += d4;
+      st[1][j] += d4 * ((y[j] - m4[j]) * r4[j]);
+      st[2][j] += g[j];
+      st[3][j] += g[j] * ((x[j] - ms[j]) * rs[j]);
+    }
+  }
+  block_reduce_channels<4, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 4 * Co, Co, blockIdx.y * cqc * 4);
+}
+
+extern "C" int dwn_block_bwd_reduce(const float* dO, const void* y_raw, const float* coef4, const float* dp,
+                                    const float* xin, const float* coef_sc, float* partial, int P, int B, int Tn, int Ho,
+                                    int Wo, int Ci, int Co, int stride, int dtype, void* stream) {
+  int cqc = dwn_largest_divisor_le(Co / 4, 64), ln = 256 / cqc;
+  dim3 grid(P, (Co / 4) / cqc), block(cqc * ln);
+  size_t sm = (size_t)block.x * 16 * sizeof(float);
+  if (dtype == DWN_DT_F32)
+    block_bwd_reduce_kernel<float><<<grid, block, sm, (cudaStream_t)stream>>>(dO, (const float*)y_raw, coef4, dp, xin,
+                                                                              coef_sc, partial, B, Tn, Ho, Wo, Ci, Co,
+                                                                              stride, cqc);
+  else
+    block_bwd_reduce_kernel<bf16><<<grid, block, sm, (cudaStream_t)stream>>>(dO, (const bf16*)y_raw, coef4, dp, xin,
+                                                                             coef_sc, partial, B, Tn, Ho, Wo, Ci, Co,
+                                                                             stride, cqc);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// pass 2: dY_raw = gamma4*rstd4*(dp*dO - c1 - yhat*c2)   (A operand of the pwl dgrad / wgrad GEMMs)
+template <typename T>
+__global__ void block_bwd_dy_kernel(const float* __restrict__ dO, const T* __restrict__ y_raw,
+                                    const float* __restrict__ coef4, const float* __restrict__ bcoef4,
+                                    const float* __restrict__ dp, T* __restrict__ dY, long Mo, long rows_per_b, int Co) {
+  const int cq4 = Co / 4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < Mo * cq4; i += (long)gridDim.x * blockDim.x) {
+    const long m = i / cq4;
+    const int c = (int)(i % cq4) * 4;
+    float g[4], y[4], o[4];
+    ldq(dO + m * Co + c, g);
+    ldq(y_raw + m * Co + c, y);
+    const float d = dp ? dp[m / rows_per_b] : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float yh = (y[j] - coef4[2 * Co + c + j]) * coef4[3 * Co + c + j];
+      o[j] = coef4[c + j] * (d * g[j] - bcoef4[c + j] - yh * bcoef4[Co + c + j]);
+    }
+    stq(dY + m * Co + c, o);
+  }
+}
+
+extern "C" int dwn_block_bwd_dy(const float* dO, const void* y_raw, const float* coef4, const float* bcoef4,
+                                const float* dp, void* dY, long Mo, long rows_per_b, int Co, int dtype, void* stream) {
+  long n = Mo * (Co / 4);
+  int gx = (int)((n + 255) / 256);
+  if (gx > 148 * 8) gx = 148 * 8;
+  if (dtype == DWN_DT_F32)
+    block_bwd_dy_kernel<float><<<gx, 256, 0, (cudaStream_t)stream>>>(dO, (const float*)y_raw, coef4, bcoef4, dp,
+                                                                     (float*)dY, Mo, rows_per_b, Co);
+  else
+    block_bwd_dy_kernel<bf16><<<gx, 256, 0, (cudaStream_t)stream>>>(dO, (const bf16*)y_raw, coef4, bcoef4, dp, (bf16*)dY,
+                                                                    Mo, rows_per_b, Co);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// gradient w.r.t. the block input: point-wise dgrad + shortcut path (nearest scatter, cyclic-tile sum, BN_sc bwd)
+__global__ void block_in_bwd_kernel(const float* __restrict__ dXpw, const float* __restrict__ dO,
+                                    const float* __restrict__ xin, const float* __restrict__ coef_sc,
+                                    const float* __restrict__ bcoef_sc, float* __restrict__ dXin, int B, int Tn, int Hi,
+                                    int Wi, int Ci, int Co, int stride) {
+  const int cq4 = Ci / 4;
+  const long Mi = (long)B * Tn * Hi * Wi;
+  const int Ho = Hi / stride, Wo = Wi / stride;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < Mi * cq4; i += (long)gridDim.x * blockDim.x) {
+    const long m = i / cq4;
+    const int c = (int)(i % cq4) * 4;
+    float o[4];
+    ldq(dXpw + m * Ci + c, o);
+    const int wq = (int)(m % Wi), hq = (int)((m / Wi) % Hi);
+    if ((hq % stride) == 0 && (wq % stride) == 0) {
+      const long bt = m / ((long)Wi * Hi);
+      const long mo = (bt * Ho + hq / stride) * Wo + wq / stride;
+      float x[4];
+      ldq(xin + m * Ci + c, x);
+      for (int cc = c; cc < Co; cc += Ci) {
+        float g[4];
+        ldq(dO + mo * Co + cc, g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xh = (x[j] - coef_sc[2 * Co + cc + j]) * coef_sc[3 * Co + cc + j];
+          o[j] += coef_sc[cc + j] * (g[j] - bcoef_sc[cc + j] - xh * bcoef_sc[Co + cc + j]);
+        }
+      }
+    }
+    stq(dXin + m * Ci + c, o);
+  }
+}
+
+extern "C" int dwn_block_in_bwd(const float* dXpw, const float* dO, const float* xin, const float* coef_sc,
+                                const float* bcoef_sc, float* dXin, int B, int Tn, int Hi, int Wi, int Ci, int Co,
+                                int stride, void* stream) {
+  long n = (long)B * Tn * Hi * Wi * (Ci / 4);
+  int gx = (int)((n + 255) / 256);
+  if (gx > 148 * 8) gx = 148 * 8;
+  block_in_bwd_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(dXpw, dO, xin, coef_sc, bcoef_sc, dXin, B, Tn, Hi, Wi, Ci, Co,
+                                                            stride);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// pool backward: dX[bt][hw][c] = dP[bt][c] / HW
+__global__ void pool_bwd_kernel(const float* __restrict__ dP, float* __restrict__ dX, long BT, int HW, int C) {
+  const int cq4 = C / 4;
+  const float inv = 1.0f / (float)HW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < BT * HW * cq4; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cq4) * 4;
+    const long bt = i / ((long)cq4 * HW);
+    float g[4];
+    ldq(dP + bt * C + c, g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[j] *= inv;
+    stq(dX + (i / cq4) * C + c, g);
+  }
+}
+extern "C" int dwn_pool_bwd(const float* dP, float* dX, long BT, int HW, int C, void* stream) {
+  long n = BT * HW * (C / 4);
+  int gx = (int)((n + 255) / 256);
+  if (gx > 148 * 8) gx = 148 * 8;
+  pool_bwd_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(dP, dX, BT, HW, C);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// squeeze-excite backward (dwiseneuro.py:38-43).  Pp[b][k][n] = sum_{m in b} a[m][k]*dY[m][n] comes from
+// the per-sample wgrad GEMM; it yields both dW_pwl and the gate gradient (u = a*g, Y = u W^T):
+//   dg[b][k] = sum_n W[n][k]*Pp[b][k][n],   dW[n][k] = sum_b g[b][k]*Pp[b][k][n]
+// =================================================================================================
+__global__ void se_bwd_a_kernel(const float* __restrict__ Pp, const float* __restrict__ wpwl,
+                                const float* __restrict__ gate, const float* __restrict__ hpre,
+                                const float* __restrict__ w1, const float* __restrict__ w2,
+                                float* __restrict__ dpre2, float* __restrict__ dhpre, float* __restrict__ dmean, int C,
+                                int Co, int RD) {
+  extern __shared__ float sm[];  // dpre2[C], dhp[RD]
+  float* s_dp2 = sm;
+  float* s_dhp = sm + C;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* P = Pp + (long)b * C * Co;
+  for (int k = tid; k < C; k += blockDim.x) {
+    float s = 0.f;
+    for (int n = 0; n < Co; ++n) s = fmaf(wpwl[(long)n * C + k], P[(long)k * Co + n], s);
+    const float g = gate[(long)b * C + k];
+    const float d = s * g * (1.0f - g);
+    s_dp2[k] = d;
+    dpre2[(long)b * C + k] = d;
+  }
+  __syncthreads();
+  const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  for (int r = wid; r < RD; r += nw) {
+    float s = 0.f;
+    for (int k = lane; k < C; k += 32) s = fmaf(s_dp2[k], w2[(long)k * RD + r], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float u = hpre[(long)b * RD + r];
+      const float sg = 1.0f / (1.0f + expf(-u));
+      const float d = s * sg * (1.0f + u * (1.0f - sg));
+      s_dhp[r] = d;
+      dhpre[(long)b * RD + r] = d;
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < C; k += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < RD; ++r) s = fmaf(s_dhp[r], w1[(long)r * C + k], s);
+    dmean[(long)b * C + k] = s;
+  }
+}
+
+// parameter gradients (sums over the batch): dWpwl [Co][C], dW2 [C][RD], db2 [C], dW1 [RD][C], db1 [RD]
+__global__ void se_bwd_b_kernel(const float* __restrict__ Pp, const float* __restrict__ gate,
+                                const float* __restrict__ hpre, const float* __restrict__ mean,
+                                const float* __restrict__ dpre2, const float* __restrict__ dhpre,
+                                float* __restrict__ dwpwl, float* __restrict__ dw2, float* __restrict__ db2,
+                                float* __restrict__ dw1, float* __restrict__ db1, int B, int C, int Co, int RD) {
+  const long n_pwl = (long)C * Co, n_w2 = (long)C * RD, n_w1 = (long)RD * C;
+  const long total = n_pwl + n_w2 + C + n_w1 + RD;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    if (i < n_pwl) {
+      const int k = (int)(i / Co), n = (int)(i % Co);
+      for (int b = 0; b < B; ++b) s = fmaf(gate[(long)b * C + k], Pp[((long)b * C + k) * Co + n], s);
+      dwpwl[(long)n * C + k] = s;
+      continue;
+    }
+    long j = i - n_pwl;
+    if (j < n_w2) {
+      const int k = (int)(j / RD), r = (int)(j % RD);
+      for (int b = 0; b < B; ++b) {
+        const float u = hpre[(long)b * RD + r];
+        s = fmaf(dpre2[(long)b * C + k], u / (1.0f + expf(-u)), s);
+      }
+      dw2[j] = s;
+      continue;
+    }
+    j -= n_w2;
+    if (j < C) {
+      for (int b = 0; b < B; ++b) s += dpre2[(long)b * C + j];
+      db2[j] = s;
+      continue;
+    }
+    j -= C;
+    if (j < n_w1) {
+      const int r = (int)(j / C), k = (int)(j % C);
+      for (int b = 0; b < B; ++b) s = fmaf(dhpre[(long)b * RD + r], mean[(long)b * C + k], s);
+      dw1[j] = s;
+      continue;
+    }
+    j -= n_w1;
+    for (int b = 0; b < B; ++b) s += dhpre[(long)b * RD + j];
+    db1[j] = s;
+  }
+}
+
+extern "C" int dwn_se_bwd(const float* Pp, const float* wpwl, const float* gate, const float* hpre, const float* mean,
+                          const float* w1, const float* w2, float* dpre2, float* dhpre, float* dmean, float* dwpwl,
+                          float* dw2, float* db2, float* dw1, float* db1, int B, int C, int Co, int RD, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  se_bwd_a_kernel<<<B, 256, (C + RD) * sizeof(float), st>>>(Pp, wpwl, gate, hpre, w1, w2, dpre2, dhpre, dmean, C, Co, RD);
+  DWN_LAUNCH_CHECK();
+  long total = (long)C * Co + (long)C * RD + C + (long)RD * C + RD;
+  int gx = (int)((total + 255) / 256);
+  if (gx > 148 * 8) gx = 148 * 8;
+  se_bwd_b_kernel<<<gx, 256, 0, st>>>(Pp, gate, hpre, mean, dpre2, dhpre, dwpwl, dw2, db2, dw1, db1, B, C, Co, RD);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// temporal dw backward, pass 1: dthat = (da + dmean[b]/Nsp) * SiLU'(BN3(Tm_raw)), written in place over da,
+// partial[P][2][C] = { sum dthat, sum dthat*xhat3 }
+// =================================================================================================
+template <typename T>
+__global__ void tdw_bwd_reduce_kernel(T* __restrict__ da, const T* __restrict__ tm, const float* __restrict__ coef3,
+                                      const float* __restrict__ dmean, float inv_nsp, float* __restrict__ partial,
+                                      long Mo, long rows_per_b, int C, int cvc) {
+  constexpr int V = VecT<T>::V;
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const int cv = tid % cvc, lane = tid / cvc, ln = blockDim.x / cvc;
+  const int c = (blockIdx.y * cvc + cv) * V;
+  float sc[V], sh[V], mu[V], rs[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    sc[j] = coef3[c + j]; sh[j] = coef3[C + c + j]; mu[j] = coef3[2 * C + c + j]; rs[j] = coef3[3 * C + c + j];
+  }
+  float st[2][V] = {};
+  for (long m = (long)blockIdx.x * ln + lane; m < Mo; m += (long)gridDim.x * ln) {
+    const long b = m / rows_per_b;
+    float g[V], x[V];
+    ldv(da + m * C + c, g);
+    ldv(tm + m * C + c, x);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float u = fmaf(x[j], sc[j], sh[j]);
+      const float d = rnd<T>((g[j] + dmean[b * C + c + j] * inv_nsp) * silu_grad_t<T>(u));
+      g[j] = d;
+      st[0][j] += d;
+      st[1][j] += d * ((x[j] - mu[j]) * rs[j]);
+    }
+    stv(da + m * C + c, g);
+  }
+  block_reduce_channels<2, V>(st, smem, cvc, ln, partial + (long)blockIdx.x * 2 * C, C, blockIdx.y * cvc * V);
+}
+
+extern "C" int dwn_tdw_bwd_reduce(void* da, const void* tm, const float* coef3, const float* dmean, int Nsp,
+                                  float* partial, int P, long Mo, int C, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DWN_DT_F32) {
+    int cvc = dwn_largest_divisor_le(C / 4, 64), ln = 256 / cvc;
+    dim3 grid(P, (C / 4) / cvc), block(cvc * ln);
+    tdw_bwd_reduce_kernel<float><<<grid, block, block.x * 8 * sizeof(float), st>>>((float*)da, (const float*)tm, coef3,
+                                                                                  dmean, 1.0f / Nsp, partial, Mo, Nsp, C,
+                                                                                  cvc);
+  } else {
+    int cvc = dwn_largest_divisor_le(C / 8, 64), ln = 256 / cvc;
+    dim3 grid(P, (C / 8) / cvc), block(cvc * ln);
+    tdw_bwd_reduce_kernel<bf16><<<grid, block, block.x * 16 * sizeof(float), st>>>((bf16*)da, (const bf16*)tm, coef3,
+                                                                                  dmean, 1.0f / Nsp, partial, Mo, Nsp, C,
+                                                                                  cvc);
+  }
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// temporal dw backward, pass 2 (thread = channel quad x position, whole T column in registers):
+//   dTm = gamma3*rstd3*(dthat - c1 - xhat3*c2)
+//   dS_act[u] = sum_k w[k]*dTm[u-k+2] ;  dw[k] += s_act[u]*dTm[u-k+2]
+//   dshat[u] = dS_act[u]*SiLU'(BN2(S_raw[u]))  -> written in place over dthat
+//   partial[P][7][C] = { sum dshat, sum dshat*xhat2, dw[0..4] }
+// =================================================================================================
+template <typename T, int TT>
+__global__ void tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restrict__ s_raw,
+                               const float* __restrict__ coef3, const float* __restrict__ bcoef3,
+                               const float* __restrict__ coef2, const float* __restrict__ wgt,
+                               float* __restrict__ partial, int B, int Tn, int HW, int C, int cqc) {
+  constexpr int TA = TT > 0 ? TT : 32;
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
+  const int c = (blockIdx.y * cqc + cq) * 4;
+  const int tn = TT > 0 ? TT : Tn;
+  float sc3[4], mu3[4], rs3[4], k1[4], k2[4], sc2[4], sh2[4], mu2[4], rs2[4], wr[5][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc3[j] = coef3[c + j]; mu3[j] = coef3[2 * C + c + j]; rs3[j] = coef3[3 * C + c + j];
+    k1[j] = bcoef3[c + j]; k2[j] = bcoef3[C + c + j];
+    sc2[j] = coef2[c + j]; sh2[j] = coef2[C + c + j]; mu2[j] = coef2[2 * C + c + j]; rs2[j] = coef2[3 * C + c + j];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) wr[k][j] = wgt[(c + j) * 5 + k];
+  }
+  float st[7][4] = {};
+  const long npos = (long)B * HW;
+  const long tstride = (long)HW * C;
+  for (long pos = (long)blockIdx.x * ln + lane; pos < npos; pos += (long)gridDim.x * ln) {
+    const long b = pos / HW, hw = pos - b * HW;
+    const long base = (b * Tn * HW + hw) * C + c;
+    float dT[TA][4];
+#pragma unroll
+    for (int t = 0; t < TA; ++t) {
+      if (t < tn) {
+        float g[4], x[4];
+        ldq(dth + base + t * tstride, g);
+        ldq(tm + base + t * tstride, x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dT[t][j] = sc3[j] * (g[j] - k1[j] - (x[j] - mu3[j]) * rs3[j] * k2[j]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < TA; ++u) {
+      if (u < tn) {
+        float s[4], o[4];
+        ldq(s_raw + base + u * tstride, s);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float sa[4], sg[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v = fmaf(s[j], sc2[j], sh2[j]);
+          const float sig = Act<T>::sigmoid(v);
+          sa[j] = v * sig;
+          sg[j] = sig * (1.0f + v * (1.0f - sig));
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int t = u - k + 2;
+          if (t >= 0 && t < tn) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[j] = fmaf(wr[k][j], dT[t][j], acc[j]);
+              st[2 + k][j] = fmaf(sa[j], dT[t][j], st[2 + k][j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[j] = rnd<T>(acc[j] * sg[j]);
+          st[0][j] += o[j];
+          st[1][j] += o[j] * ((s[j] - mu2[j]) * rs2[j]);
+        }
+        stq(dth + base + u * tstride, o);
+      }
+    }
+  }
+  block_reduce_channels<7, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 7 * C, C, blockIdx.y * cqc * 4);
+}
+
+extern "C" int dwn_tdw_bwd(void* dth, const void* tm, const void* s_raw, const float* coef3, const float* bcoef3,
+                           const float* coef2, const float* wgt, float* partial, int P, int B, int Tn, int HW, int C,
+                           int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DWN_REQUIRE(Tn <= 32, "dwn_tdw_bwd: T > 32 unsupported");
+  int cqc = dwn_largest_divisor_le(C / 4, 64);
+  int ln = 128 / cqc;
+  if (ln < 1) ln = 1;
+  dim3 grid(P, (C / 4) / cqc), block(cqc * ln);
+  size_t sm = (size_t)block.x * 28 * sizeof(float);
+#define GO(TY, TTV)                                                                                              \
+  tdw_bwd_kernel<TY, TTV><<<grid, block, sm, st>>>((TY*)dth, (const TY*)tm, (const TY*)s_raw, coef3, bcoef3, coef2, wgt, \
+                                                   partial, B, Tn, HW, C, cqc)
+  if (dtype == DWN_DT_F32) {
+    if (Tn == 16) GO(float, 16); else if (Tn == 8) GO(float, 8); else GO(float, 0);
+  } else {
+    if (Tn == 16) GO(bf16, 16); else if (Tn == 8) GO(bf16, 8); else GO(bf16, 0);
+  }
+#undef GO
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// spatial dw backward.  CTA tile: one (b,t) plane, THI input rows, all W, CC channels.
+//   smem: dS_raw tile = gamma2*rstd2*(dshat - c1 - xhat2*c2) with zero halo (BN2 backward applied on load)
+//   thread (channel quad, wi): for each input row: load E_raw once -> ehat, e_act, SiLU';
+//     dE_act = sum_taps w*dS_raw ;  dw[tap] += e_act*dS_raw   (same smem values serve dgrad and wgrad)
+//     dehat = dE_act*SiLU'(ehat) -> dE_pre ;  partial[P][11][C] = { sum dehat, sum dehat*xhat1, dw[0..8] }
+// =================================================================================================
+template <typename T, int S, int THI>
+__global__ void sdw_bwd_kernel(const T* __restrict__ dsh, const T* __restrict__ s_raw, const T* __restrict__ e_raw,
+                               const float* __restrict__ coef2, const float* __restrict__ bcoef2,
+                               const float* __restrict__ coef1, const float* __restrict__ wgt, T* __restrict__ dE,
+                               float* __restrict__ partial, int NP, int H, int W, int C, int CC) {
+  constexpr int V = VecT<T>::V;
+  constexpr int NR = S == 1 ? THI + 2 : THI / 2 + 1;
+  extern __shared__ float tile[];
+  const int Ho = H / S, Wo = W / S, WP = Wo + 2;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int c0 = blockIdx.y * CC;
+  const int cvn = CC / V;
+  const int lcv = tid % cvn;
+  float l_sc[V], l_mu[V], l_rs[V], l_k1[V], l_k2[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int cc = c0 + lcv * V + j;
+    l_sc[j] = coef2[cc]; l_mu[j] = coef2[2 * C + cc]; l_rs[j] = coef2[3 * C + cc];
+    l_k1[j] = bcoef2[cc]; l_k2[j] = bcoef2[C + cc];
+  }
+  const int cqn = CC / 4;
+  const int cq = tid % cqn, wi = tid / cqn;
+  const int cch = c0 + cq * 4;
+  float wr[9][4], sc1[4], sh1[4], mu1[4], rs1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc1[j] = coef1[cch + j]; sh1[j] = coef1[C + cch + j]; mu1[j] = coef1[2 * C + cch + j]; rs1[j] = coef1[3 * C + cch + j];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wr[k][j] = wgt[(cch + j) * 9 + k];
+  }
+  // S == 2: w-direction tap slots are thread constants (wi parity)
+  const bool odd_w = (wi & 1) != 0;
+  const int kwA = (S == 1) ? 0 : (odd_w ? 0 : 1);
+  const int colA = (S == 1) ? 0 : (odd_w ? (wi + 1) / 2 : wi / 2);
+  const int colB = (wi - 1) / 2;  // only used when odd_w (kw = 2)
+  float st[11][4] = {};
+  const int nb = H / THI;
+  const int ntiles = NP * nb;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int p = t / nb, hi0 = (t % nb) * THI;
+    const int ho_first = (S == 1) ? hi0 - 1 : hi0 / 2;
+    __syncthreads();
+    // ---- load dS_raw tile (cols: S==1 -> wo+1 in [0,Wo+1]; S==2 -> wo in [0,Wo])
+    for (int i = tid; i < NR * WP * cvn; i += nthr) {
+      const int r = i / (WP * cvn);
+      const int col = (i / cvn) % WP;
+      const int ho = ho_first + r;
+      const int wo = (S == 1) ? col - 1 : col;
+      float v[V];
+      if (ho >= 0 && ho < Ho && wo >= 0 && wo < Wo) {
+        float g[V], x[V];
+        const long off = (((long)p * Ho + ho) * Wo + wo) * C + c0 + lcv * V;
+        ldv(dsh + off, g);
+        ldv(s_raw + off, x);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = l_sc[j] * (g[j] - l_k1[j] - (x[j] - l_mu[j]) * l_rs[j] * l_k2[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = 0.f;
+      }
+      float* dst = tile + ((r * WP + col) * CC + lcv * V);
+#pragma unroll
+      for (int j = 0; j < V; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int hl = 0; hl < THI; ++hl) {
+      const int hi = hi0 + hl;
+      float e[4], ea[4], sg[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const long eoff = (((long)p * H + hi) * W + wi) * C + cch;
+      ldq(e_raw + eoff, e);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = fmaf(e[j], sc1[j], sh1[j]);
+        const float sig = Act<T>::sigmoid(v);
+        ea[j] = v * sig;
+        sg[j] = sig * (1.0f + v * (1.0f - sig));
+      }
+      if (S == 1) {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int r = hl - kh + 2;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float4 q = *reinterpret_cast<const float4*>(tile + ((r * WP + wi - kw + 2) * CC + cq * 4));
+            const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[j] = fmaf(wr[kh * 3 + kw][j], v[j], acc[j]);
+              st[2 + kh * 3 + kw][j] = fmaf(ea[j], v[j], st[2 + kh * 3 + kw][j]);
+            }
+          }
+        }
+      } else {
+        // valid kh: hl even -> kh=1 (row hl/2); hl odd -> kh=0 (row (hl+1)/2), kh=2 (row (hl-1)/2)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          if (((hl & 1) == 0) != (kh == 1)) continue;
+          const int r = (kh == 1) ? hl / 2 : (kh == 0 ? (hl + 1) / 2 : (hl - 1) / 2);
+          {
+            const float4 q = *reinterpret_cast<const float4*>(tile + ((r * WP + colA) * CC + cq * 4));
+            const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float wv = odd_w ? wr[kh * 3 + 0][j] : wr[kh * 3 + 1][j];
+              acc[j] = fmaf(wv, v[j], acc[j]);
+              const float pr = ea[j] * v[j];
+              if (odd_w) st[2 + kh * 3 + 0][j] += pr; else st[2 + kh * 3 + 1][j] += pr;
+            }
+          }
+          if (odd_w) {
+            const float4 q = *reinterpret_cast<const float4*>(tile + ((r * WP + colB) * CC + cq * 4));
+            const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[j] = fmaf(wr[kh * 3 + 2][j], v[j], acc[j]);
+              st[2 + kh * 3 + 2][j] = fmaf(ea[j], v[j], st[2 + kh * 3 + 2][j]);
+            }
+          }
+        }
+      }
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[j] = rnd<T>(acc[j] * sg[j]);
+        st[0][j] += o[j];
+        st[1][j] += o[j] * ((e[j] - mu1[j]) * rs1[j]);
+      }
+      stq(dE + eoff, o);
+    }
+  }
+  (void)kwA;
+  __syncthreads();
+  block_reduce_channels<11, 4>(st, tile, cqn, W, partial + (long)blockIdx.x * 11 * C, C, c0);
+}
+
+template <typename T, int S>
+static int sdw_bwd_launch(const void* dsh, const void* s_raw, const void* e_raw, const float* coef2, const float* bcoef2,
+                          const float* coef1, const float* wgt, void* dE, float* partial, int P, int NP, int H, int W,
+                          int C, cudaStream_t st) {
+  const int Wo = W / S;
+  int CC = 1024 / W;
+  if (CC > 128) CC = 128;
+  while (CC >= 8 && (C % CC != 0)) CC /= 2;
+  DWN_REQUIRE(CC >= 8 && C % CC == 0 && (CC / 4) * W <= 1024, "dwn_sdw_bwd: unsupported C=%d W=%d", C, W);
+  int THI = (H % 8 == 0) ? 8 : (H % 4 == 0 ? 4 : 2);
+  DWN_REQUIRE(H % THI == 0, "dwn_sdw_bwd: H must be even");
+  const int NR = S == 1 ? THI + 2 : THI / 2 + 1;
+  size_t sm = (size_t)NR * (Wo + 2) * CC * sizeof(float);
+  size_t sm_red = (size_t)(CC / 4) * W * 11 * 4 * sizeof(float);
+  if (sm_red > sm) sm = sm_red;
+  dim3 grid(P, C / CC), block((CC / 4) * W);
+#define LAUNCH(THI_)                                                                                              \
+  {                                                                                                               \
+    auto k = sdw_bwd_kernel<T, S, THI_>;                                                                          \
+    if (sm > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);            \
+    k<<<grid, block, sm, st>>>((const T*)dsh, (const T*)s_raw, (const T*)e_raw, coef2, bcoef2, coef1, wgt, (T*)dE, \
+                               partial, NP, H, W, C, CC);                                                         \
+  }
+  switch (THI) {
+    case 8: LAUNCH(8) break;
+    case 4: LAUNCH(4) break;
+    default: LAUNCH(2) break;
+  }
+#undef LAUNCH
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dwn_sdw_bwd(const void* dsh, const void* s_raw, const void* e_raw, const float* coef2,
+                           const float* bcoef2, const float* coef1, const float* wgt, void* dE, float* partial, int P,
+                           int NP, int H, int W, int C, int stride, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DWN_REQUIRE(stride == 1 || stride == 2, "dwn_sdw_bwd: stride %d unsupported", stride);
+  if (dtype == DWN_DT_F32)
+    return stride == 1
+               ? sdw_bwd_launch<float, 1>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st)
+               : sdw_bwd_launch<float, 2>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st);
+  return stride == 1
+             ? sdw_bwd_launch<bf16, 1>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st)
+             : sdw_bwd_launch<bf16, 2>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st);
+}
+
+// BN backward apply in place: g <- gamma*rstd*(g - c1 - xhat*c2)
+template <typename T>
+__global__ void bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ x, const float* __restrict__ coef,
+                                    const float* __restrict__ bcoef, long M, int C) {
+  constexpr int V = VecT<T>::V;
+  const int cvn = C / V;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < M * cvn; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cvn) * V;
+    const long off = (i / cvn) * C + c;
+    float gv[V], xv[V];
+    ldv(g + off, gv);
+    ldv(x + off, xv);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float xh = (xv[j] - coef[2 * C + c + j]) * coef[3 * C + c + j];
+      gv[j] = coef[c + j] * (gv[j] - bcoef[c + j] - xh * bcoef[C + c + j]);
+    }
+    stv(g + off, gv);
+  }
+}
+
+extern "C" int dwn_bn_bwd_apply(void* g, const void* x, const float* coef, const float* bcoef, long M, int C, int dtype,
+                                void* stream) {
+  const int V = dtype == DWN_DT_F32 ? 4 : 8;
+  long n = M * (C / V);
+  int gx = (int)((n + 255) / 256);
+  if (gx > 148 * 16) gx = 148 * 16;
+  if (dtype == DWN_DT_F32)
+    bn_bwd_apply_kernel<float><<<gx, 256, 0, (cudaStream_t)stream>>>((float*)g, (const float*)x, coef, bcoef, M, C);
+  else
+    bn_bwd_apply_kernel<bf16><<<gx, 256, 0, (cudaStream_t)stream>>>((bf16*)g, (const bf16*)x, coef, bcoef, M, C);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[i] = sum_z partial[z][i]   (split-K / per-CTA partial reductions); optional transposed channel layout
+__global__ void reduce_rows_kernel(const float* __restrict__ partial, int Z, long n, float* __restrict__ out) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < Z; ++z) s += partial[(long)z * n + i];
+    out[i] = s;
+  }
+}
+extern "C" int dwn_reduce_rows(const float* partial, int Z, long n, float* out, void* stream) {
+  int gx = (int)((n + 255) / 256);
+  if (gx > 148 * 8) gx = 148 * 8;
+  reduce_rows_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(partial, Z, n, out);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// depth-wise weight gradient from partial[P][NQ][C] quantities q0..q0+KK-1 -> dw[C][KK]
+__global__ void dw_wgrad_finalize_kernel(const float* __restrict__ partial, int P, int NQ, int q0, int KK,
+                                         float* __restrict__ dw, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * KK) return;
+  const int c = i % C, k = i / C;
+  double s = 0;
+  for (int p = 0; p < P; ++p) s += (double)partial[((long)p * NQ + q0 + k) * C + c];
+  dw[(long)c * KK + k] = (float)s;
+}
+extern "C" int dwn_dw_wgrad_finalize(const float* partial, int P, int NQ, int q0, int KK, float* dw, int C, void* stream) {
+  dw_wgrad_finalize_kernel<<<(C * KK + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, P, NQ, q0, KK, dw, C);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// stem backward: one pass over dX0 [M][C0] and the 5-channel input accumulates
+//   partial[P][CIN+1][C0] = { G[c][k] = sum_m dy[m][c]*x[m][k] (k<CIN), S[c] = sum_m dy[m][c] }
+// the BN backward and the weight gradient then follow analytically from the input moments.
+// =================================================================================================
+template <int CIN>
+__global__ void stem_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                       float* __restrict__ partial, long plane, long M, int C0, int cqc) {
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
+  const int c = (blockIdx.y * cqc + cq) * 4;
+  float st[CIN + 1][4] = {};
+  for (long m = (long)blockIdx.x * ln + lane; m < M; m += (long)gridDim.x * ln) {
+    const long b = m / plane, pos = m - b * plane;
+    float g[4];
+    ldq(dy + m * C0 + c, g);
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) {
+      const float xv = __ldg(&x[(b * CIN + k) * plane + pos]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st[k][j] = fmaf(g[j], xv, st[k][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st[CIN][j] += g[j];
+  }
+  block_reduce_channels<CIN + 1, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * (CIN + 1) * C0, C0,
+                                    blockIdx.y * cqc * 4);
+}
+
+// one thread per output channel, double precision
+__global__ void stem_bwd_finalize_kernel(const float* __restrict__ partial, int P, int cin, const double* __restrict__ mom,
+                                         double count, const float* __restrict__ w, const float* __restrict__ coef,
+                                         float* __restrict__ dw, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                         int C0) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C0) return;
+  double G[8], S = 0;
+  for (int k = 0; k < cin; ++k) G[k] = 0;
+  for (int p = 0; p < P; ++p) {
+    for (int k = 0; k < cin; ++k) G[k] += (double)partial[((long)p * (cin + 1) + k) * C0 + c];
+    S += (double)partial[((long)p * (cin + 1) + cin) * C0 + c];
+  }
+  // second moments X2[j][k] from the packed upper triangle
+  double X1[8], X2[8][8];
+  int q = cin;
+  for (int j = 0; j < cin; ++j) X1[j] = mom[j];
+  for (int j = 0; j < cin; ++j)
+    for (int k = j; k < cin; ++k) { X2[j][k] = mom[q]; X2[k][j] = mom[q]; ++q; }
+  const double mean = coef[2 * C0 + c], rstd = coef[3 * C0 + c];
+  const double gr = (double)coef[c];  // gamma*rstd
+  double dot = 0;
+  for (int k = 0; k < cin; ++k) dot += (double)w[c * cin + k] * G[k];  // sum_m dy*y_raw
+  const double dg = rstd * (dot - mean * S);                           // sum dy*yhat
+  dbeta[c] = (float)S;
+  dgamma[c] = (float)dg;
+  for (int k = 0; k < cin; ++k) {
+    double wx = 0;  // sum_m y_raw*x_k = sum_j w_cj X2[j][k]
+    for (int j = 0; j < cin; ++j) wx += (double)w[c * cin + j] * X2[j][k];
+    const double yhx = rstd * (wx - mean * X1[k]);  // sum_m yhat*x_k
+    dw[c * cin + k] = (float)(gr * (G[k] - (S / count) * X1[k] - (dg / count) * yhx));
+  }
+}
+
+extern "C" int dwn_stem_bwd(const float* dy, const float* x, float* partial, int P, const double* mom, const float* w,
+                            const float* coef, float* dw, float* dgamma, float* dbeta, int B, int cin, long plane, int C0,
+                            void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int cqc = dwn_largest_divisor_le(C0 / 4, 64), ln = 256 / cqc;
+  dim3 grid(P, (C0 / 4) / cqc), block(cqc * ln);
+  size_t sm = (size_t)block.x * (cin + 1) * 4 * sizeof(float);
+  const long M = (long)B * plane;
+  switch (cin) {
+#define CASE(N) case N: stem_bwd_reduce_kernel<N><<<grid, block, sm, st>>>(dy, x, partial, plane, M, C0, cqc); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    default: return dwn_fail("dwn_stem_bwd: in_channels=%d unsupported", cin);
+  }
+  DWN_LAUNCH_CHECK();
+  stem_bwd_finalize_kernel<<<(C0 + 63) / 64, 64, 0, st>>>(partial, P, cin, mom, (double)M, w, coef, dw, dgamma, dbeta, C0);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// cortex layer backward (forward: dwn_cortex_out).  j = output channel, c = src(j) = conv channel.
+//   partial[J][4][O] = { [c] sum dyh, [c] sum dyh*yhat, [j] sum dOut, [j] sum dOut*xhat_sc }
+// =================================================================================================
+template <typename T>
+__global__ void cortex_bwd_reduce_kernel(const float* __restrict__ dOut, const T* __restrict__ y,
+                                         const float* __restrict__ coef, const float* __restrict__ dp,
+                                         const float* __restrict__ xin, const float* __restrict__ coef_sc,
+                                         float* __restrict__ partial, int M, int Tn, int I, int O, int G) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= O) return;
+  const int per = O / G;
+  const int c = (j % G) * per + j / G;
+  const float sc = coef[c], sh = coef[O + c], mu = coef[2 * O + c], rs = coef[3 * O + c];
+  const float ms = coef_sc[2 * O + j], rss = coef_sc[3 * O + j];
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+  for (int m = blockIdx.y; m < M; m += gridDim.y) {
+    const float g = dOut[(long)m * O + j];
+    const float yv = ld1<T>(y + (long)m * O + c);
+    const float d = (dp ? dp[m / Tn] : 1.0f) * g * silu_grad_t<T>(fmaf(yv, sc, sh));
+    q0 += d;
+    q1 += d * ((yv - mu) * rs);
+    q2 += g;
+    q3 += g * ((xin[(long)m * I + (j % I)] - ms) * rss);
+  }
+  float* p = partial + (long)blockIdx.y * 4 * O;
+  p[c] = q0;
+  p[O + c] = q1;
+  p[2 * O + j] = q2;
+  p[3 * O + j] = q3;
+}
+
+template <typename T>
+__global__ void cortex_bwd_dy_kernel(const float* __restrict__ dOut, const T* __restrict__ y,
+                                     const float* __restrict__ coef, const float* __restrict__ bcoef,
+                                     const float* __restrict__ dp, T* __restrict__ dY, int M, int Tn, int O, int G) {
+  const int per = O / G;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)M * O; i += (long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / O), c = (int)(i % O);
+    const int j = (c % per) * G + c / per;  // inverse shuffle
+    const float yv = ld1<T>(y + i);
+    const float d = (dp ? dp[m / Tn] : 1.0f) * dOut[(long)m * O + j] * silu_grad_t<T>(fmaf(yv, coef[c], coef[O + c]));
+    const float yh = (yv - coef[2 * O + c]) * coef[3 * O + c];
+    st1<T>(dY + i, coef[c] * (d - bcoef[c] - yh * bcoef[O + c]));
+  }
+}
+
+__global__ void cortex_in_bwd_kernel(const float* __restrict__ dXc, const float* __restrict__ dOut,
+                                     const float* __restrict__ xin, const float* __restrict__ coef_sc,
+                                     const float* __restrict__ bcoef_sc, float* __restrict__ dX, int M, int I, int O) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)M * I; i += (long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / I), k = (int)(i % I);
+    float s = dXc[i];
+    const float x = xin[i];
+    for (int j = k; j < O; j += I) {
+      const float xh = (x - coef_sc[2 * O + j]) * coef_sc[3 * O + j];
+      s += coef_sc[j] * (dOut[(long)m * O + j] - bcoef_sc[j] - xh * bcoef_sc[O + j]);
+    }
+    dX[i] = s;
+  }
+}
+
+extern "C" int dwn_cortex_bwd_reduce(const float* dOut, const void* y, const float* coef, const float* dp,
+                                     const float* xin, const float* coef_sc, float* partial, int J, int M, int Tn, int I,
+                                     int O, int G, int dtype, void* stream) {
+  dim3 grid((O + 127) / 128, J);
+  if (dtype == DWN_DT_F32)
+    cortex_bwd_reduce_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(dOut, (const float*)y, coef, dp, xin, coef_sc,
+                                                                            partial, M, Tn, I, O, G);
+  else
+    cortex_bwd_reduce_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>(dOut, (const bf16*)y, coef, dp, xin, coef_sc,
+                                                                           partial, M, Tn, I, O, G);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int dwn_cortex_bwd_dy(const float* dOut, const void* y, const float* coef, const float* bcoef, const float* dp,
+                                 void* dY, int M, int Tn, int O, int G, int dtype, void* stream) {
+  long n = (long)M * O;
+  int gx = (int)((n + 255) / 256);
+  if (gx > 2048) gx = 2048;
+  if (dtype == DWN_DT_F32)
+    cortex_bwd_dy_kernel<float><<<gx, 256, 0, (cudaStream_t)stream>>>(dOut, (const float*)y, coef, bcoef, dp, (float*)dY,
+                                                                      M, Tn, O, G);
+  else
+    cortex_bwd_dy_kernel<bf16><<<gx, 256, 0, (cudaStream_t)stream>>>(dOut, (const bf16*)y, coef, bcoef, dp, (bf16*)dY, M,
+                                                                     Tn, O, G);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int dwn_cortex_in_bwd(const float* dXc, const float* dOut, const float* xin, const float* coef_sc,
+                                 const float* bcoef_sc, float* dX, int M, int I, int O, void* stream) {
+  long n = (long)M * I;
+  int gx = (int)((n + 255) / 256);
+  if (gx > 2048) gx = 2048;
+  cortex_in_bwd_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(dXc, dOut, xin, coef_sc, bcoef_sc, dX, M, I, O);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}

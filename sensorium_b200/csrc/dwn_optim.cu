@@ -1,0 +1,109 @@
+// Multi-tensor AdamW (torch.optim.AdamW semantics, configs/true_batch_001.py:45-48) fused with the
+// bf16 weight-shadow refresh and the ModelEma update (ema.py:47-55); multi-tensor EMA for buffers.
+#include "dwn_common.cuh"
+
+struct DwnTensorEntry {  // 64 bytes, built by the host as an int64[8] row
+  float* p;              // parameter (fp32)            | EMA: model tensor (float or int64)
+  const float* g;        // gradient                    | EMA: unused
+  float* m;              // exp_avg                     | EMA: unused
+  float* v;              // exp_avg_sq                  | EMA: unused
+  bf16* shadow;          // optional bf16 copy of p     | EMA: unused
+  float* ema;            // optional EMA copy of p      | EMA: ema tensor
+  long n;                // elements
+  long flags;            // bit0: int64 tensor (EMA kernel)
+};
+
+constexpr int OPT_CHUNK = 16384;
+
+// steps[t] += active[t]  (per-tensor step counters: tensors without a gradient are skipped entirely)
+__global__ void adamw_step_kernel(int* __restrict__ steps, const int* __restrict__ active, int nt) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nt && (!active || active[t])) steps[t] += 1;
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(const DwnTensorEntry* __restrict__ tab,
+                                                    const int* __restrict__ chunk_tensor,
+                                                    const long* __restrict__ chunk_off, const int* __restrict__ steps,
+                                                    const int* __restrict__ active, float lr, float wd, float b1, float b2,
+                                                    float eps, float ema_decay) {
+  const int t = chunk_tensor[blockIdx.x];
+  if (active && !active[t]) return;
+  const DwnTensorEntry e = tab[t];
+  const long off = chunk_off[blockIdx.x];
+  const long end = min(off + (long)OPT_CHUNK, e.n);
+  __shared__ float s_c[2];
+  if (threadIdx.x == 0) {
+    const double st = (double)steps[t];
+    s_c[0] = (float)(1.0 - pow((double)b1, st));
+    s_c[1] = (float)sqrt(1.0 - pow((double)b2, st));
+  }
+  __syncthreads();
+  const float step_size = lr / s_c[0];
+  const float bc2s = s_c[1];
+  const float decay = 1.0f - lr * wd;
+  for (long i = off + threadIdx.x; i < end; i += blockDim.x) {
+    const float g = e.g[i];
+    float p = e.p[i] * decay;
+    float m = e.m[i];
+    m = m + (g - m) * (1.0f - b1);
+    const float v = e.v[i] * b2 + (1.0f - b2) * g * g;
+    const float denom = sqrtf(v) / bc2s + eps;
+    p = p - step_size * (m / denom);
+    e.p[i] = p;
+    e.m[i] = m;
+    e.v[i] = v;
+    if (e.shadow) e.shadow[i] = __float2bfloat16_rn(p);
+    if (e.ema) e.ema[i] = ema_decay * e.ema[i] + (1.0f - ema_decay) * p;
+  }
+}
+
+extern "C" int dwn_adamw(const void* tab, const int* chunk_tensor, const long* chunk_off, int nchunks, int* steps,
+                         const int* active, int nt, float lr, float wd, float b1, float b2, float eps, float ema_decay,
+                         void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  adamw_step_kernel<<<(nt + 127) / 128, 128, 0, st>>>(steps, active, nt);
+  DWN_LAUNCH_CHECK();
+  adamw_kernel<<<nchunks, 256, 0, st>>>((const DwnTensorEntry*)tab, chunk_tensor, chunk_off, steps, active, lr, wd, b1, b2,
+                                        eps, ema_decay);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ema <- decay*ema + (1-decay)*model for every state entry; int64 entries go through fp32 and truncate
+__global__ void __launch_bounds__(256) ema_kernel(const DwnTensorEntry* __restrict__ tab,
+                                                  const int* __restrict__ chunk_tensor,
+                                                  const long* __restrict__ chunk_off, float decay) {
+  const DwnTensorEntry e = tab[chunk_tensor[blockIdx.x]];
+  const long off = chunk_off[blockIdx.x];
+  const long end = min(off + (long)OPT_CHUNK, e.n);
+  if (e.flags & 1) {
+    long long* em = (long long*)e.ema;
+    const long long* mo = (const long long*)e.p;
+    for (long i = off + threadIdx.x; i < end; i += blockDim.x)
+      em[i] = (long long)(decay * (float)em[i] + (1.0f - decay) * (float)mo[i]);
+  } else {
+    for (long i = off + threadIdx.x; i < end; i += blockDim.x) e.ema[i] = decay * e.ema[i] + (1.0f - decay) * e.p[i];
+  }
+}
+
+extern "C" int dwn_ema(const void* tab, const int* chunk_tensor, const long* chunk_off, int nchunks, float decay,
+                       void* stream) {
+  ema_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>((const DwnTensorEntry*)tab, chunk_tensor, chunk_off, decay);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dwn_opt_chunk(void) { return OPT_CHUNK; }
+
+// scale a flat fp32 buffer (gradient averaging after the data-parallel all-reduce)
+__global__ void scale_kernel(float* __restrict__ x, long n, float s) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] *= s;
+}
+extern "C" int dwn_scale(float* x, long n, float s, void* stream) {
+  int gx = (int)((n + 255) / 256);
+  if (gx > 148 * 8) gx = 148 * 8;
+  if (gx < 1) gx = 1;
+  scale_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(x, n, s);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}

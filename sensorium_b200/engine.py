@@ -29,7 +29,6 @@ _P_MOM = 296
 _J_SE = 16
 
 _plans = weakref.WeakKeyDictionary()
-_shadows = weakref.WeakKeyDictionary()
 
 
 def _stream(dev):
@@ -65,19 +64,22 @@ def pe_tables(pe_mod, C: int, T: int, H: int, W: int, dev):
 
 
 def _shadow(p: torch.Tensor) -> torch.Tensor:
-    """bf16 shadow of an fp32 GEMM weight, refreshed when the parameter version changes."""
-    ent = _shadows.get(p)
-    if ent is not None and ent[0] == p._version and ent[1].device == p.device and ent[2] == p.data_ptr():
+    """bf16 shadow of an fp32 GEMM weight, refreshed when the parameter version / storage changes.
+
+    The cache lives on the parameter object itself (tensors cannot key a WeakKeyDictionary: ``==`` is
+    element-wise)."""
+    ent = getattr(p, "_dwn_shadow", None)
+    if ent is not None and ent[0] == p._version and ent[2] == p.data_ptr() and ent[1].device == p.device:
         return ent[1]
     sh = torch.empty(p.shape, dtype=torch.bfloat16, device=p.device)
     call("dwn_cast_bf16", p.detach(), sh, p.numel(), _stream(p.device))
-    _shadows[p] = (p._version, sh, p.data_ptr())
+    p._dwn_shadow = (p._version, sh, p.data_ptr())
     return sh
 
 
 def set_shadow(p: torch.Tensor, sh: torch.Tensor) -> None:
     """Used by the fused optimizer, which writes the bf16 shadow itself."""
-    _shadows[p] = (p._version, sh, p.data_ptr())
+    p._dwn_shadow = (p._version, sh, p.data_ptr())
 
 
 def _bn_coef(bn, partial, P, count, C, Cp, training, st, dev):

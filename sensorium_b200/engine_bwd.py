@@ -1,0 +1,199 @@
+"""Backward plan of DwiseNeuro over the hand-written kernels (formulas: SURVEY.md §7.4).
+
+``run_backward`` consumes the state saved by ``engine.run_forward(..., save=True)`` and the gradients of the
+readout outputs and returns one gradient (or None) per parameter in ``mod.parameters()`` order.  Mice whose
+output gradient is None keep ``grad=None`` exactly like the reference, where ``MicePoissonLoss`` skips absent
+mice (losses.py:17) and torch AdamW then skips those tensors.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from ._lib import call, gemm
+from .engine import BF16, F32, _P, _P_SDW, _empty, _shadow, _stream
+
+_J_CORTEX = 32
+
+
+def _bn_bwd(part, P, NQ, q0, count, bn, grads, C, st, dev):
+    bcoef = _empty((2, C), torch.float32, dev)
+    dgamma = _empty((C,), torch.float32, dev)
+    dbeta = _empty((C,), torch.float32, dev)
+    call("dwn_bn_bwd_finalize", part, P, NQ, q0, float(count), dgamma, dbeta, bcoef, C, st)
+    grads[bn.weight] = dgamma
+    grads[bn.bias] = dbeta
+    return bcoef
+
+
+def _split_k(rows: int, tiles: int) -> int:
+    z = 1
+    while z * 2 * tiles <= 160 and rows % (z * 2) == 0 and rows // (z * 2) >= 256:
+        z *= 2
+    return z
+
+
+def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[Optional[torch.Tensor]]:
+    cfg = mod.cfg
+    bf = sv.mode == "bf16"
+    adt = torch.bfloat16 if bf else torch.float32
+    dcode = BF16 if bf else F32
+    dev = sv.x.device
+    st = _stream(dev)
+    B, T = sv.B, sv.T
+    G = cfg["groups"]
+    Mbt = B * T
+    grads: Dict[torch.Tensor, torch.Tensor] = {}
+    if not mod.training:
+        raise NotImplementedError("sensorium_b200: backward is implemented for train mode (batch-stat BatchNorm)")
+
+    # ---------------- readouts -------------------------------------------------------------------
+    K = cfg["cortex_features"][-1]
+    Kg = K // G
+    live = [(r, g) for r, g in zip(sv.readouts, grad_outs) if g is not None]
+    dX = _empty((Mbt, K), torch.float32, dev)
+    if live:
+        dxm = _empty((len(live), Mbt, K), torch.float32, dev)
+        has_mask = live[0][0].mask is not None
+        masks = torch.stack([r.mask.reshape(B, K) for r, _ in live]).contiguous() if has_mask else None
+        for j, (r, g) in enumerate(live):
+            conv = mod.readouts[r.m].layer[1]
+            half = r.half
+            half_pad = ((half + 63) // 64) * 64
+            dz_nm = _empty((G * half, Mbt), adt, dev)
+            dz_mn = _empty((Mbt, G * half_pad), adt, dev)
+            db = _empty((G * half,), torch.float32, dev)
+            call("dwn_readout_bwd_prep", r.pred, g.contiguous(), cfg["softplus_beta"], dz_nm, dz_mn, db, B, T, r.n_out,
+                 half, half_pad, G, dcode, st)
+            dW = _empty((G * half, Kg, 1), torch.float32, dev)
+            gemm(st, dtype=dcode, A=dz_nm, B=r.xt, lda=Mbt, ldb=Mbt, a_zstride=half * Mbt, b_zstride=Kg * Mbt, a_zmode=1,
+                 b_zmode=1, M=half, N=Kg, K=Mbt, Z=G, D=dW, d_dtype=F32, ldd=Kg, d_zstride=half * Kg)
+            wr = conv.weight
+            gemm(st, dtype=dcode, A=dz_mn, B=_shadow(wr) if bf else wr, b_mn=1, lda=G * half_pad, ldb=Kg,
+                 a_zstride=half_pad, b_zstride=half * Kg, a_zmode=1, b_zmode=1, M=Mbt, N=Kg, K=half, Z=G, D=dxm[j],
+                 d_dtype=F32, ldd=K, d_zstride=Kg)
+            grads[conv.weight] = dW
+            grads[conv.bias] = db
+        call("dwn_readout_dx_combine", dxm, masks, len(live), dX, Mbt, K, T, st)
+    else:
+        dX.zero_()
+
+    # ---------------- cortex ---------------------------------------------------------------------
+    dOut = dX
+    for layer, c in zip(reversed(list(mod.cortex.layers)), reversed(sv.cortex)):
+        I, O = c.I, c.O
+        part = _empty((_J_CORTEX, 4, O), torch.float32, dev)
+        call("dwn_cortex_bwd_reduce", dOut, c.Y, c.coef, c.dp, c.x, c.coef_sc, part, _J_CORTEX, Mbt, T, I, O, G, dcode, st)
+        bcoef = _bn_bwd(part, _J_CORTEX, 4, 0, Mbt, layer.bn.bn, grads, O, st, dev)
+        bcoef_sc = _bn_bwd(part, _J_CORTEX, 4, 2, Mbt, layer.bn_sc.bn, grads, O, st, dev)
+        dY = _empty((Mbt, O), adt, dev)
+        call("dwn_cortex_bwd_dy", dOut, c.Y, c.coef, bcoef, c.dp, dY, Mbt, T, O, G, dcode, st)
+        dW = _empty((O, I // G, 1), torch.float32, dev)
+        gemm(st, dtype=dcode, A=dY, B=c.xb if bf else c.x, a_mn=1, b_mn=1, lda=O, ldb=I, a_zstride=O // G,
+             b_zstride=I // G, a_zmode=1, b_zmode=1, M=O // G, N=I // G, K=Mbt, Z=G, D=dW, d_dtype=F32, ldd=I // G,
+             d_zstride=(O // G) * (I // G))
+        grads[layer.conv.weight] = dW
+        wc = layer.conv.weight
+        dXc = _empty((Mbt, I), torch.float32, dev)
+        gemm(st, dtype=dcode, A=dY, B=_shadow(wc) if bf else wc, b_mn=1, lda=O, ldb=I // G, a_zstride=O // G,
+             b_zstride=(O // G) * (I // G), a_zmode=1, b_zmode=1, M=Mbt, N=I // G, K=O // G, Z=G, D=dXc, d_dtype=F32,
+             ldd=I, d_zstride=I // G)
+        dXn = _empty((Mbt, I), torch.float32, dev)
+        call("dwn_cortex_in_bwd", dXc, dOut, c.x, c.coef_sc, bcoef_sc, dXn, Mbt, I, O, st)
+        dOut = dXn
+
+    # ---------------- pool -----------------------------------------------------------------------
+    HW, CL = sv.pool.HW, sv.pool.C
+    dO = _empty((Mbt * HW, CL), torch.float32, dev)
+    call("dwn_pool_bwd", dOut, dO, Mbt, HW, CL, st)
+
+    # ---------------- inverted-residual blocks ---------------------------------------------------
+    nb = len(sv.blocks)
+    for i in range(nb - 1, -1, -1):
+        b = sv.blocks[i]
+        blk = mod.core.blocks[2 * i + 1]
+        ci, co, mid, s, rd = b.ci, b.co, b.mid, b.s, b.rd
+        Mi, Mo, Nsp = B * T * b.Hi * b.Wi, B * T * b.Ho * b.Wo, T * b.Ho * b.Wo
+        part = _empty((_P, 4, co), torch.float32, dev)
+        call("dwn_block_bwd_reduce", dO, b.Y, b.coef4, b.dp, b.X, b.coef_sc, part, _P, B, T, b.Ho, b.Wo, ci, co, s, dcode,
+             st)
+        bcoef4 = _bn_bwd(part, _P, 4, 0, Mo, blk.conv_pwl[1].bn, grads, co, st, dev)
+        bcoef_sc = _bn_bwd(part, _P, 4, 2, Mo, blk.bn_sc.bn, grads, co, st, dev)
+        dY = _empty((Mo, co), adt, dev)
+        call("dwn_block_bwd_dy", dO, b.Y, b.coef4, bcoef4, b.dp, dY, Mo, Nsp, co, dcode, st)
+        # per-sample projection wgrad  Pp[b][mid][co] = a_b^T dY_b  -> dW_pwl and the SE gate gradient
+        Pp = _empty((B, mid, co), torch.float32, dev)
+        gemm(st, dtype=dcode, A=b.A, B=dY, a_mn=1, b_mn=1, lda=mid, ldb=co, a_zstride=Nsp * mid, b_zstride=Nsp * co,
+             a_zmode=1, b_zmode=1, M=mid, N=co, K=Nsp, Z=B, D=Pp, d_dtype=F32, ldd=co, d_zstride=mid * co)
+        dpre2 = _empty((B, mid), torch.float32, dev)
+        dhpre = _empty((B, rd), torch.float32, dev)
+        dmean = _empty((B, mid), torch.float32, dev)
+        se = blk.se
+        dwpwl = torch.empty_like(blk.conv_pwl[0].weight)
+        dw2, db2 = torch.empty_like(se.conv_expand.weight), torch.empty_like(se.conv_expand.bias)
+        dw1, db1 = torch.empty_like(se.conv_reduce.weight), torch.empty_like(se.conv_reduce.bias)
+        call("dwn_se_bwd", Pp, blk.conv_pwl[0].weight, b.gate, b.hpre, b.mean, se.conv_reduce.weight,
+             se.conv_expand.weight, dpre2, dhpre, dmean, dwpwl, dw2, db2, dw1, db1, B, mid, co, rd, st)
+        grads[blk.conv_pwl[0].weight] = dwpwl
+        grads[se.conv_expand.weight], grads[se.conv_expand.bias] = dw2, db2
+        grads[se.conv_reduce.weight], grads[se.conv_reduce.bias] = dw1, db1
+        # projection dgrad with the gated per-sample weights: da = dY Wb
+        da = _empty((Mo, mid), adt, dev)
+        gemm(st, dtype=dcode, A=dY, B=b.Wb, b_mn=1, lda=co, ldb=mid, a_zstride=Nsp * co, b_zstride=co * mid, a_zmode=1,
+             b_zmode=1, M=Nsp, N=mid, K=co, Z=B, D=da, d_dtype=dcode, ldd=mid, d_zstride=Nsp * mid)
+        # temporal dw backward
+        part = _empty((_P, 2, mid), torch.float32, dev)
+        call("dwn_tdw_bwd_reduce", da, b.Tm, b.coef3, dmean, Nsp, part, _P, Mo, mid, dcode, st)
+        bcoef3 = _bn_bwd(part, _P, 2, 0, Mo, blk.temp_covn_dw[1].bn, grads, mid, st, dev)
+        part7 = _empty((_P, 7, mid), torch.float32, dev)
+        call("dwn_tdw_bwd", da, b.Tm, b.S, b.coef3, bcoef3, b.coef2, blk.temp_covn_dw[0].weight, part7, _P, B, T,
+             b.Ho * b.Wo, mid, dcode, st)
+        bcoef2 = _bn_bwd(part7, _P, 7, 0, Mo, blk.spat_covn_dw[1].bn, grads, mid, st, dev)
+        dwt = torch.empty_like(blk.temp_covn_dw[0].weight)
+        call("dwn_dw_wgrad_finalize", part7, _P, 7, 2, 5, dwt, mid, st)
+        grads[blk.temp_covn_dw[0].weight] = dwt
+        # spatial dw backward (da now holds d s_hat)
+        dE = _empty((Mi, mid), adt, dev)
+        part11 = _empty((_P_SDW, 11, mid), torch.float32, dev)
+        call("dwn_sdw_bwd", da, b.S, b.E, b.coef2, bcoef2, b.coef1, blk.spat_covn_dw[0].weight, dE, part11, _P_SDW, B * T,
+             b.Hi, b.Wi, mid, s, dcode, st)
+        del da
+        bcoef1 = _bn_bwd(part11, _P_SDW, 11, 0, Mi, blk.conv_pw[1].bn, grads, mid, st, dev)
+        dws = torch.empty_like(blk.spat_covn_dw[0].weight)
+        call("dwn_dw_wgrad_finalize", part11, _P_SDW, 11, 2, 9, dws, mid, st)
+        grads[blk.spat_covn_dw[0].weight] = dws
+        call("dwn_bn_bwd_apply", dE, b.E, b.coef1, bcoef1, Mi, mid, dcode, st)
+        # point-wise expansion: dgrad + split-K wgrad
+        wpw = blk.conv_pw[0].weight
+        dXpw = _empty((Mi, ci), torch.float32, dev)
+        gemm(st, dtype=dcode, A=dE, B=_shadow(wpw) if bf else wpw, b_mn=1, lda=mid, ldb=ci, M=Mi, N=ci, K=mid, Z=1,
+             D=dXpw, d_dtype=F32, ldd=ci)
+        tiles = math.ceil(mid / 128) * math.ceil(ci / 256)
+        Zs = _split_k(Mi, tiles)
+        rows = Mi // Zs
+        wpart = _empty((Zs, mid, ci), torch.float32, dev)
+        gemm(st, dtype=dcode, A=dE, B=b.Xb if bf else b.X, a_mn=1, b_mn=1, lda=mid, ldb=ci, a_zstride=rows * mid,
+             b_zstride=rows * ci, a_zmode=1, b_zmode=1, M=mid, N=ci, K=rows, Z=Zs, D=wpart, d_dtype=F32, ldd=ci,
+             d_zstride=mid * ci)
+        dwpw = torch.empty_like(wpw)
+        call("dwn_reduce_rows", wpart, Zs, mid * ci, dwpw, st)
+        grads[wpw] = dwpw
+        del dE
+        dXin = _empty((Mi, ci), torch.float32, dev)
+        call("dwn_block_in_bwd", dXpw, dO, b.X, b.coef_sc, bcoef_sc, dXin, B, T, b.Hi, b.Wi, ci, co, s, st)
+        dO = dXin
+
+    # ---------------- stem -----------------------------------------------------------------------
+    stem_conv, stem_bn = mod.core.stem[0], mod.core.stem[1].bn
+    cin = stem_conv.weight.shape[1]
+    C0 = stem_conv.weight.shape[0]
+    part = _empty((_P, cin + 1, C0), torch.float32, dev)
+    dw = torch.empty_like(stem_conv.weight)
+    dgam, dbet = torch.empty_like(stem_bn.weight), torch.empty_like(stem_bn.bias)
+    call("dwn_stem_bwd", dO, sv.x, part, _P, sv.stem.mom, stem_conv.weight, sv.stem.coef, dw, dgam, dbet, B, cin,
+         sv.T * sv.H * sv.W, C0, st)
+    grads[stem_conv.weight], grads[stem_bn.weight], grads[stem_bn.bias] = dw, dgam, dbet
+
+    return [grads.get(p) if p.requires_grad else None for p in mod.parameters()]

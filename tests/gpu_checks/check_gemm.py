@@ -10,6 +10,7 @@ sys.path.insert(0, ".")
 from sensorium_b200 import _lib  # noqa: E402
 
 torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
 dev = torch.device("cuda:0")
 st = torch.cuda.current_stream(dev).cuda_stream
 fails = 0
