@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — DwiseNeuro train-step throughput on B200 (BASELINE.json configs[1]: true_batch_001 shape,
+batch 32 per GPU, all 10 readouts, bf16, fwd + Poisson loss + bwd + AdamW + EMA), synthetic data,
+random-init weights.  One JSON line on stdout (rank 0).
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+  python bench.py --impl reference ...                   # reference algorithm on the host CPU (oracle port)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from collections import defaultdict
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "train clips/s DwiseNeuro (true_batch_001, batch 32/GPU, 10 readouts)"
+NUM_NEURONS = [7863, 7908, 8202, 7939, 8122, 7440, 7928, 8285, 7671, 7495]
+MODEL_KW = dict(in_channels=5, core_features=(64, 64, 64, 64, 128, 128, 128, 256, 256),
+                spatial_strides=(2, 1, 1, 1, 2, 1, 1, 2, 1), spatial_kernel=3, temporal_kernel=5, expansion_ratio=7,
+                se_reduce_ratio=32, cortex_features=(1024, 2048, 4096), groups=2, softplus_beta=0.07, drop_rate=0.4,
+                drop_path_rate=0.1)
+BATCH, FRAMES, SIZE = 32, 16, 64
+LR, WD, EMA_DECAY = 3e-4 * 32 / 4, 0.05, 0.999
+
+
+def synthetic_batch(batch: int, seed: int):
+    """clip (B,5,16,64,64) + one labelled mouse per sample, dense zero targets elsewhere."""
+    from oracle.dwiseneuro_oracle import synthetic_clip, synthetic_targets
+    x = synthetic_clip(batch, FRAMES, SIZE, seed=seed)
+    tg, w = synthetic_targets(batch, NUM_NEURONS, FRAMES, seed=seed + 1)
+    return x, tg, w
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 6 and s[2 + i].startswith("Active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_step(batch: int, steps: int, warmup: int):
+    """Reference algorithm (oracle port: functional torch restatement) on the host cores: fp32 train step
+    fwd + loss + bwd + AdamW, expansion 7, all readouts.  Returns clips/s, threads."""
+    from oracle import dwiseneuro_oracle as O
+    from sensorium_b200 import DwiseNeuro
+    from sensorium_b200.utils import init_weights
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net = DwiseNeuro(readout_outputs=NUM_NEURONS, **MODEL_KW)
+    init_weights(net)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    names = [k for k, _ in net.named_parameters()]
+    del net
+    params = [sd[k].requires_grad_(True) for k in names]
+    opt = torch.optim.AdamW(params, lr=LR, weight_decay=WD)
+    cfg = O.make_cfg(NUM_NEURONS, **MODEL_KW)
+    x, tg, w = synthetic_batch(batch, 0)
+    t_total = 0.0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        out = O.dwiseneuro_forward(x, sd, cfg, None, True)
+        loss = O.mice_poisson_loss(out, tg, w)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            t_total += dt
+    return batch * steps / t_total, threads, t_total / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = 2
+    val, threads, sec = cpu_reference_step(sample_b, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DwiseNeuro true_batch_001 train step (fwd+Poisson loss+bwd+AdamW), all 10 readouts",
+                   "sample": f"batch {sample_b} per step on host CPU"},
+        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} train steps of batch {sample_b} (oracle port, fp32, torch CPU)"},
+        "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--profile-out", default="")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from sensorium_b200 import _lib
+    from sensorium_b200.argus_models import MouseModel
+    from sensorium_b200.ema import ModelEma
+    from sensorium_b200.utils import init_weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+
+    torch.manual_seed(0)
+    params = {
+        "nn_module": ("dwiseneuro", {"readout_outputs": NUM_NEURONS, **MODEL_KW}),
+        "loss": ("mice_poisson", {"log_input": False, "full": False, "eps": 1e-8}),
+        "optimizer": ("FusedAdamW", {"lr": LR, "weight_decay": WD}),
+        "device": str(dev), "amp": True, "iter_size": 1,
+    }
+    model = MouseModel(params)
+    init_weights(model.nn_module)
+    if world > 1:
+        from sensorium_b200.parallel import DataParallelGrads
+        model.optimizer.active_provider = DataParallelGrads.attach(model.nn_module)
+    model.model_ema = ModelEma(model.nn_module, decay=EMA_DECAY)
+
+    x, tg, w = synthetic_batch(BATCH, 1000 + rank)
+    host_batch = (x.pin_memory(), ([t.pin_memory() for t in tg], w.pin_memory()))
+    dev_x = x.to(dev)
+    dev_tg = [t.to(dev) for t in tg]
+    dev_w = w.to(dev)
+    live = (w != 0).any(0).tolist()
+
+    def device_step():
+        model.train()
+        model.optimizer.zero_grad()
+        model.loss.set_live_hint(live)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            pred = model.nn_module(dev_x)
+            loss = model.loss(pred, (dev_tg, dev_w))
+        loss.backward()
+        model.optimizer.step()
+        model.model_ema.update(model.nn_module)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.PROF = []
+    launches0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        device_step()
+    e1.record()
+    barrier()
+    prof, _lib.PROF = _lib.PROF, None
+    launches = _lib.LAUNCHES - launches0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---- end-to-end: public API (MouseModel.train_step) with pinned HOST buffers, H2D + loss.item() inside
+    for _ in range(2):
+        model.train_step(host_batch, None)
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.e2e_steps):
+        model.train_step(host_batch, None)
+    g1.record()
+    barrier()
+    e2e_ms = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    sampler.stop_flag = True
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel accounting from the CUDA events recorded inside the timed region
+    agg = defaultdict(lambda: [0.0, 0, 0, 0])
+    for name, tag, nbytes, flops, a, b in prof:
+        k = tag or name
+        agg[k][0] += a.elapsed_time(b)
+        agg[k][1] += 1
+        agg[k][2] += nbytes
+        agg[k][3] += flops
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    total_kernel_ms = sum(v[0] for v in agg.values())
+    table = sorted(((k, v[0] / args.steps, v[1] // args.steps, v[2] / max(v[0], 1e-9) * 1e-6, v[3] / max(v[0], 1e-9) * 1e-9)
+                    for k, v in agg.items()), key=lambda r: -r[1])
+    top = table[0]
+    top_entry = agg[top[0]]
+    roofline = {"bound": "hbm", "kernel": top[0], "achieved": top[3], "peak": hbm_peak, "unit": "GB/s",
+                "frac": top[3] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": top_entry[0] / max(total_kernel_ms, 1e-9),
+                "launches_per_step": top[2], "ms_per_step": top[1]}
+    if args.profile_out:
+        with open(args.profile_out, "w") as f:
+            f.write("kernel,ms_per_step,launches_per_step,GB/s,TFLOP/s,share\n")
+            for k, msps, n, gbs, tf in table:
+                f.write(f"{k},{msps:.4f},{n},{gbs:.1f},{tf:.2f},{msps * args.steps / total_kernel_ms:.4f}\n")
+
+    clips = BATCH * world * args.steps
+    value = clips / (ms * 1e-3)
+    h2d = x.numel() * 4 + sum(t.numel() for t in tg) * 4 + w.numel() * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "DwiseNeuro true_batch_001 (expansion 7) full train step: fwd + MicePoissonLoss + bwd + "
+                               "AdamW + EMA, all 10 readouts, batch 32 per GPU, clip 5x16x64x64",
+                   "global_batch": BATCH * world, "parallelism": f"dp{world}", "weights": "random-init (init_weights)",
+                   "l2": "working set per step (>15 GB of activations) exceeds the 126 MB L2"},
+        "e2e": {"value": BATCH * world * args.e2e_steps / (e2e_ms * 1e-3), "unit": "clips/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": args.e2e_steps},
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+        "kernel_table_ms_per_step": {k: round(msps, 3) for k, msps, *_ in table[:12]},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        val, threads, sec = cpu_reference_step(2, 1, 1)
+        line["cpu_baseline"] = {"value": val, "unit": "clips/s", "cores": threads, "kind": "port",
+                                "sample": "1 train step of batch 2 after 1 warm-up (oracle port, fp32, torch CPU)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -91,6 +91,77 @@ int dwn_readout_prep(const float* x, const float* mask, void* xm, void* xt, int 
                      void* stream);
 int dwn_cast_bf16(const float* in, void* out, long n, void* stream);
 
+/* ==== backward ============================================================================================
+ * The reference gets every gradient from torch autograd through the library kernels of dwiseneuro.py; the entry
+ * points below are the hand-written backward of the same ops (formulas: SURVEY.md 7.4). */
+int dwn_bn_bwd_finalize(const float* partial, int P, int NQ, int q0, double count, float* dgamma, float* dbeta,
+                        float* bcoef, int C, void* stream);                                /* dwiseneuro.py:9-22 */
+int dwn_block_bwd_reduce(const float* dO, const void* y_raw, const float* coef4, const float* dp, const float* xin,
+                         const float* coef_sc, float* partial, int P, int B, int Tn, int Ho, int Wo, int Ci, int Co,
+                         int stride, int dtype, void* stream);                              /* dwiseneuro.py:136-144 */
+int dwn_block_bwd_dy(const float* dO, const void* y_raw, const float* coef4, const float* bcoef4, const float* dp,
+                     void* dY, long Mo, long rows_per_b, int Co, int dtype, void* stream);
+int dwn_block_in_bwd(const float* dXpw, const float* dO, const float* xin, const float* coef_sc, const float* bcoef_sc,
+                     float* dXin, int B, int Tn, int Hi, int Wi, int Ci, int Co, int stride, void* stream); /* :125-134 */
+int dwn_pool_bwd(const float* dP, float* dX, long BT, int HW, int C, void* stream);       /* dwiseneuro.py:374,400 */
+int dwn_se_bwd(const float* Pp, const float* wt, const float* gate, const float* hpre, const float* mean,
+               const float* w1, const float* w2, float* dpre2, float* dhpre, float* dmean, float* dwpwl, float* dw2,
+               float* db2, float* dw1, float* db1, int B, int C, int Co, int RD, void* stream); /* dwiseneuro.py:25-43 */
+int dwn_tdw_bwd_reduce(void* da, const void* tm, const float* coef3, const float* dmean, int Nsp, float* partial, int P,
+                       long Mo, int C, int dtype, void* stream);                           /* dwiseneuro.py:105-111 */
+int dwn_tdw_bwd(void* dth, const void* tm, const void* s_raw, const float* coef3, const float* bcoef3,
+                const float* coef2, const float* wgt, float* partial, int P, int B, int Tn, int HW, int C, int dtype,
+                void* stream);
+int dwn_sdw_bwd(const void* dsh, const void* s_raw, const void* e_raw, const float* coef2, const float* bcoef2,
+                const float* coef1, const float* wgt, void* dE, float* partial, int P, int NP, int H, int W, int C,
+                int stride, int dtype, void* stream);                                      /* dwiseneuro.py:96-102 */
+int dwn_bn_bwd_apply(void* g, const void* x, const float* coef, const float* bcoef, long M, int C, int dtype,
+                     void* stream);
+int dwn_reduce_rows(const float* partial, int Z, long n, float* out, void* stream);
+int dwn_dw_wgrad_finalize(const float* partial, int P, int NQ, int q0, int KK, float* dw, int C, void* stream);
+int dwn_stem_bwd(const float* dy, const float* x, float* partial, int P, const double* mom, const float* w,
+                 const float* coef, float* dw, float* dgamma, float* dbeta, int B, int cin, long plane, int C0,
+                 void* stream);                                                            /* dwiseneuro.py:306-309 */
+int dwn_cortex_bwd_reduce(const float* dOut, const void* y, const float* coef, const float* dp, const float* xin,
+                          const float* coef_sc, float* partial, int J, int M, int Tn, int I, int O, int G, int dtype,
+                          void* stream);                                                   /* dwiseneuro.py:195-234 */
+int dwn_cortex_bwd_dy(const float* dOut, const void* y, const float* coef, const float* bcoef, const float* dp, void* dY,
+                      int M, int Tn, int O, int G, int dtype, void* stream);
+int dwn_cortex_in_bwd(const float* dXc, const float* dOut, const float* xin, const float* coef_sc,
+                      const float* bcoef_sc, float* dX, int M, int I, int O, void* stream);
+
+/* ==== loss (src/losses.py:5-21), readout backward prep (dwiseneuro.py:266-287) ============================== */
+int dwn_poisson_fwd(const float* pred, const float* tgt, const float* wn, int wstride, int B, long per_b, float eps,
+                    double* partial, int J, void* stream);
+int dwn_poisson_bwd(const float* pred, const float* tgt, const float* wn, int wstride, const float* gout, int B,
+                    long per_b, float eps, float* dpred, void* stream);
+int dwn_readout_bwd_prep(const float* pred, const float* dpred, float beta, void* dz_nm, void* dz_mn, float* dbias,
+                         int B, int Tn, int n_out, int half, int half_pad, int G, int dtype, void* stream);
+int dwn_readout_dx_combine(const float* dxm, const float* masks, int nlive, float* dX, int M, int K, int Tn,
+                           void* stream);
+
+/* ==== distillation target fill (src/argus_models.py:31-41) ================================================== */
+int dwn_distill_prepare(const float* w, int n, float ratio, void* mask, float* dweight, void* stream);
+int dwn_distill_fill(float* tgt, const float* teacher, const void* mask, int nmice, int mouse, int B, long per_b,
+                     void* stream);
+int dwn_distill_weights(float* w, const void* mask, const float* dweight, int n, void* stream);
+
+/* ==== sliding-window predictor (src/predictors.py:36-55, src/indexes.py:23-30) ============================== */
+int dwn_window_gather(const float* inp, float* clips, int Cn, int L, long HW, int size, int step, int first_index,
+                      int nwin, void* stream);
+int dwn_window_blend(const float* pred, const float* blend, float* out, int n_out, int L, int size, int step, int win0,
+                     int nwin, long pred_wstride, void* stream);
+
+/* ==== optimizer (torch.optim.AdamW as configured in configs/true_batch_001.py:45-48) and EMA (src/ema.py:47-55)
+ * tab: device array of 8 x int64 rows {p, g, m, v, shadow_bf16, ema, n, flags}; chunk tables map CTAs to
+ * (tensor, offset) in units of dwn_opt_chunk() elements. */
+int dwn_opt_chunk(void);
+int dwn_adamw(const void* tab, const int* chunk_tensor, const long* chunk_off, int nchunks, int* steps,
+              const int* active, int nt, float lr, float wd, float b1, float b2, float eps, float ema_decay,
+              void* stream);
+int dwn_ema(const void* tab, const int* chunk_tensor, const long* chunk_off, int nchunks, float decay, void* stream);
+int dwn_scale(float* x, long n, float s, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,17 +108,47 @@ def _ptr(x):
     return x
 
 
-def call(name: str, *args):
+# kernels launched per C-ABI call (default 1) — used for the bench's gpu_launches claim
+_LAUNCHES_PER_CALL = {"dwn_input_moments": 2, "dwn_se_bwd": 2, "dwn_adamw": 2, "dwn_stem_bwd": 2}
+LAUNCHES = 0
+PROF = None  # when set to a list, every call appends (name, tag, bytes, flops, start_event, end_event)
+
+
+def call(name: str, *args, _bytes: int = 0, _flops: int = 0, _tag: str = ""):
+    global LAUNCHES
     fn = getattr(lib(), name)
+    prof = PROF
+    if prof is not None:
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = fn(*[_ptr(a) for a in args])
     if rc != 0:
         raise DwnError(f"{name} failed: {lib().dwn_last_error().decode()}")
+    LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)
+    if prof is not None:
+        e1.record()
+        prof.append((name, _tag, _bytes, _flops, e0, e1))
 
 
-def gemm(stream, **kw):
+def gemm(stream, _bytes: int = 0, _flops: int = 0, _tag: str = "", **kw):
+    global LAUNCHES
     d = GemmDesc()
     for k, v in kw.items():
         setattr(d, k, _ptr(v))
+    prof = PROF
+    if prof is not None:
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = lib().dwn_gemm(C.byref(d), stream)
     if rc != 0:
         raise DwnError(f"dwn_gemm failed: {lib().dwn_last_error().decode()}")
+    LAUNCHES += 1
+    if prof is not None:
+        e1.record()
+        if not _flops:
+            _flops = 2 * d.M * d.N * d.K * d.Z
+        prof.append(("dwn_gemm", _tag, _bytes, _flops, e0, e1))

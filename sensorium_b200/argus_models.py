@@ -1,0 +1,115 @@
+"""MouseModel — the argus model wrapper of /root/reference/src/argus_models.py:13-99 over the B200 engine.
+
+Same attributes (iter_size, amp, grad_scaler, model_ema, distill_model, distill_ratio) and the same
+train_step / val_step / predict / add_distill_predictions contracts.  Differences, all on the device side:
+ * AMP uses bf16 autocast (BASELINE.json north_star) so no loss scaling is needed; ``grad_scaler`` is kept
+   as a disabled GradScaler for attribute compatibility;
+ * the distillation target fill is three kernel launches instead of a 288-iteration Python loop;
+ * the set of live mice is taken from the host copy of the weights, so the loss needs no device sync.
+"""
+from __future__ import annotations
+
+import torch
+
+try:  # pragma: no cover - the real package is absent in this image
+    import argus  # type: ignore
+    from argus.engine import State  # type: ignore
+    from argus.loss import pytorch_losses  # type: ignore
+    from argus.utils import deep_to, deep_detach, deep_chunk  # type: ignore
+    _Base = argus.Model
+    _register = lambda c: c  # noqa: E731
+except ImportError:
+    from .argus_shim import Model as _Base, State, pytorch_losses, deep_to, deep_detach, deep_chunk
+    from .argus_shim import register_model as _register
+
+from ._lib import call
+from .dwiseneuro import DwiseNeuro
+from .ema import ModelEma
+from .losses import MicePoissonLoss
+from .optim import FusedAdamW
+
+
+@_register
+class MouseModel(_Base):
+    nn_module = {"dwiseneuro": DwiseNeuro}
+    loss = {**pytorch_losses, "mice_poisson": MicePoissonLoss}
+    optimizer = {"FusedAdamW": FusedAdamW, "AdamW": FusedAdamW}
+
+    def __init__(self, params: dict):
+        super().__init__(params)
+        self.iter_size = int(params.get("iter_size", 1))
+        self.amp = bool(params.get("amp", False))
+        self.grad_scaler = torch.amp.GradScaler("cuda", enabled=False)
+        self.model_ema: ModelEma | None = None
+        self.distill_model: torch.nn.Module | None = None
+        self.distill_ratio: float = 0.0
+
+    # argus_models.py:31-41
+    @torch.no_grad()
+    def add_distill_predictions(self, input, target):
+        if self.distill_model is not None and self.distill_ratio:
+            teacher = self.distill_model(input)
+            target_tensors, mice_weights = target
+            dev = mice_weights.device
+            st = torch.cuda.current_stream(dev).cuda_stream
+            B, nm = mice_weights.shape
+            mask = torch.empty((B, nm), dtype=torch.uint8, device=dev)
+            dweight = torch.empty((1,), dtype=torch.float32, device=dev)
+            call("dwn_distill_prepare", mice_weights, B * nm, float(self.distill_ratio), mask, dweight, st)
+            for m in range(nm):
+                t = target_tensors[m]
+                call("dwn_distill_fill", t, teacher[m].float().contiguous(), mask, nm, m, B, t.numel() // B, st)
+            call("dwn_distill_weights", mice_weights, mask, dweight, B * nm, st)
+
+    # argus_models.py:43-71
+    def train_step(self, batch, state: State) -> dict:
+        self.train()
+        self.optimizer.zero_grad()
+        loss_value = 0
+        for i, chunk_batch in enumerate(deep_chunk(batch, self.iter_size)):
+            host_w = chunk_batch[1][1]
+            distill = self.distill_model is not None and self.distill_ratio
+            if isinstance(self.loss, MicePoissonLoss) and not host_w.is_cuda:
+                self.loss.set_live_hint([True] * host_w.shape[1] if distill else (host_w != 0).any(0).tolist())
+            input, target = deep_to(chunk_batch, self.device, non_blocking=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+                self.add_distill_predictions(input, target)
+                prediction = self.nn_module(input)
+                loss = self.loss(prediction, target)
+                loss = loss / self.iter_size
+            self.grad_scaler.scale(loss).backward()
+            loss_value += loss.item()
+        self.grad_scaler.step(self.optimizer)
+        self.grad_scaler.update()
+        if self.model_ema is not None:
+            self.model_ema.update(self.nn_module)
+        prediction = deep_detach(prediction)
+        target = deep_detach(target)
+        prediction = self.prediction_transform(prediction)
+        return {"prediction": prediction, "target": target, "loss": loss_value}
+
+    # argus_models.py:73-87
+    def val_step(self, batch, state: State) -> dict:
+        self.eval()
+        with torch.no_grad():
+            input, target = deep_to(batch, device=self.device, non_blocking=True)
+            if self.model_ema is None:
+                prediction = self.nn_module(input)
+            else:
+                prediction = self.model_ema.ema(input)
+            loss = self.loss(prediction, target)
+            prediction = self.prediction_transform(prediction)
+            return {"prediction": prediction, "target": target, "loss": loss.item()}
+
+    # argus_models.py:89-99
+    def predict(self, input, mouse_index: int | None = None):
+        self._check_predict_ready()
+        with torch.no_grad():
+            self.eval()
+            input = deep_to(input, self.device)
+            if self.model_ema is None:
+                prediction = self.nn_module(input, mouse_index)
+            else:
+                prediction = self.model_ema.ema(input, mouse_index)
+            prediction = self.prediction_transform(prediction)
+            return prediction

@@ -5,39 +5,41 @@
 // (sum dy, sum dy*xhat) of the *next* BN in the chain, so each tensor is read once per stage.
 #include "dwn_common.cuh"
 #include "dwn_reduce.cuh"
+#include <type_traits>
 
 // =================================================================================================
 // BN backward finalize: partial[P][NQ][C] (quantities q0, q0+1 = sum dy, sum dy*xhat)
 //   -> dgamma, dbeta (parameter gradients) and bcoef[2][C] = sums / N
 // =================================================================================================
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int P, int NQ, int q0, double count,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ bcoef, int C) {
-  __shared__ double s0[8][32], s1[8][32];
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int P, int NQ, int q0,
+                                                              double count, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, float* __restrict__ bcoef,
+                                                              int C) {
+  __shared__ float s0[32][33], s1[32][33];
   const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
-  double a = 0, b = 0;
+  float a = 0.f, b = 0.f;
   if (c < C)
-    for (int p = sl; p < P; p += 8) {
-      a += (double)partial[((long)p * NQ + q0) * C + c];
-      b += (double)partial[((long)p * NQ + q0 + 1) * C + c];
+    for (int p = sl; p < P; p += 32) {
+      a += partial[((long)p * NQ + q0) * C + c];
+      b += partial[((long)p * NQ + q0 + 1) * C + c];
     }
   s0[sl][cl] = a;
   s1[sl][cl] = b;
   __syncthreads();
   if (sl != 0 || c >= C) return;
-  a = 0; b = 0;
-  for (int i = 0; i < 8; ++i) { a += s0[i][cl]; b += s1[i][cl]; }
-  if (dbeta) dbeta[c] = (float)a;
-  if (dgamma) dgamma[c] = (float)b;
-  bcoef[c] = (float)(a / count);
-  bcoef[C + c] = (float)(b / count);
+  double da = 0, db = 0;
+  for (int i = 0; i < 32; ++i) { da += (double)s0[i][cl]; db += (double)s1[i][cl]; }
+  if (dbeta) dbeta[c] = (float)da;
+  if (dgamma) dgamma[c] = (float)db;
+  bcoef[c] = (float)(da / count);
+  bcoef[C + c] = (float)(db / count);
 }
 
 extern "C" int dwn_bn_bwd_finalize(const float* partial, int P, int NQ, int q0, double count, float* dgamma,
                                    float* dbeta, float* bcoef, int C, void* stream) {
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partial, P, NQ, q0, count, dgamma, dbeta, bcoef,
-                                                                          C);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(partial, P, NQ, q0, count, dgamma, dbeta,
+                                                                           bcoef, C);
   DWN_LAUNCH_CHECK();
   return 0;
 }
@@ -217,24 +219,34 @@ extern "C" int dwn_pool_bwd(const float* dP, float* dX, long BT, int HW, int C, 
 // the per-sample wgrad GEMM; it yields both dW_pwl and the gate gradient (u = a*g, Y = u W^T):
 //   dg[b][k] = sum_n W[n][k]*Pp[b][k][n],   dW[n][k] = sum_b g[b][k]*Pp[b][k][n]
 // =================================================================================================
-__global__ void se_bwd_a_kernel(const float* __restrict__ Pp, const float* __restrict__ wpwl,
-                                const float* __restrict__ gate, const float* __restrict__ hpre,
-                                const float* __restrict__ w1, const float* __restrict__ w2,
-                                float* __restrict__ dpre2, float* __restrict__ dhpre, float* __restrict__ dmean, int C,
-                                int Co, int RD) {
+// a1: dpre2[b][k] = g(1-g) * sum_n Wt[k][n]*Pp[b][k][n]   (warp per k, lanes over n: both operands row-contiguous)
+__global__ void __launch_bounds__(256) se_bwd_a1_kernel(const float* __restrict__ Pp, const float* __restrict__ wt,
+                                                       const float* __restrict__ gate, float* __restrict__ dpre2, int C,
+                                                       int Co) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (k >= C) return;
+  const float* P = Pp + ((long)b * C + k) * Co;
+  const float* w = wt + (long)k * Co;
+  float s = 0.f;
+  for (int n = lane; n < Co; n += 32) s = fmaf(w[n], P[n], s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    const float g = gate[(long)b * C + k];
+    dpre2[(long)b * C + k] = s * g * (1.0f - g);
+  }
+}
+
+// a2: one CTA per sample: dh -> dhpre -> dmean
+__global__ void se_bwd_a2_kernel(const float* __restrict__ dpre2, const float* __restrict__ hpre,
+                                 const float* __restrict__ w1, const float* __restrict__ w2,
+                                 float* __restrict__ dhpre, float* __restrict__ dmean, int C, int RD) {
   extern __shared__ float sm[];  // dpre2[C], dhp[RD]
   float* s_dp2 = sm;
   float* s_dhp = sm + C;
   const int b = blockIdx.x, tid = threadIdx.x;
-  const float* P = Pp + (long)b * C * Co;
-  for (int k = tid; k < C; k += blockDim.x) {
-    float s = 0.f;
-    for (int n = 0; n < Co; ++n) s = fmaf(wpwl[(long)n * C + k], P[(long)k * Co + n], s);
-    const float g = gate[(long)b * C + k];
-    const float d = s * g * (1.0f - g);
-    s_dp2[k] = d;
-    dpre2[(long)b * C + k] = d;
-  }
+  for (int k = tid; k < C; k += blockDim.x) s_dp2[k] = dpre2[(long)b * C + k];
   __syncthreads();
   const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
   for (int r = wid; r < RD; r += nw) {
@@ -302,11 +314,15 @@ __global__ void se_bwd_b_kernel(const float* __restrict__ Pp, const float* __res
   }
 }
 
-extern "C" int dwn_se_bwd(const float* Pp, const float* wpwl, const float* gate, const float* hpre, const float* mean,
+// wt = projection weight transposed to [C(mid)][Co] (tiny; prepared by the caller)
+extern "C" int dwn_se_bwd(const float* Pp, const float* wt, const float* gate, const float* hpre, const float* mean,
                           const float* w1, const float* w2, float* dpre2, float* dhpre, float* dmean, float* dwpwl,
                           float* dw2, float* db2, float* dw1, float* db1, int B, int C, int Co, int RD, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  se_bwd_a_kernel<<<B, 256, (C + RD) * sizeof(float), st>>>(Pp, wpwl, gate, hpre, w1, w2, dpre2, dhpre, dmean, C, Co, RD);
+  dim3 g1((C + 7) / 8, B);
+  se_bwd_a1_kernel<<<g1, 256, 0, st>>>(Pp, wt, gate, dpre2, C, Co);
+  DWN_LAUNCH_CHECK();
+  se_bwd_a2_kernel<<<B, 256, (C + RD) * sizeof(float), st>>>(dpre2, hpre, w1, w2, dhpre, dmean, C, RD);
   DWN_LAUNCH_CHECK();
   long total = (long)C * Co + (long)C * RD + C + (long)RD * C + RD;
   int gx = (int)((total + 255) / 256);
@@ -486,51 +502,69 @@ extern "C" int dwn_tdw_bwd(void* dth, const void* tm, const void* s_raw, const f
 //     dehat = dE_act*SiLU'(ehat) -> dE_pre ;  partial[P][11][C] = { sum dehat, sum dehat*xhat1, dw[0..8] }
 // =================================================================================================
 template <typename T, int S, int THI>
-__global__ void sdw_bwd_kernel(const T* __restrict__ dsh, const T* __restrict__ s_raw, const T* __restrict__ e_raw,
-                               const float* __restrict__ coef2, const float* __restrict__ bcoef2,
-                               const float* __restrict__ coef1, const float* __restrict__ wgt, T* __restrict__ dE,
-                               float* __restrict__ partial, int NP, int H, int W, int C, int CC) {
+__global__ void __launch_bounds__(256, 2)
+sdw_bwd_kernel(const T* __restrict__ dsh, const T* __restrict__ s_raw, const T* __restrict__ e_raw,
+               const float* __restrict__ coef2, const float* __restrict__ bcoef2, const float* __restrict__ coef1,
+               const float* __restrict__ wgt, T* __restrict__ dE, float* __restrict__ partial, int NP, int H, int W,
+               int C, int CC, int nchunks, int wpsh, int cvsh) {
+  // 1-D grid, channel chunk fastest (see sdw_fwd_kernel).  wpsh = log2(Wo+2) is never a power of two, so only
+  // the channel-vector split uses a shift; the (row, col) split uses one division per vector.
   constexpr int V = VecT<T>::V;
   constexpr int NR = S == 1 ? THI + 2 : THI / 2 + 1;
   extern __shared__ float tile[];
   const int Ho = H / S, Wo = W / S, WP = Wo + 2;
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int c0 = blockIdx.y * CC;
+  const int chunk = blockIdx.x % nchunks, worker = blockIdx.x / nchunks, nworkers = gridDim.x / nchunks;
+  const int c0 = chunk * CC;
   const int cvn = CC / V;
   const int lcv = tid % cvn;
-  float l_sc[V], l_mu[V], l_rs[V], l_k1[V], l_k2[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    const int cc = c0 + lcv * V + j;
-    l_sc[j] = coef2[cc]; l_mu[j] = coef2[2 * C + cc]; l_rs[j] = coef2[3 * C + cc];
-    l_k1[j] = bcoef2[cc]; l_k2[j] = bcoef2[C + cc];
-  }
   const int cqn = CC / 4;
   const int cq = tid % cqn, wi = tid / cqn;
   const int cch = c0 + cq * 4;
-  float wr[9][4], sc1[4], sh1[4], mu1[4], rs1[4];
+  // per-channel constants live in shared memory (registers are needed for the 44 accumulators + 36 weights):
+  //   sco[0..2] : BN2 backward on load  dS_raw = la*g - ld*x - lb
+  //   sco[3..6] : BN1+SiLU constants p0, p1 and mean1, rstd1
+  float* sco = tile + (size_t)NR * (Wo + 2) * CC;
+  for (int i = tid; i < CC; i += nthr) {
+    const int cc = c0 + i;
+    const float sc = coef2[cc], mu = coef2[2 * C + cc], rs = coef2[3 * C + cc];
+    const float k1 = bcoef2[cc], k2 = bcoef2[C + cc];
+    sco[i] = sc;
+    sco[CC + i] = sc * (k1 - mu * rs * k2);
+    sco[2 * CC + i] = sc * rs * k2;
+    float q0, q1;
+    BnSilu<T>::prep(coef1[cc], coef1[C + cc], q0, q1);
+    sco[3 * CC + i] = q0;
+    sco[4 * CC + i] = q1;
+    sco[5 * CC + i] = coef1[2 * C + cc];
+    sco[6 * CC + i] = coef1[3 * C + cc];
+  }
+  float wr[9][4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    sc1[j] = coef1[cch + j]; sh1[j] = coef1[C + cch + j]; mu1[j] = coef1[2 * C + cch + j]; rs1[j] = coef1[3 * C + cch + j];
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int k = 0; k < 9; ++k) wr[k][j] = wgt[(cch + j) * 9 + k];
-  }
   // S == 2: w-direction tap slots are thread constants (wi parity)
   const bool odd_w = (wi & 1) != 0;
-  const int kwA = (S == 1) ? 0 : (odd_w ? 0 : 1);
   const int colA = (S == 1) ? 0 : (odd_w ? (wi + 1) / 2 : wi / 2);
   const int colB = (wi - 1) / 2;  // only used when odd_w (kw = 2)
   float st[11][4] = {};
   const int nb = H / THI;
   const int ntiles = NP * nb;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  const int nvec = NR * WP * cvn;
+  for (int t = worker; t < ntiles; t += nworkers) {
     const int p = t / nb, hi0 = (t % nb) * THI;
     const int ho_first = (S == 1) ? hi0 - 1 : hi0 / 2;
+    // prefetch the first E row of this tile while the dS tile is staged
+    float e_nxt[4];
+    ldq(e_raw + (((long)p * H + hi0) * W + wi) * C + cch, e_nxt);
     __syncthreads();
     // ---- load dS_raw tile (cols: S==1 -> wo+1 in [0,Wo+1]; S==2 -> wo in [0,Wo])
-    for (int i = tid; i < NR * WP * cvn; i += nthr) {
-      const int r = i / (WP * cvn);
-      const int col = (i / cvn) % WP;
+#pragma unroll 2
+    for (int i = tid; i < nvec; i += nthr) {
+      const int pos = cvsh >= 0 ? (i >> cvsh) : (i / cvn);
+      const int r = pos / WP;
+      const int col = pos - r * WP;
       const int ho = ho_first + r;
       const int wo = (S == 1) ? col - 1 : col;
       float v[V];
@@ -539,8 +573,9 @@ __global__ void sdw_bwd_kernel(const T* __restrict__ dsh, const T* __restrict__ 
         const long off = (((long)p * Ho + ho) * Wo + wo) * C + c0 + lcv * V;
         ldv(dsh + off, g);
         ldv(s_raw + off, x);
+        const float* ca = sco + lcv * V;
 #pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = l_sc[j] * (g[j] - l_k1[j] - (x[j] - l_mu[j]) * l_rs[j] * l_k2[j]);
+        for (int j = 0; j < V; ++j) v[j] = fmaf(ca[j], g[j], -fmaf(ca[2 * CC + j], x[j], ca[CC + j]));
       } else {
 #pragma unroll
         for (int j = 0; j < V; ++j) v[j] = 0.f;
@@ -550,18 +585,22 @@ __global__ void sdw_bwd_kernel(const T* __restrict__ dsh, const T* __restrict__ 
       for (int j = 0; j < V; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
     __syncthreads();
-#pragma unroll
-    for (int hl = 0; hl < THI; ++hl) {
+    // rows are processed in pairs so the stride-2 tap parity is a compile-time constant without fully
+    // unrolling the band (full unrolling costs >200 registers)
+    auto row_body = [&](const int hl, auto par_c) {
+      constexpr int PAR = decltype(par_c)::value;
       const int hi = hi0 + hl;
       float e[4], ea[4], sg[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
       const long eoff = (((long)p * H + hi) * W + wi) * C + cch;
-      ldq(e_raw + eoff, e);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float v = fmaf(e[j], sc1[j], sh1[j]);
-        const float sig = Act<T>::sigmoid(v);
-        ea[j] = v * sig;
-        sg[j] = sig * (1.0f + v * (1.0f - sig));
+      for (int j = 0; j < 4; ++j) e[j] = e_nxt[j];
+      if (hl + 1 < THI) ldq(e_raw + eoff + (long)W * C, e_nxt);
+      {
+        const float4 q0 = *reinterpret_cast<const float4*>(sco + 3 * CC + cq * 4);
+        const float4 q1 = *reinterpret_cast<const float4*>(sco + 4 * CC + cq * 4);
+        const float a0[4] = {q0.x, q0.y, q0.z, q0.w}, a1[4] = {q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ea[j] = BnSilu<T>::act_grad(e[j], a0[j], a1[j], sg[j]);
       }
       if (S == 1) {
 #pragma unroll
@@ -579,10 +618,10 @@ __global__ void sdw_bwd_kernel(const T* __restrict__ dsh, const T* __restrict__ 
           }
         }
       } else {
-        // valid kh: hl even -> kh=1 (row hl/2); hl odd -> kh=0 (row (hl+1)/2), kh=2 (row (hl-1)/2)
+        // valid kh: even row -> kh=1 (tile row hl/2); odd row -> kh=0 (row (hl+1)/2), kh=2 (row (hl-1)/2)
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
-          if (((hl & 1) == 0) != (kh == 1)) continue;
+          if ((PAR == 0) != (kh == 1)) continue;
           const int r = (kh == 1) ? hl / 2 : (kh == 0 ? (hl + 1) / 2 : (hl - 1) / 2);
           {
             const float4 q = *reinterpret_cast<const float4*>(tile + ((r * WP + colA) * CC + cq * 4));
@@ -592,7 +631,8 @@ __global__ void sdw_bwd_kernel(const T* __restrict__ dsh, const T* __restrict__ 
               const float wv = odd_w ? wr[kh * 3 + 0][j] : wr[kh * 3 + 1][j];
               acc[j] = fmaf(wv, v[j], acc[j]);
               const float pr = ea[j] * v[j];
-              if (odd_w) st[2 + kh * 3 + 0][j] += pr; else st[2 + kh * 3 + 1][j] += pr;
+              st[2 + kh * 3 + 0][j] += odd_w ? pr : 0.f;
+              st[2 + kh * 3 + 1][j] += odd_w ? 0.f : pr;
             }
           }
           if (odd_w) {
@@ -607,42 +647,65 @@ __global__ void sdw_bwd_kernel(const T* __restrict__ dsh, const T* __restrict__ 
         }
       }
       float o[4];
+      {
+        const float4 qm = *reinterpret_cast<const float4*>(sco + 5 * CC + cq * 4);
+        const float4 qr = *reinterpret_cast<const float4*>(sco + 6 * CC + cq * 4);
+        const float mu1[4] = {qm.x, qm.y, qm.z, qm.w}, rs1[4] = {qr.x, qr.y, qr.z, qr.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        o[j] = rnd<T>(acc[j] * sg[j]);
-        st[0][j] += o[j];
-        st[1][j] += o[j] * ((e[j] - mu1[j]) * rs1[j]);
+        for (int j = 0; j < 4; ++j) {
+          o[j] = rnd<T>(acc[j] * sg[j]);
+          st[0][j] += o[j];
+          st[1][j] = fmaf(o[j], (e[j] - mu1[j]) * rs1[j], st[1][j]);
+        }
       }
       stq(dE + eoff, o);
+    };
+    if (S == 1) {
+#pragma unroll 1
+      for (int hl = 0; hl < THI; ++hl) row_body(hl, std::integral_constant<int, 0>{});
+    } else {
+#pragma unroll 1
+      for (int hl = 0; hl < THI; hl += 2) {
+        row_body(hl, std::integral_constant<int, 0>{});
+        row_body(hl + 1, std::integral_constant<int, 1>{});
+      }
     }
   }
-  (void)kwA;
   __syncthreads();
-  block_reduce_channels<11, 4>(st, tile, cqn, W, partial + (long)blockIdx.x * 11 * C, C, c0);
+  block_reduce_channels<11, 4>(st, tile, cqn, W, partial + (long)worker * 11 * C, C, c0);
+}
+
+static inline int ilog2_exact_b(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return (1 << s) == v ? s : -1;
 }
 
 template <typename T, int S>
 static int sdw_bwd_launch(const void* dsh, const void* s_raw, const void* e_raw, const float* coef2, const float* bcoef2,
                           const float* coef1, const float* wgt, void* dE, float* partial, int P, int NP, int H, int W,
                           int C, cudaStream_t st) {
+  constexpr int V = VecT<T>::V;
   const int Wo = W / S;
   int CC = 1024 / W;
   if (CC > 128) CC = 128;
   while (CC >= 8 && (C % CC != 0)) CC /= 2;
-  DWN_REQUIRE(CC >= 8 && C % CC == 0 && (CC / 4) * W <= 1024, "dwn_sdw_bwd: unsupported C=%d W=%d", C, W);
+  DWN_REQUIRE(CC >= 8 && C % CC == 0 && (CC / 4) * W <= 256, "dwn_sdw_bwd: unsupported C=%d W=%d", C, W);
   int THI = (H % 8 == 0) ? 8 : (H % 4 == 0 ? 4 : 2);
   DWN_REQUIRE(H % THI == 0, "dwn_sdw_bwd: H must be even");
   const int NR = S == 1 ? THI + 2 : THI / 2 + 1;
-  size_t sm = (size_t)NR * (Wo + 2) * CC * sizeof(float);
+  size_t sm = ((size_t)NR * (Wo + 2) + 7) * CC * sizeof(float);
   size_t sm_red = (size_t)(CC / 4) * W * 11 * 4 * sizeof(float);
   if (sm_red > sm) sm = sm_red;
-  dim3 grid(P, C / CC), block((CC / 4) * W);
+  const int nchunks = C / CC;
+  const int cvsh = ilog2_exact_b(CC / V);
+  dim3 grid(P * nchunks), block((CC / 4) * W);
 #define LAUNCH(THI_)                                                                                              \
   {                                                                                                               \
     auto k = sdw_bwd_kernel<T, S, THI_>;                                                                          \
     if (sm > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);            \
     k<<<grid, block, sm, st>>>((const T*)dsh, (const T*)s_raw, (const T*)e_raw, coef2, bcoef2, coef1, wgt, (T*)dE, \
-                               partial, NP, H, W, C, CC);                                                         \
+                               partial, NP, H, W, C, CC, nchunks, -1, cvsh);                                      \
   }
   switch (THI) {
     case 8: LAUNCH(8) break;
@@ -668,23 +731,31 @@ extern "C" int dwn_sdw_bwd(const void* dsh, const void* s_raw, const void* e_raw
              : sdw_bwd_launch<bf16, 2>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st);
 }
 
-// BN backward apply in place: g <- gamma*rstd*(g - c1 - xhat*c2)
+// BN backward apply in place: g <- gamma*rstd*(g - c1 - xhat*c2).  Thread = fixed channel vector (coefficients
+// live in registers), rows strided over the grid: pure 16-byte streaming.
 template <typename T>
 __global__ void bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ x, const float* __restrict__ coef,
-                                    const float* __restrict__ bcoef, long M, int C) {
+                                    const float* __restrict__ bcoef, long M, int C, int cvc) {
   constexpr int V = VecT<T>::V;
-  const int cvn = C / V;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < M * cvn; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cvn) * V;
-    const long off = (i / cvn) * C + c;
+  const int tid = threadIdx.x;
+  const int cv = tid % cvc, lane = tid / cvc, ln = blockDim.x / cvc;
+  const int c = (blockIdx.y * cvc + cv) * V;
+  float a[V], bb[V], dd[V];  // dx = a*g - bb - dd*x  with a = scale, dd = scale*rstd*c2, bb = scale*(c1 - mean*rstd*c2)
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const float sc = coef[c + j], mu = coef[2 * C + c + j], rs = coef[3 * C + c + j];
+    const float c1 = bcoef[c + j], c2 = bcoef[C + c + j];
+    a[j] = sc;
+    dd[j] = sc * rs * c2;
+    bb[j] = sc * (c1 - mu * rs * c2);
+  }
+  for (long m = (long)blockIdx.x * ln + lane; m < M; m += (long)gridDim.x * ln) {
+    const long off = m * C + c;
     float gv[V], xv[V];
     ldv(g + off, gv);
     ldv(x + off, xv);
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const float xh = (xv[j] - coef[2 * C + c + j]) * coef[3 * C + c + j];
-      gv[j] = coef[c + j] * (gv[j] - bcoef[c + j] - xh * bcoef[C + c + j]);
-    }
+    for (int j = 0; j < V; ++j) gv[j] = fmaf(a[j], gv[j], -fmaf(dd[j], xv[j], bb[j]));
     stv(g + off, gv);
   }
 }
@@ -692,13 +763,15 @@ __global__ void bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ x, 
 extern "C" int dwn_bn_bwd_apply(void* g, const void* x, const float* coef, const float* bcoef, long M, int C, int dtype,
                                 void* stream) {
   const int V = dtype == DWN_DT_F32 ? 4 : 8;
-  long n = M * (C / V);
-  int gx = (int)((n + 255) / 256);
-  if (gx > 148 * 16) gx = 148 * 16;
+  DWN_REQUIRE(C % V == 0, "dwn_bn_bwd_apply: C %% %d != 0", V);
+  int cvc = dwn_largest_divisor_le(C / V, 64), ln = 256 / cvc;
+  const int ny = (C / V) / cvc;
+  int gx = (148 * 8 + ny - 1) / ny;
+  dim3 grid(gx, ny), block(cvc * ln);
   if (dtype == DWN_DT_F32)
-    bn_bwd_apply_kernel<float><<<gx, 256, 0, (cudaStream_t)stream>>>((float*)g, (const float*)x, coef, bcoef, M, C);
+    bn_bwd_apply_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((float*)g, (const float*)x, coef, bcoef, M, C, cvc);
   else
-    bn_bwd_apply_kernel<bf16><<<gx, 256, 0, (cudaStream_t)stream>>>((bf16*)g, (const bf16*)x, coef, bcoef, M, C);
+    bn_bwd_apply_kernel<bf16><<<grid, block, 0, (cudaStream_t)stream>>>((bf16*)g, (const bf16*)x, coef, bcoef, M, C, cvc);
   DWN_LAUNCH_CHECK();
   return 0;
 }
@@ -720,17 +793,24 @@ extern "C" int dwn_reduce_rows(const float* partial, int Z, long n, float* out, 
 }
 
 // depth-wise weight gradient from partial[P][NQ][C] quantities q0..q0+KK-1 -> dw[C][KK]
-__global__ void dw_wgrad_finalize_kernel(const float* __restrict__ partial, int P, int NQ, int q0, int KK,
-                                         float* __restrict__ dw, int C) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * KK) return;
-  const int c = i % C, k = i / C;
+__global__ void __launch_bounds__(1024) dw_wgrad_finalize_kernel(const float* __restrict__ partial, int P, int NQ, int q0,
+                                                                int KK, float* __restrict__ dw, int C) {
+  __shared__ float s0[32][33];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl, k = blockIdx.y;
+  float a = 0.f;
+  if (c < C)
+    for (int p = sl; p < P; p += 32) a += partial[((long)p * NQ + q0 + k) * C + c];
+  s0[sl][cl] = a;
+  __syncthreads();
+  if (sl != 0 || c >= C) return;
   double s = 0;
-  for (int p = 0; p < P; ++p) s += (double)partial[((long)p * NQ + q0 + k) * C + c];
+  for (int i = 0; i < 32; ++i) s += (double)s0[i][cl];
   dw[(long)c * KK + k] = (float)s;
 }
 extern "C" int dwn_dw_wgrad_finalize(const float* partial, int P, int NQ, int q0, int KK, float* dw, int C, void* stream) {
-  dw_wgrad_finalize_kernel<<<(C * KK + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, P, NQ, q0, KK, dw, C);
+  dim3 grid((C + 31) / 32, KK);
+  dw_wgrad_finalize_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(partial, P, NQ, q0, KK, dw, C);
   DWN_LAUNCH_CHECK();
   return 0;
 }

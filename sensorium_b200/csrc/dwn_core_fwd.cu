@@ -125,13 +125,14 @@ extern "C" int dwn_stem_coef(const double* mom, int cin, double count, const flo
 // =================================================================================================
 // generic BN finalize: partial[P][2][C] (sum, sumsq) -> coef[4][C]; eval mode uses running stats.
 // =================================================================================================
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int P, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
-                                   long long* __restrict__ nbt, float momentum, float eps, int training,
-                                   float* __restrict__ coef, int C, int Cp) {
-  // block = (32 channels, 8 slices); partial has Cp channels, channel c reads column c % Cp
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int P, double count,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ rmean, float* __restrict__ rvar,
+                                                          long long* __restrict__ nbt, float momentum, float eps,
+                                                          int training, float* __restrict__ coef, int C, int Cp) {
+  // block = (32 channels, 32 slices); partial has Cp channels, channel c reads column c % Cp
   // (cyclic channel tiling of the shortcut, dwiseneuro.py:130-132)
-  __shared__ double s_sum[8][32], s_sq[8][32];
+  __shared__ double s_sum[32][33], s_sq[32][33];
   int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
   int c = blockIdx.x * 32 + cl;
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt && training) *nbt += 1;
@@ -140,7 +141,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int P, dou
     double s = 0, q = 0;
     if (c < C) {
       const int cp = c % Cp;
-      for (int p = sl; p < P; p += 8) {
+      for (int p = sl; p < P; p += 32) {
         s += (double)partial[((long)p * 2) * Cp + cp];
         q += (double)partial[((long)p * 2 + 1) * Cp + cp];
       }
@@ -150,7 +151,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int P, dou
     __syncthreads();
     if (sl != 0 || c >= C) return;
     s = 0; q = 0;
-    for (int i = 0; i < 8; ++i) { s += s_sum[i][cl]; q += s_sq[i][cl]; }
+    for (int i = 0; i < 32; ++i) { s += s_sum[i][cl]; q += s_sq[i][cl]; }
     mean = s / count;
     var = q / count - mean * mean;
     if (var < 0) var = 0;
@@ -175,7 +176,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int P, dou
 extern "C" int dwn_bn_finalize(const float* partial, int P, double count, const float* gamma, const float* beta,
                                float* rmean, float* rvar, long long* nbt, float momentum, float eps, int training,
                                float* coef, int C, int Cp, void* stream) {
-  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partial, P, count, gamma, beta, rmean, rvar, nbt,
+  bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(partial, P, count, gamma, beta, rmean, rvar, nbt,
                                                                       momentum, eps, training, coef, C, Cp > 0 ? Cp : C);
   DWN_LAUNCH_CHECK();
   return 0;
@@ -263,23 +264,25 @@ extern "C" int dwn_stem_fwd(const float* x, const float* w, const float* coef, c
 // CTA tile: one (b,t) plane, THO output rows, all W, CC channels; activated halo tile in smem (fp32).
 // =================================================================================================
 template <typename T, int S, int THO>
-__global__ void sdw_fwd_kernel(const T* __restrict__ in, const float* __restrict__ coef, const float* __restrict__ wgt,
-                               T* __restrict__ out, float* __restrict__ partial, int NP, int H, int W, int C, int CC) {
+__global__ void __launch_bounds__(256, 2)
+sdw_fwd_kernel(const T* __restrict__ in, const float* __restrict__ coef, const float* __restrict__ wgt,
+               T* __restrict__ out, float* __restrict__ partial, int NP, int H, int W, int C, int CC, int nchunks,
+               int wsh, int cvsh) {
+  // grid is 1-D with the channel chunk fastest: CTAs that share a (plane, band) tile run together, so every
+  // 128-byte line of E_raw is consumed while it is L2 resident.  wsh/cvsh = log2(W), log2(CC/V) or -1.
   constexpr int V = VecT<T>::V;
   constexpr int NR = (THO - 1) * S + 3;
   extern __shared__ float tile[];
   const int Ho = H / S, Wo = W / S, WP = W + 2;
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int c0 = blockIdx.y * CC;
-  // ---- per-thread constants for the load phase
+  const int chunk = blockIdx.x % nchunks, worker = blockIdx.x / nchunks, nworkers = gridDim.x / nchunks;
+  const int c0 = chunk * CC;
+  // ---- per-thread constants for the load phase (fixed channel vector)
   const int cvn = CC / V;
   const int lcv = tid % cvn;
-  float lsc[V], lsh[V];
+  float lp0[V], lp1[V];
 #pragma unroll
-  for (int j = 0; j < V; ++j) {
-    lsc[j] = coef[c0 + lcv * V + j];
-    lsh[j] = coef[C + c0 + lcv * V + j];
-  }
+  for (int j = 0; j < V; ++j) BnSilu<T>::prep(coef[c0 + lcv * V + j], coef[C + c0 + lcv * V + j], lp0[j], lp1[j]);
   // ---- per-thread constants for the compute phase
   const int cqn = CC / 4;
   const int cq = tid % cqn, wo = tid / cqn;
@@ -297,19 +300,22 @@ __global__ void sdw_fwd_kernel(const T* __restrict__ in, const float* __restrict
   }
   const int nb = Ho / THO;
   const int ntiles = NP * nb;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  const int nvec = NR * W * cvn;
+  for (int t = worker; t < ntiles; t += nworkers) {
     const int p = t / nb, ho0 = (t % nb) * THO;
     const int hi0 = ho0 * S - 1;
     __syncthreads();  // previous compute done before overwriting the tile
-    for (int i = tid; i < NR * W * cvn; i += nthr) {
-      int r = i / (W * cvn);
-      int wq = (i / cvn) % W;
-      int hi = hi0 + r;
+#pragma unroll 2
+    for (int i = tid; i < nvec; i += nthr) {
+      int r, wq;
+      if (wsh >= 0) { r = i >> (wsh + cvsh); wq = (i >> cvsh) & (W - 1); }
+      else { r = i / (W * cvn); wq = (i / cvn) % W; }
+      const int hi = hi0 + r;
       float v[V];
       if (hi >= 0 && hi < H) {
         ldv(in + (((long)p * H + hi) * W + wq) * C + c0 + lcv * V, v);
 #pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = silu_t<T>(fmaf(v[j], lsc[j], lsh[j]));
+        for (int j = 0; j < V; ++j) v[j] = BnSilu<T>::act(v[j], lp0[j], lp1[j]);
       } else {
 #pragma unroll
         for (int j = 0; j < V; ++j) v[j] = 0.f;
@@ -344,33 +350,43 @@ __global__ void sdw_fwd_kernel(const T* __restrict__ in, const float* __restrict
       for (int j = 0; j < 4; ++j) {
         float r = rnd<T>(acc[j]);
         st[0][j] += r;
-        st[1][j] += r * r;
+        st[1][j] = fmaf(r, r, st[1][j]);
       }
     }
   }
   __syncthreads();
-  if (partial) block_reduce_channels<2, 4>(st, tile, cqn, Wo, partial + (long)blockIdx.x * 2 * C, C, c0);
+  if (partial) block_reduce_channels<2, 4>(st, tile, cqn, Wo, partial + (long)worker * 2 * C, C, c0);
+}
+
+static inline int ilog2_exact(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return (1 << s) == v ? s : -1;
 }
 
 template <typename T, int S>
 static int sdw_fwd_launch(const void* in, const float* coef, const float* wgt, void* out, float* partial, int P, int NP,
                           int H, int W, int C, cudaStream_t st) {
+  constexpr int V = VecT<T>::V;
   const int Ho = H / S, Wo = W / S;
   int CC = 1024 / Wo;  // (CC/4)*Wo = 256 threads
   if (CC > 128) CC = 128;
   while (CC >= 8 && (C % CC != 0)) CC /= 2;
-  DWN_REQUIRE(CC >= 8 && C % CC == 0 && (CC / 4) * Wo <= 1024, "dwn_sdw_fwd: unsupported C=%d W=%d", C, W);
+  DWN_REQUIRE(CC >= 8 && C % CC == 0 && (CC / 4) * Wo <= 256, "dwn_sdw_fwd: unsupported C=%d W=%d", C, W);
   int THO = (S == 1 && Ho % 8 == 0) ? 8 : (Ho % 4 == 0 ? 4 : (Ho % 2 == 0 ? 2 : 1));
   const int NR = (THO - 1) * S + 3;
   size_t sm = (size_t)NR * (W + 2) * CC * sizeof(float);
   size_t sm_red = (size_t)(CC / 4) * Wo * 2 * 4 * sizeof(float);
   if (sm_red > sm) sm = sm_red;
-  dim3 grid(P, C / CC), block((CC / 4) * Wo);
+  const int nchunks = C / CC;
+  int wsh = ilog2_exact(W), cvsh = ilog2_exact(CC / V);
+  if (wsh < 0 || cvsh < 0) wsh = cvsh = -1;
+  dim3 grid(P * nchunks), block((CC / 4) * Wo);
 #define LAUNCH(THO_)                                                                                             \
   {                                                                                                              \
     auto k = sdw_fwd_kernel<T, S, THO_>;                                                                         \
     if (sm > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);           \
-    k<<<grid, block, sm, st>>>((const T*)in, coef, wgt, (T*)out, partial, NP, H, W, C, CC);                      \
+    k<<<grid, block, sm, st>>>((const T*)in, coef, wgt, (T*)out, partial, NP, H, W, C, CC, nchunks, wsh, cvsh);  \
   }
   switch (THO) {
     case 8: LAUNCH(8) break;

@@ -1,0 +1,67 @@
+"""ModelEma — same surface as /root/reference/src/ema.py:12-58 (timm ModelEmaV2 semantics: the EMA runs over
+*every* state_dict entry in order; int64 buffers go through fp32 and are truncated on copy), but one
+multi-tensor kernel launch instead of ~1.4k tiny launches per step."""
+from __future__ import annotations
+
+from copy import deepcopy
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import call
+from .optim import _chunk_tables
+
+
+class ModelEma(nn.Module):
+    def __init__(self, model, decay=0.9999, device=None):
+        super().__init__()
+        self.ema = deepcopy(model)
+        self.ema.eval()
+        self.decay = decay
+        self.device = device
+        if self.device is not None:
+            self.ema.to(device=device)
+        self._key = None
+        self._tab = None
+
+    def _tables(self, model):
+        ev = list(self.ema.state_dict().values())
+        mv = list(model.state_dict().values())
+        key = tuple((e.data_ptr(), m.data_ptr()) for e, m in zip(ev, mv))
+        if key != self._key:
+            dev = ev[0].device
+            rows = []
+            for e, m in zip(ev, mv):
+                if e.device != m.device:
+                    raise RuntimeError("sensorium_b200.ModelEma: EMA and model must live on the same CUDA device")
+                if e.dtype == torch.float32:
+                    flag = 0
+                elif e.dtype == torch.int64:
+                    flag = 1
+                else:
+                    raise RuntimeError(f"unsupported state dtype {e.dtype}")
+                rows.append([m.data_ptr(), 0, 0, 0, 0, e.data_ptr(), e.numel(), flag])
+            self._tab = torch.tensor(rows, dtype=torch.int64).to(dev)
+            self._chunks = _chunk_tables([e.numel() for e in ev], _lib.lib().dwn_opt_chunk(), dev)
+            self._key = key
+            self._nelem = sum(e.numel() for e in ev)
+        return ev[0].device
+
+    @torch.no_grad()
+    def update(self, model):
+        dev = self._tables(model)
+        if dev.type != "cuda":
+            raise RuntimeError("sensorium_b200.ModelEma runs on CUDA only: no CPU fallback")
+        ct, co, nch = self._chunks
+        call("dwn_ema", self._tab, ct, co, nch, float(self.decay), torch.cuda.current_stream(dev).cuda_stream,
+             _tag="ema", _bytes=self._nelem * 12)
+        # weights of the EMA module changed behind autograd's back: drop stale bf16 shadows
+        for p in self.ema.parameters():
+            if getattr(p, "_dwn_shadow", None) is not None:
+                p._dwn_shadow = None
+
+    @torch.no_grad()
+    def set(self, model):
+        for e, m in zip(self.ema.state_dict().values(), model.state_dict().values()):
+            e.copy_(m)

@@ -95,7 +95,7 @@ def _bn_coef(bn, partial, P, count, C, Cp, training, st, dev):
 
 def _colstats(x, M, ld, C, dcode, st, dev):
     part = _empty((_P, 2, C), torch.float32, dev)
-    call("dwn_colstats", x, M, ld, C, part, _P, dcode, st)
+    call("dwn_colstats", x, M, ld, C, part, _P, dcode, st, _tag="colstats", _bytes=M * C * (2 if dcode == BF16 else 4))
     return part
 
 
@@ -115,6 +115,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
     bf = mode == "bf16"
     adt = torch.bfloat16 if bf else torch.float32
     dcode = BF16 if bf else F32
+    es = 2 if bf else 4
     x = x.detach().contiguous().float()
     B, Cin, T, H, W = x.shape
     feats = cfg["core_features"]
@@ -149,7 +150,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
     if H % strides[0] or W % strides[0]:
         raise NotImplementedError("spatial size must be divisible by the block stride")
     call("dwn_stem_fwd", x, stem_conv.weight, coef0, pe[0], pe[1], pe[2], X, Xb, sc_part, _P, strides[0], B, Cin, T, H,
-         W, C0, st)
+         W, C0, st, _tag="stem_fwd", _bytes=M0 * (Cin * 4 + C0 * (4 + (2 if bf else 0))))
     if save:
         sv.stem = SimpleNamespace(coef=coef0, mom=mom)
 
@@ -169,24 +170,27 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         wpw = blk.conv_pw[0].weight
         E = _empty((Mi, mid), adt, dev)
         gemm(st, dtype=dcode, A=Xb if bf else X, B=_shadow(wpw) if bf else wpw, lda=ci, ldb=ci, M=Mi, N=mid, K=ci, Z=1,
-             D=E, d_dtype=dcode, ldd=mid)
+             D=E, d_dtype=dcode, ldd=mid, _tag="pw_fwd", _bytes=(Mi * ci + mid * ci + Mi * mid) * es)
         coef1 = _bn_coef(blk.conv_pw[1].bn, _colstats(E, Mi, mid, mid, dcode, st, dev) if training else None, _P, Mi,
                          mid, 0, training, st, dev)
         # 2. spatial depth-wise (BN1+SiLU on load)
         S = _empty((Mo, mid), adt, dev)
         part = _empty((_P, 2, mid), torch.float32, dev) if training else None
-        call("dwn_sdw_fwd", E, coef1, blk.spat_covn_dw[0].weight, S, part, _P_SDW, B * T, Hi, Wi, mid, s, dcode, st)
+        call("dwn_sdw_fwd", E, coef1, blk.spat_covn_dw[0].weight, S, part, _P_SDW, B * T, Hi, Wi, mid, s, dcode, st,
+             _tag="sdw_fwd", _bytes=(Mi + Mo) * mid * es)
         coef2 = _bn_coef(blk.spat_covn_dw[1].bn, part, _P_SDW, Mo, mid, 0, training, st, dev)
         # 3. temporal depth-wise (BN2+SiLU on load)
         Tm = _empty((Mo, mid), adt, dev)
         part = _empty((_P, 2, mid), torch.float32, dev) if training else None
-        call("dwn_tdw_fwd", S, coef2, blk.temp_covn_dw[0].weight, Tm, part, _P, B, T, Ho * Wo, mid, dcode, st)
+        call("dwn_tdw_fwd", S, coef2, blk.temp_covn_dw[0].weight, Tm, part, _P, B, T, Ho * Wo, mid, dcode, st,
+             _tag="tdw_fwd", _bytes=2 * Mo * mid * es)
         coef3 = _bn_coef(blk.temp_covn_dw[1].bn, part, _P, Mo, mid, 0, training, st, dev)
         # 4. squeeze-excite: a = SiLU(BN3(Tm)), gate folded into per-sample projection weights
         A = _empty((Mo, mid), adt, dev)
         rd = blk.se.conv_reduce.weight.shape[0]
         pool_part = _empty((B, _J_SE, mid), torch.float32, dev)
-        call("dwn_se_pool", Tm, coef3, A, pool_part, _J_SE, B, Nsp, mid, dcode, st)
+        call("dwn_se_pool", Tm, coef3, A, pool_part, _J_SE, B, Nsp, mid, dcode, st, _tag="se_pool",
+             _bytes=2 * Mo * mid * es)
         mean = _empty((B, mid), torch.float32, dev)
         hpre = _empty((B, rd), torch.float32, dev)
         gate = _empty((B, mid), torch.float32, dev)
@@ -197,7 +201,8 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         # 5. point-wise linear projection, batched over samples (B operand = gated weights of the sample)
         Y = _empty((Mo, co), adt, dev)
         gemm(st, dtype=dcode, A=A, B=Wb, lda=mid, ldb=mid, a_zstride=Nsp * mid, b_zstride=co * mid, a_zmode=1,
-             b_zmode=1, M=Nsp, N=co, K=mid, Z=B, D=Y, d_dtype=dcode, ldd=co, d_zstride=Nsp * co)
+             b_zmode=1, M=Nsp, N=co, K=mid, Z=B, D=Y, d_dtype=dcode, ldd=co, d_zstride=Nsp * co, _tag="pwl_fwd",
+             _bytes=(Mo * mid + B * co * mid + Mo * co) * es)
         coef4 = _bn_coef(blk.conv_pwl[1].bn, _colstats(Y, Mo, co, co, dcode, st, dev) if training else None, _P, Mo, co,
                          0, training, st, dev)
         coef_sc = _bn_coef(blk.bn_sc.bn, sc_part, _P, Mo, co, ci, training, st, dev)
@@ -211,7 +216,8 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         Xnb = _empty((Mo, co), torch.bfloat16, dev) if (bf and not last) else None
         nsc_part = _empty((_P, 2, co), torch.float32, dev) if (training and not last) else None
         call("dwn_block_out", Y, coef4, dp, X, coef_sc, pe[0], pe[1], pe[2], Xn, Xnb, nsc_part, _P,
-             1 if last else strides[i + 1], B, T, Ho, Wo, ci, co, s, dcode, st)
+             1 if last else strides[i + 1], B, T, Ho, Wo, ci, co, s, dcode, st, _tag="block_out",
+             _bytes=Mo * (co * es + ci * 4 + co * (4 + (2 if bf else 0))))
         if save:
             sv.blocks.append(SimpleNamespace(X=X, Xb=Xb, E=E, S=S, Tm=Tm, A=A, Y=Y, Wb=Wb, coef1=coef1, coef2=coef2,
                                              coef3=coef3, coef4=coef4, coef_sc=coef_sc, gate=gate, hpre=hpre,
@@ -274,7 +280,8 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         wr = conv.weight
         gemm(st, dtype=dcode, A=_shadow(wr) if bf else wr, B=xm, lda=Kg, ldb=K, a_zstride=half * Kg, b_zstride=Kg,
              a_zmode=1, b_zmode=1, M=half, N=Mbt, K=Kg, Z=G, epi=1, D=pred, bias=conv.bias, beta=cfg["softplus_beta"],
-             Tn=T, n_out_total=n_out, row_offset_per_z=half, n_limit=Mbt)
+             Tn=T, n_out_total=n_out, row_offset_per_z=half, n_limit=Mbt, _tag="readout_fwd",
+             _bytes=G * half * Kg * es + Mbt * K * es + B * n_out * T * 4)
         preds.append(pred)
         if save:
             sv.readouts.append(SimpleNamespace(m=m, mask=mask, xm=xm, xt=xt, pred=pred, n_out=n_out, half=half))

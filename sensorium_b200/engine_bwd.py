@@ -40,6 +40,7 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
     bf = sv.mode == "bf16"
     adt = torch.bfloat16 if bf else torch.float32
     dcode = BF16 if bf else F32
+    es = 2 if bf else 4
     dev = sv.x.device
     st = _stream(dev)
     B, T = sv.B, sv.T
@@ -48,6 +49,10 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
     grads: Dict[torch.Tensor, torch.Tensor] = {}
     if not mod.training:
         raise NotImplementedError("sensorium_b200: backward is implemented for train mode (batch-stat BatchNorm)")
+
+    dp = getattr(mod, "_dp", None)
+    if dp is not None:
+        dp.begin([g is not None for g in grad_outs], dev)
 
     # ---------------- readouts -------------------------------------------------------------------
     K = cfg["cortex_features"][-1]
@@ -69,16 +74,28 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
                  half, half_pad, G, dcode, st)
             dW = _empty((G * half, Kg, 1), torch.float32, dev)
             gemm(st, dtype=dcode, A=dz_nm, B=r.xt, lda=Mbt, ldb=Mbt, a_zstride=half * Mbt, b_zstride=Kg * Mbt, a_zmode=1,
-                 b_zmode=1, M=half, N=Kg, K=Mbt, Z=G, D=dW, d_dtype=F32, ldd=Kg, d_zstride=half * Kg)
+                 b_zmode=1, M=half, N=Kg, K=Mbt, Z=G, D=dW, d_dtype=F32, ldd=Kg, d_zstride=half * Kg, _tag="readout_wgrad",
+                 _bytes=G * half * Mbt * es + K * Mbt * es + G * half * Kg * 4)
             wr = conv.weight
             gemm(st, dtype=dcode, A=dz_mn, B=_shadow(wr) if bf else wr, b_mn=1, lda=G * half_pad, ldb=Kg,
                  a_zstride=half_pad, b_zstride=half * Kg, a_zmode=1, b_zmode=1, M=Mbt, N=Kg, K=half, Z=G, D=dxm[j],
-                 d_dtype=F32, ldd=K, d_zstride=Kg)
+                 d_dtype=F32, ldd=K, d_zstride=Kg, _tag="readout_dgrad",
+                 _bytes=Mbt * G * half_pad * es + G * half * Kg * es + Mbt * K * 4)
             grads[conv.weight] = dW
             grads[conv.bias] = db
+            if dp is not None:
+                dp.reduce(grads, [conv.weight, conv.bias])
         call("dwn_readout_dx_combine", dxm, masks, len(live), dX, Mbt, K, T, st)
     else:
         dX.zero_()
+    if dp is not None:
+        # mice without a local sample still take part in the exchange with a zero bucket
+        for r, g in zip(sv.readouts, grad_outs):
+            if g is None:
+                conv = mod.readouts[r.m].layer[1]
+                grads[conv.weight] = torch.zeros_like(conv.weight)
+                grads[conv.bias] = torch.zeros_like(conv.bias)
+                dp.reduce(grads, [conv.weight, conv.bias])
 
     # ---------------- cortex ---------------------------------------------------------------------
     dOut = dX
@@ -103,6 +120,8 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         dXn = _empty((Mbt, I), torch.float32, dev)
         call("dwn_cortex_in_bwd", dXc, dOut, c.x, c.coef_sc, bcoef_sc, dXn, Mbt, I, O, st)
         dOut = dXn
+        if dp is not None:
+            dp.reduce(grads, list(layer.parameters()))
 
     # ---------------- pool -----------------------------------------------------------------------
     HW, CL = sv.pool.HW, sv.pool.C
@@ -118,15 +137,17 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         Mi, Mo, Nsp = B * T * b.Hi * b.Wi, B * T * b.Ho * b.Wo, T * b.Ho * b.Wo
         part = _empty((_P, 4, co), torch.float32, dev)
         call("dwn_block_bwd_reduce", dO, b.Y, b.coef4, b.dp, b.X, b.coef_sc, part, _P, B, T, b.Ho, b.Wo, ci, co, s, dcode,
-             st)
+             st, _tag="block_bwd_reduce", _bytes=Mo * (co * (4 + es) + ci * 4))
         bcoef4 = _bn_bwd(part, _P, 4, 0, Mo, blk.conv_pwl[1].bn, grads, co, st, dev)
         bcoef_sc = _bn_bwd(part, _P, 4, 2, Mo, blk.bn_sc.bn, grads, co, st, dev)
         dY = _empty((Mo, co), adt, dev)
-        call("dwn_block_bwd_dy", dO, b.Y, b.coef4, bcoef4, b.dp, dY, Mo, Nsp, co, dcode, st)
+        call("dwn_block_bwd_dy", dO, b.Y, b.coef4, bcoef4, b.dp, dY, Mo, Nsp, co, dcode, st, _tag="block_bwd_dy",
+             _bytes=Mo * co * (4 + 2 * es))
         # per-sample projection wgrad  Pp[b][mid][co] = a_b^T dY_b  -> dW_pwl and the SE gate gradient
         Pp = _empty((B, mid, co), torch.float32, dev)
         gemm(st, dtype=dcode, A=b.A, B=dY, a_mn=1, b_mn=1, lda=mid, ldb=co, a_zstride=Nsp * mid, b_zstride=Nsp * co,
-             a_zmode=1, b_zmode=1, M=mid, N=co, K=Nsp, Z=B, D=Pp, d_dtype=F32, ldd=co, d_zstride=mid * co)
+             a_zmode=1, b_zmode=1, M=mid, N=co, K=Nsp, Z=B, D=Pp, d_dtype=F32, ldd=co, d_zstride=mid * co, _tag="pwl_wgrad",
+             _bytes=Mo * (mid + co) * es + B * mid * co * 4)
         dpre2 = _empty((B, mid), torch.float32, dev)
         dhpre = _empty((B, rd), torch.float32, dev)
         dmean = _empty((B, mid), torch.float32, dev)
@@ -134,7 +155,8 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         dwpwl = torch.empty_like(blk.conv_pwl[0].weight)
         dw2, db2 = torch.empty_like(se.conv_expand.weight), torch.empty_like(se.conv_expand.bias)
         dw1, db1 = torch.empty_like(se.conv_reduce.weight), torch.empty_like(se.conv_reduce.bias)
-        call("dwn_se_bwd", Pp, blk.conv_pwl[0].weight, b.gate, b.hpre, b.mean, se.conv_reduce.weight,
+        wt = blk.conv_pwl[0].weight.detach().reshape(co, mid).t().contiguous()
+        call("dwn_se_bwd", Pp, wt, b.gate, b.hpre, b.mean, se.conv_reduce.weight,
              se.conv_expand.weight, dpre2, dhpre, dmean, dwpwl, dw2, db2, dw1, db1, B, mid, co, rd, st)
         grads[blk.conv_pwl[0].weight] = dwpwl
         grads[se.conv_expand.weight], grads[se.conv_expand.bias] = dw2, db2
@@ -142,14 +164,16 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         # projection dgrad with the gated per-sample weights: da = dY Wb
         da = _empty((Mo, mid), adt, dev)
         gemm(st, dtype=dcode, A=dY, B=b.Wb, b_mn=1, lda=co, ldb=mid, a_zstride=Nsp * co, b_zstride=co * mid, a_zmode=1,
-             b_zmode=1, M=Nsp, N=mid, K=co, Z=B, D=da, d_dtype=dcode, ldd=mid, d_zstride=Nsp * mid)
+             b_zmode=1, M=Nsp, N=mid, K=co, Z=B, D=da, d_dtype=dcode, ldd=mid, d_zstride=Nsp * mid, _tag="pwl_dgrad",
+             _bytes=(Mo * co + B * co * mid + Mo * mid) * es)
         # temporal dw backward
         part = _empty((_P, 2, mid), torch.float32, dev)
-        call("dwn_tdw_bwd_reduce", da, b.Tm, b.coef3, dmean, Nsp, part, _P, Mo, mid, dcode, st)
+        call("dwn_tdw_bwd_reduce", da, b.Tm, b.coef3, dmean, Nsp, part, _P, Mo, mid, dcode, st, _tag="tdw_bwd_reduce",
+             _bytes=3 * Mo * mid * es)
         bcoef3 = _bn_bwd(part, _P, 2, 0, Mo, blk.temp_covn_dw[1].bn, grads, mid, st, dev)
         part7 = _empty((_P, 7, mid), torch.float32, dev)
         call("dwn_tdw_bwd", da, b.Tm, b.S, b.coef3, bcoef3, b.coef2, blk.temp_covn_dw[0].weight, part7, _P, B, T,
-             b.Ho * b.Wo, mid, dcode, st)
+             b.Ho * b.Wo, mid, dcode, st, _tag="tdw_bwd", _bytes=4 * Mo * mid * es)
         bcoef2 = _bn_bwd(part7, _P, 7, 0, Mo, blk.spat_covn_dw[1].bn, grads, mid, st, dev)
         dwt = torch.empty_like(blk.temp_covn_dw[0].weight)
         call("dwn_dw_wgrad_finalize", part7, _P, 7, 2, 5, dwt, mid, st)
@@ -158,32 +182,35 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         dE = _empty((Mi, mid), adt, dev)
         part11 = _empty((_P_SDW, 11, mid), torch.float32, dev)
         call("dwn_sdw_bwd", da, b.S, b.E, b.coef2, bcoef2, b.coef1, blk.spat_covn_dw[0].weight, dE, part11, _P_SDW, B * T,
-             b.Hi, b.Wi, mid, s, dcode, st)
+             b.Hi, b.Wi, mid, s, dcode, st, _tag="sdw_bwd", _bytes=(2 * Mo + 2 * Mi) * mid * es)
         del da
         bcoef1 = _bn_bwd(part11, _P_SDW, 11, 0, Mi, blk.conv_pw[1].bn, grads, mid, st, dev)
         dws = torch.empty_like(blk.spat_covn_dw[0].weight)
         call("dwn_dw_wgrad_finalize", part11, _P_SDW, 11, 2, 9, dws, mid, st)
         grads[blk.spat_covn_dw[0].weight] = dws
-        call("dwn_bn_bwd_apply", dE, b.E, b.coef1, bcoef1, Mi, mid, dcode, st)
+        call("dwn_bn_bwd_apply", dE, b.E, b.coef1, bcoef1, Mi, mid, dcode, st, _tag="bn_bwd_apply", _bytes=3 * Mi * mid * es)
         # point-wise expansion: dgrad + split-K wgrad
         wpw = blk.conv_pw[0].weight
         dXpw = _empty((Mi, ci), torch.float32, dev)
         gemm(st, dtype=dcode, A=dE, B=_shadow(wpw) if bf else wpw, b_mn=1, lda=mid, ldb=ci, M=Mi, N=ci, K=mid, Z=1,
-             D=dXpw, d_dtype=F32, ldd=ci)
+             D=dXpw, d_dtype=F32, ldd=ci, _tag="pw_dgrad", _bytes=Mi * mid * es + mid * ci * es + Mi * ci * 4)
         tiles = math.ceil(mid / 128) * math.ceil(ci / 256)
         Zs = _split_k(Mi, tiles)
         rows = Mi // Zs
         wpart = _empty((Zs, mid, ci), torch.float32, dev)
         gemm(st, dtype=dcode, A=dE, B=b.Xb if bf else b.X, a_mn=1, b_mn=1, lda=mid, ldb=ci, a_zstride=rows * mid,
              b_zstride=rows * ci, a_zmode=1, b_zmode=1, M=mid, N=ci, K=rows, Z=Zs, D=wpart, d_dtype=F32, ldd=ci,
-             d_zstride=mid * ci)
+             d_zstride=mid * ci, _tag="pw_wgrad", _bytes=Mi * (mid + ci) * es + Zs * mid * ci * 4)
         dwpw = torch.empty_like(wpw)
         call("dwn_reduce_rows", wpart, Zs, mid * ci, dwpw, st)
         grads[wpw] = dwpw
         del dE
         dXin = _empty((Mi, ci), torch.float32, dev)
-        call("dwn_block_in_bwd", dXpw, dO, b.X, b.coef_sc, bcoef_sc, dXin, B, T, b.Hi, b.Wi, ci, co, s, st)
+        call("dwn_block_in_bwd", dXpw, dO, b.X, b.coef_sc, bcoef_sc, dXin, B, T, b.Hi, b.Wi, ci, co, s, st,
+             _tag="block_in_bwd", _bytes=Mi * ci * 12 + Mo * co * 4)
         dO = dXin
+        if dp is not None:
+            dp.reduce(grads, list(blk.parameters()))
 
     # ---------------- stem -----------------------------------------------------------------------
     stem_conv, stem_bn = mod.core.stem[0], mod.core.stem[1].bn
@@ -195,5 +222,8 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
     call("dwn_stem_bwd", dO, sv.x, part, _P, sv.stem.mom, stem_conv.weight, sv.stem.coef, dw, dgam, dbet, B, cin,
          sv.T * sv.H * sv.W, C0, st)
     grads[stem_conv.weight], grads[stem_bn.weight], grads[stem_bn.bias] = dw, dgam, dbet
+    if dp is not None:
+        dp.reduce(grads, [stem_conv.weight, stem_bn.weight, stem_bn.bias])
+        dp.finish(dev)
 
     return [grads.get(p) if p.requires_grad else None for p in mod.parameters()]

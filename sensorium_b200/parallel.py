@@ -1,0 +1,98 @@
+"""Data-parallel gradient exchange for DwiseNeuro training (BASELINE.json configs[2]).
+
+One process per GPU (``torch.distributed``, NCCL over NVLink 5 / NVSwitch).  The reference has no
+distributed path at all; this is DDP semantics: local BatchNorm statistics, gradients
+averaged over ranks.  The exchange is *bucketed and overlapped with backward*: ``engine_bwd.run_backward``
+hands every finished group of gradients to ``reduce()`` as soon as its kernels are enqueued — the ten readout
+weight gradients (95 % of the bytes) go first, as one ~65 MB all-reduce each, and overlap with the whole
+core backward; the ~190 small core/cortex gradients are coalesced into one flat bucket per block.
+Mice absent from a rank's batch contribute a zero bucket; a per-mouse "has-grad" flag is MAX-reduced so a
+mouse absent on *every* rank is skipped by the optimizer exactly like ``grad is None`` in the reference.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+_BIG = 1 << 20
+
+
+class DataParallelGrads:
+    def __init__(self, mod, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.works: List = []
+        self._post: List = []
+        self.mod = mod
+        params = list(mod.parameters())
+        self.param_mouse = torch.full((len(params),), -1, dtype=torch.int64)
+        index = {id(p): i for i, p in enumerate(params)}
+        for m, r in enumerate(mod.readouts):
+            for p in r.parameters():
+                self.param_mouse[index[id(p)]] = m
+        self.n_mice = len(mod.readouts)
+        self.active: Optional[torch.Tensor] = None
+        self._avg = dist.get_backend(group) == "nccl"  # gloo (CPU tests) has no ReduceOp.AVG
+        self._pm_dev = None
+        self.bytes_reduced = 0
+
+    def __deepcopy__(self, memo):
+        return None  # copies of the module (ModelEma) are not trained: no exchange state to carry
+
+    @staticmethod
+    def attach(mod, group=None) -> "DataParallelGrads":
+        """Broadcast rank 0's parameters / buffers and enable the overlapped gradient exchange."""
+        with torch.no_grad():
+            for t in mod.state_dict().values():
+                dist.broadcast(t, src=0, group=group)
+        mod._dp = DataParallelGrads(mod, group)
+        return mod._dp
+
+    # called by engine_bwd.run_backward ---------------------------------------------------------------
+    def begin(self, local_live: List[bool], dev) -> None:
+        self.bytes_reduced = 0
+        flags = torch.tensor([1 if v else 0 for v in local_live], dtype=torch.int32).to(dev, non_blocking=True)
+        self.works.append(dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group, async_op=True))
+        self._flags = flags
+
+    def reduce(self, grads: Dict[torch.Tensor, torch.Tensor], keys) -> None:
+        keys = [k for k in keys if grads.get(k) is not None]
+        small = []
+        for k in keys:
+            g = grads[k]
+            if g.numel() >= _BIG:
+                self.works.append(self._allreduce_mean(g))
+                self.bytes_reduced += g.numel() * 4
+            else:
+                small.append(k)
+        if small:
+            flat = torch.cat([grads[k].reshape(-1) for k in small])
+            self.works.append(self._allreduce_mean(flat))
+            self.bytes_reduced += flat.numel() * 4
+            off = 0
+            for k in small:
+                n = grads[k].numel()
+                grads[k] = flat[off:off + n].view(grads[k].shape)
+                off += n
+
+    def _allreduce_mean(self, t):
+        if self._avg:
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._post.append(t)
+        return w
+
+    def finish(self, dev) -> None:
+        for w in self.works:
+            w.wait()  # stream-level wait: the compute stream waits for the NCCL stream, the host does not block
+        self.works.clear()
+        for t in self._post:
+            t.mul_(1.0 / self.world)
+        self._post.clear()
+        if self._pm_dev is None or self._pm_dev.device != dev:
+            self._pm_dev = self.param_mouse.to(dev)
+        pm = self._pm_dev
+        one = torch.ones((), dtype=torch.int32, device=dev)
+        self.active = torch.where(pm >= 0, self._flags[pm.clamp(min=0)], one).to(torch.int32).contiguous()

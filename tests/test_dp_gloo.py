@@ -1,0 +1,66 @@
+"""CPU, world_size 2 over gloo: the bucketed gradient exchange of sensorium_b200.parallel (host logic of the N>1 path):
+big tensors reduced individually, small ones coalesced into one flat bucket, result == mean over ranks, and the
+per-mouse has-grad flags are MAX-reduced so a mouse absent everywhere stays inactive."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sensorium_b200 import DwiseNeuro
+    from sensorium_b200.parallel import DataParallelGrads
+    torch.manual_seed(rank)  # different weights per rank before attach
+    net = DwiseNeuro(readout_outputs=(5, 4, 3), core_features=(8,), spatial_strides=(1,), expansion_ratio=2,
+                     se_reduce_ratio=4, cortex_features=(8,), groups=2)
+    dp = DataParallelGrads.attach(net)
+    w0 = net.core.stem[0].weight.detach().clone()
+    params = list(net.parameters())
+    g = torch.Generator().manual_seed(100 + rank)
+    grads = {p: torch.randn(p.shape, generator=g) for p in params}
+    big = torch.randn(1 << 20, generator=g)
+    grads["big"] = big.clone()
+    local = {k: v.clone() for k, v in grads.items()}
+    live = [rank == 0, False, True]  # mouse 0 only on rank 0, mouse 1 nowhere, mouse 2 everywhere
+    dp.begin(live, torch.device("cpu"))
+    dp.reduce(grads, list(grads.keys()))
+    dp.finish(torch.device("cpu"))
+    # reference: gather every rank's local grads
+    ok = True
+    for k in local:
+        bucket = [torch.zeros_like(local[k]) for _ in range(world)]
+        dist.all_gather(bucket, local[k])
+        mean = sum(bucket) / world
+        ok &= torch.allclose(grads[k], mean, atol=1e-6)
+    idx = {id(p): i for i, p in enumerate(params)}
+    act = dp.active.tolist()
+    m0 = idx[id(net.readouts[0].layer[1].weight)]
+    m1 = idx[id(net.readouts[1].layer[1].weight)]
+    m2 = idx[id(net.readouts[2].layer[1].bias)]
+    ok &= act[m0] == 1 and act[m1] == 0 and act[m2] == 1 and act[idx[id(net.core.stem[0].weight)]] == 1
+    q.put((rank, bool(ok), w0))
+    dist.destroy_process_group()
+
+
+def test_bucketed_exchange_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res)
+    assert torch.equal(res[0][2], res[1][2])  # attach() broadcast rank 0's weights

@@ -1,0 +1,361 @@
+"""GPU parity tests (-m gpu): the CUDA path (through the C ABI) against the oracle and the committed golden fixtures.
+
+Tolerances (BASELINE.json north_star): fp32 mode <= 1e-4 relative; bf16 mode <= 2e-2 relative with per-neuron
+single-trial correlation within 1e-3; integer / index work bit-exact."""
+import copy
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dwiseneuro_oracle as O
+from tests.shapes import TINY_KW, TINY_OUTS, TRUE_BATCH_KW
+
+pytestmark = pytest.mark.gpu
+FP32_TOL, BF16_TOL = 1e-4, 2e-2
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _tiny(dev, seed=0):
+    from sensorium_b200 import DwiseNeuro
+    from sensorium_b200.utils import init_weights
+    torch.manual_seed(seed)
+    net = DwiseNeuro(readout_outputs=TINY_OUTS, **TINY_KW)
+    init_weights(net)
+    return net.to(dev)
+
+
+def _corr_gap(pred, ref, target):
+    """|corr(pred, target) - corr(ref, target)| per neuron (metrics.py:11-31 semantics)."""
+    a = O.corr(pred.permute(1, 0, 2).reshape(pred.shape[1], -1), target.permute(1, 0, 2).reshape(pred.shape[1], -1))
+    b = O.corr(ref.permute(1, 0, 2).reshape(pred.shape[1], -1), target.permute(1, 0, 2).reshape(pred.shape[1], -1))
+    return float((a - b).abs().max())
+
+
+def test_tiny_golden_forward_loss_grads(dev, golden_dir):
+    from sensorium_b200.losses import MicePoissonLoss
+    g = torch.load(golden_dir / "tiny_forward_backward.pt", weights_only=False)
+    x = O.synthetic_clip(4, 16, 32, seed=0).to(dev)
+    tg, w = O.synthetic_targets(4, TINY_OUTS, 16, seed=1)
+    tgd, wd = [t.to(dev) for t in tg], w.to(dev)
+    for mode, tol in (("fp32", FP32_TOL), ("bf16", BF16_TOL)):
+        net = _tiny(dev)
+        net.precision = mode
+        net.eval()
+        with torch.no_grad():
+            ev = net(x)
+        for a, b in zip(ev, g["eval_out"]):
+            assert rel(a.cpu(), b) < tol
+        net.train()
+        torch.manual_seed(5)
+        tr = net(x)
+        for a, b in zip(tr, g["train_out"]):
+            assert rel(a.detach().cpu(), b) < tol
+        loss = MicePoissonLoss()(tr, (tgd, wd))
+        assert abs(float(loss) - float(g["loss"])) / abs(float(g["loss"])) < tol
+        loss.backward()
+        gmax = max(float(v.abs().max()) for v in g["grads"].values())
+        for k, p in net.named_parameters():
+            if k in g["none_grads"]:
+                assert p.grad is None, k
+                continue
+            err = float((p.grad.cpu() - g["grads"][k]).abs().max())
+            # biases in front of a batch-stat BatchNorm have an analytically zero gradient: absolute floor
+            assert err <= (3 if mode == "bf16" else 1) * tol * max(float(g["grads"][k].abs().max()), 1e-3 * gmax), k
+        for k, v in g["running"].items():
+            got = net.state_dict()[k].cpu()
+            if v.dtype == torch.int64:
+                assert torch.equal(got, v), k           # num_batches_tracked: bit-exact
+            else:
+                assert rel(got, v) < tol, k
+        if mode == "bf16":
+            for m in range(len(TINY_OUTS)):
+                assert _corr_gap(tr[m].detach().cpu(), g["train_out"][m], tg[m] + 0.1 * g["train_out"][m]) < 1e-3
+
+
+def test_c1_full_architecture_golden(dev, golden_dir):
+    """BASELINE configs[0]: true_batch_001 architecture, batch 1, 16x64x64 clip, single-mouse readout."""
+    from sensorium_b200 import DwiseNeuro, constants
+    from sensorium_b200.utils import init_weights
+    g = torch.load(golden_dir / "c1_forward_index0.pt", weights_only=False)
+    torch.manual_seed(0)
+    net = DwiseNeuro(readout_outputs=constants.num_neurons, **TRUE_BATCH_KW)
+    init_weights(net)
+    net = net.to(dev).eval()
+    x = O.synthetic_clip(1, 16, 64, seed=0).to(dev)
+    with torch.no_grad():
+        y32 = net(x, 0)
+        assert y32.shape == (1, 7863, 16) and y32.dtype == torch.float32
+        assert rel(y32.cpu(), g["out_index0"]) < FP32_TOL
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y16 = net(x, 0)
+        assert rel(y16.cpu(), g["out_index0"]) < BF16_TOL
+        # index / list consistency and batch invariance of the eval graph (windows can be batched, predictors.py)
+        full = net(x)
+        assert len(full) == 10 and torch.equal(full[0], y32)
+        x3 = torch.cat([x, O.synthetic_clip(2, 16, 64, seed=7).to(dev)])
+        y3 = net(x3, 0)
+        assert rel(y3[:1].cpu(), g["out_index0"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,T,HW,seed", [(3, 8, 16, 1), (2, 16, 32, 2)])
+def test_train_step_vs_oracle_shared_rng(dev, mode, B, T, HW, seed):
+    """Ragged shapes (odd batch, T != 16, odd neuron counts); drop-path and Dropout1d masks come from the same torch
+    RNG calls as the reference, so a shared seed gives the same masks."""
+    net = _tiny(dev, seed)
+    for n_, p in net.named_parameters():  # non-trivial BN affine / biases
+        if p.dim() == 1:
+            torch.nn.init.uniform_(p, 0.5, 1.5) if n_.endswith("bn.weight") else torch.nn.init.uniform_(p, -0.3, 0.3)
+    net.train()
+    net.precision = mode
+    x = O.synthetic_clip(B, T, HW, seed=seed).to(dev)
+    tg, w = O.synthetic_targets(B, TINY_OUTS, T, seed=seed + 1)
+    tg, w = [t.to(dev) for t in tg], w.to(dev)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    names = [k for k, _ in net.named_parameters()]
+    for k in names:
+        sd[k].requires_grad_(True)
+    cfg = O.make_cfg(TINY_OUTS, **TINY_KW)
+    torch.manual_seed(11)
+    ref = O.dwiseneuro_forward(x, sd, cfg, None, True)
+    ref_loss = O.mice_poisson_loss(ref, tg, w)
+    ref_loss.backward()
+    torch.manual_seed(11)
+    out = net(x)
+    loss = O.mice_poisson_loss(out, tg, w)
+    loss.backward()
+    tol = FP32_TOL if mode == "fp32" else BF16_TOL
+    for a, b in zip(out, ref):
+        assert rel(a, b) < tol
+    gmax = max(float(sd[k].grad.abs().max()) for k in names if sd[k].grad is not None)
+    for k, p in net.named_parameters():
+        if sd[k].grad is None:
+            assert p.grad is None
+            continue
+        err = float((p.grad - sd[k].grad).abs().max())
+        assert err <= (4 if mode == "bf16" else 1) * tol * max(float(sd[k].grad.abs().max()), 1e-3 * gmax), k
+
+
+def test_loss_kernels_and_absent_mice(dev):
+    from sensorium_b200.losses import MicePoissonLoss
+    torch.manual_seed(0)
+    outs = (33, 20, 7)
+    preds = [torch.rand(5, n, 16, device=dev) * 3 + 0.01 for n in outs]
+    for p in preds:
+        p.requires_grad_(True)
+    tg, w = O.synthetic_targets(5, outs, 16, seed=3)
+    w[:, 1] = 0  # mouse 1 absent
+    w[:, 0] = torch.tensor([0.5, 0, 1, 0, 0.25])
+    w[:, 2] = torch.tensor([0, 1, 0, 0, 0.75])
+    tg, w = [t.to(dev) for t in tg], w.to(dev)
+    loss = MicePoissonLoss()(preds, (tg, w))
+    loss.backward()
+    ref_p = [p.detach().clone().requires_grad_(True) for p in preds]
+    ref = O.mice_poisson_loss(ref_p, tg, w)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) / abs(float(ref)) < 1e-6
+    assert preds[1].grad is None and ref_p[1].grad is None
+    for a, b in ((preds[0], ref_p[0]), (preds[2], ref_p[2])):
+        assert rel(a.grad, b.grad) < 1e-6
+        assert float(a.grad[3].abs().max()) == 0.0  # sample 3 is masked for both mice: exactly zero
+
+
+def test_fused_adamw_and_ema_golden(dev, golden_dir):
+    from sensorium_b200.ema import ModelEma
+    from sensorium_b200.optim import FusedAdamW
+    a = torch.load(golden_dir / "adamw_steps.pt", weights_only=False)
+    p = torch.nn.Parameter(a["p0"].clone().to(dev))
+    q = torch.nn.Parameter(torch.ones(7, device=dev))  # never receives a gradient: must stay untouched
+    opt = FusedAdamW([p, q], lr=a["lr"], weight_decay=a["wd"])
+    for i, g in enumerate(a["grads"]):
+        p.grad = g.clone().to(dev)
+        opt.step()
+        assert rel(p.detach().cpu(), a["traj"][i]) < 1e-6
+    assert torch.equal(q.detach().cpu(), torch.ones(7)) and int(opt.state[q]["step"]) == 0 and int(opt.state[p]["step"]) == 3
+    # EMA over every state entry, int64 buffers through fp32 with truncation (ema.py:49-55)
+    g = torch.load(golden_dir / "ema_update.pt", weights_only=False)
+    from sensorium_b200 import DwiseNeuro
+    net = DwiseNeuro(readout_outputs=(5, 4), core_features=(8,), spatial_strides=(1,), expansion_ratio=2,
+                     se_reduce_ratio=4, cortex_features=(8,), groups=2)
+    net.load_state_dict(g["before"])
+    net = net.to(dev)
+    ema = ModelEma(net, decay=g["decay"])
+    net.load_state_dict(g["model"])
+    ema.update(net)
+    for k, v in ema.ema.state_dict().items():
+        if v.dtype == torch.int64:
+            assert torch.equal(v.cpu(), g["after"][k]), k
+        else:
+            assert rel(v.cpu(), g["after"][k]) < 1e-6 or float(g["after"][k].abs().max()) == 0.0, k
+
+
+def test_distill_fill_golden(dev, golden_dir):
+    from sensorium_b200.argus_models import MouseModel
+    d = torch.load(golden_dir / "distill_fill.pt", weights_only=False)
+    mm = MouseModel.__new__(MouseModel)
+    mm.distill_ratio = d["ratio"]
+    teacher = [t.to(dev) for t in d["teacher"]]
+    mm.distill_model = lambda inp: teacher
+    tg = [t.clone().to(dev) for t in d["targets_in"]]
+    w = d["weights_in"].clone().to(dev)
+    mm.add_distill_predictions(None, (tg, w))
+    assert rel(w.cpu(), d["weights_out"]) < 1e-6
+    for a, b in zip(tg, d["targets_out"]):
+        assert torch.equal(a.cpu(), b)
+
+
+def test_window_kernels_golden(dev, golden_dir):
+    """Integer index work of the predictor is bit-exact: gather == fancy indexing, blend == reference loop."""
+    from sensorium_b200._lib import call
+    g = torch.load(golden_dir / "predictor_blend.pt", weights_only=False)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    inputs = O.stack_inputs(g["video"], g["behavior"], g["pupil"]).to(dev)
+    Cn, L, H, W = inputs.shape
+    size, step, behind = 16, 2, 30
+    nwin = L - behind
+    clips = torch.empty(nwin, Cn, size, H, W, device=dev)
+    call("dwn_window_gather", inputs, clips, Cn, L, H * W, size, step, behind, nwin, st)
+    for wi in (0, 5, nwin - 1):
+        idx = O.make_window_indexes(behind + wi, size, step)
+        assert torch.equal(clips[wi], inputs[:, idx])
+    n_out = g["n_out"]
+    feat = clips[:, :, :, 20:24, 30:34].mean((1, 3, 4))                       # (nwin, 16)
+    preds = (feat[:, None, :] * torch.arange(1, n_out + 1, device=dev)[None, :, None]).float().contiguous()
+    for blend in ("ones", "linear"):
+        bw = torch.ones(size, device=dev) if blend == "ones" else torch.linspace(0, 1, size, dtype=torch.float64).float().to(dev)
+        out = torch.empty(n_out, L, device=dev)
+        call("dwn_window_blend", preds, bw, out, n_out, L, size, step, 0, nwin, n_out * size, st)
+        assert rel(out.cpu(), g["responses"][blend]) < 1e-5
+        assert float(out[:, 1].abs().max()) == float(g["responses"][blend][:, 1].abs().max())
+
+
+def test_predictor_end_to_end(dev, tmp_path):
+    """Batched device predictor == the reference's per-window loop (oracle.predict_trial) on a real (tiny) model."""
+    from sensorium_b200.argus_models import MouseModel
+    from sensorium_b200.predictors import Predictor
+    from sensorium_b200.utils import init_weights
+    kw = {"readout_outputs": (9, 6), "core_features": (8, 16), "spatial_strides": (2, 2), "expansion_ratio": 2,
+          "se_reduce_ratio": 4, "cortex_features": (16,), "groups": 2}
+    params = {"nn_module": ("dwiseneuro", kw), "loss": None, "optimizer": None, "device": "cuda:0",
+              "frame_stack": {"size": 16, "step": 2, "position": "last"},
+              "inputs_processor": ("stack_inputs", {"size": (64, 64), "pad_fill_value": 0.0}),
+              "responses_processor": ("identity", {}), "amp": True, "iter_size": 1}
+    torch.manual_seed(3)
+    m = MouseModel(params)
+    init_weights(m.nn_module)
+    with torch.no_grad():  # non-trivial running stats
+        for k, v in m.nn_module.state_dict().items():
+            if "running_mean" in k:
+                v.uniform_(-0.2, 0.2)
+            if "running_var" in k:
+                v.uniform_(0.5, 1.5)
+    path = tmp_path / "model-001-0.100000.pth"
+    m.save(path)
+    pr = Predictor(path, device="cuda:0", blend_weights="ones", window_batch=7)
+    rs = np.random.RandomState(0)
+    L = 41
+    video = rs.randint(0, 256, (36, 64, L)).astype(np.uint8)
+    beh, pup = rs.rand(2, L).astype(np.float32), rs.rand(2, L).astype(np.float32)
+    got = pr.predict_trial(video, beh, pup, 1)
+    assert got.shape == (6, L) and got.dtype == np.float32
+    sd = {k: v.detach().cpu() for k, v in m.nn_module.state_dict().items()}
+    cfg = O.make_cfg(kw["readout_outputs"], **{k: v for k, v in kw.items() if k != "readout_outputs"})
+    inputs = O.stack_inputs(torch.from_numpy(video), torch.from_numpy(beh), torch.from_numpy(pup))
+    with torch.no_grad():
+        want = O.predict_trial(lambda c: O.dwiseneuro_forward(c, sd, cfg, 1, False), inputs, 6, 16, 2, "ones")
+    assert rel(torch.from_numpy(got), want) < FP32_TOL
+    assert float(np.abs(got[:, :1]).max()) >= 0.0 and np.all(got[:, [1, 3]] == 0.0) == bool((want[:, [1, 3]] == 0).all())
+
+
+def test_mouse_model_train_step_and_determinism(dev):
+    """The public wrapper (argus_models.py:43-71 contract): host batch in, dict out, weights move, EMA follows,
+    absent mice keep their readouts untouched; two identical runs are bit-identical (deterministic reductions)."""
+    from sensorium_b200.argus_models import MouseModel
+    from sensorium_b200.ema import ModelEma
+    from sensorium_b200.utils import init_weights
+
+    def run():
+        params = {"nn_module": ("dwiseneuro", {"readout_outputs": TINY_OUTS, **TINY_KW}),
+                  "loss": ("mice_poisson", {}), "optimizer": ("AdamW", {"lr": 2e-3, "weight_decay": 0.05}),
+                  "device": "cuda:0", "amp": True, "iter_size": 1}
+        torch.manual_seed(0)
+        m = MouseModel(params)
+        init_weights(m.nn_module)
+        m.model_ema = ModelEma(m.nn_module, decay=0.9)
+        x = O.synthetic_clip(4, 16, 32, seed=0)
+        tg, w = O.synthetic_targets(4, TINY_OUTS, 16, seed=1)
+        w[:, 2] = 0
+        w[:, 0] = 1
+        losses = []
+        torch.manual_seed(9)
+        for _ in range(3):
+            out = m.train_step((x, (tg, w)), None)
+            losses.append(out["loss"])
+        return m, out, losses
+
+    m1, out, l1 = run()
+    m2, _, l2 = run()
+    assert set(out) == {"prediction", "target", "loss"} and len(out["prediction"]) == 3
+    assert l1 == l2 and all(math.isfinite(v) for v in l1) and l1[2] < l1[0]
+    for a, b in zip(m1.nn_module.state_dict().values(), m2.nn_module.state_dict().values()):
+        assert torch.equal(a, b)
+    fresh = _tiny(dev)
+    assert torch.equal(m1.nn_module.readouts[2].layer[1].weight, fresh.readouts[2].layer[1].weight)  # absent mouse
+    assert not torch.equal(m1.nn_module.readouts[0].layer[1].weight, fresh.readouts[0].layer[1].weight)
+    assert int(m1.nn_module.core.stem[1].bn.num_batches_tracked) == 3
+    v = m1.val_step((O.synthetic_clip(2, 16, 32, seed=5), O.synthetic_targets(2, TINY_OUTS, 16, seed=6)), None)
+    assert math.isfinite(v["loss"])
+
+
+def test_full_size_properties(dev):
+    """BASELINE configs[1] shape (true_batch_001, batch 32 is benchmarked; batch 8 here to bound test time):
+    size-independent properties instead of an oracle run."""
+    from sensorium_b200 import DwiseNeuro, constants
+    from sensorium_b200.losses import MicePoissonLoss
+    from sensorium_b200.utils import init_weights
+    torch.manual_seed(0)
+    net = DwiseNeuro(readout_outputs=constants.num_neurons, **TRUE_BATCH_KW)
+    init_weights(net)
+    net = net.to(dev).train()
+    B = 8
+    x = O.synthetic_clip(B, 16, 64, seed=3).to(dev)
+    tg, w = O.synthetic_targets(B, constants.num_neurons, 16, seed=4)
+    tg, w = [t.to(dev) for t in tg], w.to(dev)
+    outs = []
+    for _ in range(2):
+        net.zero_grad(set_to_none=True)
+        torch.manual_seed(1)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            pred = net(x)
+            loss = MicePoissonLoss()(pred, (tg, w))
+        loss.backward()
+        outs.append((float(loss), [p.detach().clone() for p in pred],
+                     {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
+        with torch.no_grad():  # restore running stats so both runs are identical
+            pass
+    assert all(p.shape == (B, n, 16) and bool(torch.isfinite(p).all()) and float(p.min()) >= 0 for p, n in
+               zip(outs[0][1], constants.num_neurons))
+    # determinism of the forward pass for identical inputs / masks
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
+    live = (w != 0).any(0).tolist()
+    for m, lv in enumerate(live):
+        has = f"readouts.{m}.layer.1.weight" in outs[0][2]
+        assert has == lv
+    # gradients of biases in front of batch-stat BN vanish (analytic property), everything finite
+    gmax = max(float(g.abs().max()) for g in outs[0][2].values())
+    assert all(bool(torch.isfinite(g).all()) for g in outs[0][2].values())
+    assert float(outs[0][2]["core.blocks.5.conv_pwl.1.bn.bias"].abs().max()) < 1e-2 * gmax
