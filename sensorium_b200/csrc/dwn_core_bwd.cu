@@ -5,6 +5,7 @@
 // (sum dy, sum dy*xhat) of the *next* BN in the chain, so each tensor is read once per stage.
 #include "dwn_common.cuh"
 #include "dwn_reduce.cuh"
+#include "dwn_sdw_v3.cuh"
 #include <type_traits>
 
 // =================================================================================================
@@ -717,6 +718,41 @@ static int sdw_bwd_launch(const void* dsh, const void* s_raw, const void* e_raw,
   return 0;
 }
 
+template <int S>
+static int sdw_bwd_v3_launch(const void* dsh, const void* s_raw, const void* e_raw, const float* coef2,
+                             const float* bcoef2, const float* coef1, const float* wgt, void* dE, float* partial, int P,
+                             int NP, int H, int W, int C, cudaStream_t st) {
+  const int Wo = W / S;
+  int CC = 1024 / W;
+  if (CC > 128) CC = 128;
+  while (CC >= 8 && (C % CC != 0)) CC /= 2;
+  if (CC < 8 || C % CC != 0 || (CC / 4) * W != 256) return 1;
+  const int cvsh = ilog2_exact_b(CC / 8);
+  if (cvsh < 0 || Wo * (CC / 8) != 128 / S || W * (CC / 8) != 128) return 1;
+  const int THI = (H % 8 == 0) ? 8 : (H % 4 == 0 ? 4 : 0);
+  if (THI == 0) return 1;
+  const int nbsh = ilog2_exact_b(H / THI);
+  if (nbsh < 0) return 1;
+  const int NR = S == 1 ? THI + 2 : THI / 2 + 1;
+  const int RPI = 2 * S, NIT = (NR + RPI - 1) / RPI;
+  size_t sm = 2 * (size_t)NIT * 256 * 16 + (size_t)THI * 128 * 16 + ((size_t)NR * (Wo + 2) + 7) * CC * sizeof(float);
+  const size_t sm_red = (size_t)256 * 11 * 4 * sizeof(float);
+  if (sm_red > sm) sm = sm_red;
+  const int nchunks = C / CC;
+  dim3 grid(P * nchunks), block(256);
+#define LAUNCH(THI_)                                                                                               \
+  {                                                                                                                \
+    auto k = sdw_bwd_v3_kernel<S, THI_>;                                                                           \
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                                 \
+    k<<<grid, block, sm, st>>>((const bf16*)dsh, (const bf16*)s_raw, (const bf16*)e_raw, coef2, bcoef2, coef1, wgt, \
+                               (bf16*)dE, partial, NP, H, W, C, CC, nchunks, nbsh, cvsh);                          \
+  }
+  if (THI == 8) LAUNCH(8) else LAUNCH(4)
+#undef LAUNCH
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int dwn_sdw_bwd(const void* dsh, const void* s_raw, const void* e_raw, const float* coef2,
                            const float* bcoef2, const float* coef1, const float* wgt, void* dE, float* partial, int P,
                            int NP, int H, int W, int C, int stride, int dtype, void* stream) {
@@ -726,6 +762,10 @@ extern "C" int dwn_sdw_bwd(const void* dsh, const void* s_raw, const void* e_raw
     return stride == 1
                ? sdw_bwd_launch<float, 1>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st)
                : sdw_bwd_launch<float, 2>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st);
+  int rc = stride == 1
+               ? sdw_bwd_v3_launch<1>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st)
+               : sdw_bwd_v3_launch<2>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st);
+  if (rc <= 0) return rc;
   return stride == 1
              ? sdw_bwd_launch<bf16, 1>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st)
              : sdw_bwd_launch<bf16, 2>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st);

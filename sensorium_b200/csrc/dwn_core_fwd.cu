@@ -2,6 +2,7 @@
 // Reference semantics: /root/reference/src/models/dwiseneuro.py (line numbers cited per kernel).
 #include "dwn_common.cuh"
 #include "dwn_reduce.cuh"
+#include "dwn_sdw_v3.cuh"
 
 // =================================================================================================
 // input moments: sums and second moments of the 5 input channels (NCDHW fp32 input).
@@ -399,6 +400,46 @@ static int sdw_fwd_launch(const void* in, const float* coef, const float* wgt, v
   return 0;
 }
 
+// pipelined bf16 path (cp.async double buffering + FFMA2); returns 1 if the shape is not eligible
+template <int S>
+static int sdw_fwd_v3_launch(const void* in, const float* coef, const float* wgt, void* out, float* partial, int P, int NP,
+                             int H, int W, int C, cudaStream_t st) {
+  const int Ho = H / S, Wo = W / S;
+  int CC = 1024 / Wo;
+  if (CC > 128) CC = 128;
+  while (CC >= 8 && (C % CC != 0)) CC /= 2;
+  if (CC < 8 || C % CC != 0 || (CC / 4) * Wo != 256) return 1;
+  const int cvsh = ilog2_exact(CC / 8);
+  const int vpr = W * (CC / 8);  // 16-byte vectors per tile row
+  if (cvsh < 0 || (vpr != 128 && vpr != 256)) return 1;
+  const int rpi = 256 / vpr;
+  const int THO = S == 1 ? (Ho % 8 == 0 ? 8 : (Ho % 4 == 0 ? 4 : 0)) : (Ho % 2 == 0 ? 2 : 0);
+  if (THO == 0) return 1;
+  const int NR = (THO - 1) * S + 3;
+  if (NR % rpi != 0) return 1;
+  const int nbsh = ilog2_exact(Ho / THO);
+  if (nbsh < 0) return 1;
+  const size_t nvec = (size_t)NR * vpr;
+  size_t sm = 2 * nvec * 16 + (size_t)NR * (W + 2) * CC * sizeof(float);
+  const int nchunks = C / CC;
+  dim3 grid(P * nchunks), block(256);
+#define LAUNCH(THO_, RPI_)                                                                                     \
+  {                                                                                                            \
+    auto k = sdw_fwd_v3_kernel<S, THO_, RPI_>;                                                                 \
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                             \
+    k<<<grid, block, sm, st>>>((const bf16*)in, coef, wgt, (bf16*)out, partial, NP, H, W, C, CC, nchunks, nbsh, cvsh); \
+  }
+  if constexpr (S == 1) {
+    if (THO == 8) { if (rpi == 2) LAUNCH(8, 2) else LAUNCH(8, 1) } else { if (rpi == 2) LAUNCH(4, 2) else LAUNCH(4, 1) }
+  } else {
+    if (rpi != 1) return 1;
+    LAUNCH(2, 1)
+  }
+#undef LAUNCH
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int dwn_sdw_fwd(const void* in, const float* coef, const float* wgt, void* out, float* partial, int P, int NP,
                            int H, int W, int C, int stride, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -407,6 +448,9 @@ extern "C" int dwn_sdw_fwd(const void* in, const float* coef, const float* wgt, 
   if (dtype == DWN_DT_F32)
     return stride == 1 ? sdw_fwd_launch<float, 1>(in, coef, wgt, out, partial, P, NP, H, W, C, st)
                        : sdw_fwd_launch<float, 2>(in, coef, wgt, out, partial, P, NP, H, W, C, st);
+  int rc = stride == 1 ? sdw_fwd_v3_launch<1>(in, coef, wgt, out, partial, P, NP, H, W, C, st)
+                       : sdw_fwd_v3_launch<2>(in, coef, wgt, out, partial, P, NP, H, W, C, st);
+  if (rc <= 0) return rc;
   return stride == 1 ? sdw_fwd_launch<bf16, 1>(in, coef, wgt, out, partial, P, NP, H, W, C, st)
                      : sdw_fwd_launch<bf16, 2>(in, coef, wgt, out, partial, P, NP, H, W, C, st);
 }

@@ -1,0 +1,422 @@
+// Pipelined bf16 spatial depth-wise kernels (forward + backward), sm_100a.
+//   * raw bf16 tiles are streamed global -> shared with cp.async (no register staging) and double-buffered, so the
+//     DRAM latency of tile k+1 is hidden behind the BN+SiLU pass and the stencil of tile k;
+//   * the stencil runs on packed fp32x2 FMAs (FFMA2), two channels per instruction;
+//   * grid is 1-D with the channel chunk fastest, so CTAs that share a (plane, band) tile are co-resident and each
+//     128-byte line of E_raw is fetched from HBM once.
+#pragma once
+#include "dwn_common.cuh"
+#include "dwn_reduce.cuh"
+#include <type_traits>
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;  // src-size 0 -> 16 bytes of zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+typedef unsigned long long f32x2;  // two packed fp32 (low word = first element)
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ void ffma2(f32x2& d, f32x2 a, f32x2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void fadd2(f32x2& d, f32x2 a) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(d) : "l"(a)); }
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// =================================================================================================
+// forward:  S_raw = dwconv3x3_stride_S( SiLU(BN1(E_raw)) ),  + per-channel sum / sumsq partials
+//   RPI = tile rows covered by one pass of the 256 threads over the raw tile (256 / (W * CC/8), 1 or 2).
+//   All per-vector addresses are loop-invariant per thread plus a compile-time multiple of a per-row step.
+// =================================================================================================
+template <int S, int THO, int RPI>
+__global__ void __launch_bounds__(256, 2)
+sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, const float* __restrict__ wgt,
+                  bf16* __restrict__ out, float* __restrict__ partial, int NP, int H, int W, int C, int CC, int nchunks,
+                  int nbsh, int cvsh) {
+  constexpr int NR = (THO - 1) * S + 3;
+  constexpr int NIT = NR / RPI;
+  static_assert(NR % RPI == 0, "tile rows must be a multiple of the rows per pass");
+  extern __shared__ __align__(16) unsigned char smem_v3[];
+  const int Ho = H / S, Wo = W / S, WP = W + 2;
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x % nchunks, worker = blockIdx.x / nchunks, nworkers = gridDim.x / nchunks;
+  const int c0 = chunk * CC;
+  const int cvn = CC >> 3;
+  constexpr int NVEC = NR * (256 / RPI);  // 16-byte vectors per raw tile (W*cvn == 256/RPI)
+  bf16* raw0 = reinterpret_cast<bf16*>(smem_v3);
+  bf16* raw1 = raw0 + (size_t)NVEC * 8;
+  float* act = reinterpret_cast<float*>(raw1 + (size_t)NVEC * 8);
+  // ---- loop-invariant coordinates of this thread inside one pass
+  const int vpr = 256 / RPI;                       // vectors per tile row
+  const int r_first = tid / vpr;                   // 0 (RPI=1) or 0/1 (RPI=2)
+  const int wq = (tid & (vpr - 1)) >> cvsh;
+  const int lcv = tid & (cvn - 1);
+  const int act_off0 = (r_first * WP + wq + 1) * CC + lcv * 8;
+  const int act_step = RPI * WP * CC;
+  const long g_off0 = ((long)r_first * W + wq) * C + c0 + lcv * 8;
+  const long g_step = (long)RPI * W * C;
+  f32x2 lp0[4], lp1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a0, a1, b0, b1;
+    BnSilu<bf16>::prep(coef[c0 + lcv * 8 + 2 * j], coef[C + c0 + lcv * 8 + 2 * j], a0, b0);
+    BnSilu<bf16>::prep(coef[c0 + lcv * 8 + 2 * j + 1], coef[C + c0 + lcv * 8 + 2 * j + 1], a1, b1);
+    lp0[j] = pk2(a0, a1);
+    lp1[j] = pk2(b0, b1);
+  }
+  const int cqn = CC >> 2;
+  const int cq = tid % cqn, wo = tid / cqn;
+  const float* act_rd = act + (wo * S) * CC + cq * 4;
+  const int row_step = WP * CC;
+  f32x2 w2[9][2];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    w2[k][0] = pk2(wgt[(c0 + cq * 4 + 0) * 9 + k], wgt[(c0 + cq * 4 + 1) * 9 + k]);
+    w2[k][1] = pk2(wgt[(c0 + cq * 4 + 2) * 9 + k], wgt[(c0 + cq * 4 + 3) * 9 + k]);
+  }
+  f32x2 st2[2][2] = {{0ull, 0ull}, {0ull, 0ull}};
+  for (int i = tid; i < NR * 2 * CC; i += 256) {  // zero halo columns once
+    const int r = i / (2 * CC), rem = i % (2 * CC);
+    act[(r * WP + ((rem / CC) ? (W + 1) : 0)) * CC + (rem % CC)] = 0.f;
+  }
+  const int nbm = (1 << nbsh) - 1;
+  const int ntiles = NP << nbsh;
+  const long plane = (long)H * W * C;
+  auto issue = [&](int t, bf16* buf) {
+    const int p = t >> nbsh, hi0 = (t & nbm) * (THO * S) - 1;
+    const bf16* src = in + (long)p * plane + (long)hi0 * W * C + g_off0;
+    bf16* dst = buf + tid * 8;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int hi = hi0 + r_first + it * RPI;
+      const bool ok = (unsigned)hi < (unsigned)H;
+      cp_async16(dst + it * 2048, ok ? src + it * g_step : in, ok);
+    }
+  };
+  int t = worker, k = 0;
+  if (t < ntiles) issue(t, raw0);
+  cp_async_commit();
+  for (; t < ntiles; t += nworkers, ++k) {
+    const bf16* cur = (k & 1) ? raw1 : raw0;
+    bf16* nxt = (k & 1) ? raw0 : raw1;
+    if (t + nworkers < ntiles) issue(t + nworkers, nxt);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();  // raw tile landed for everybody; everybody is done with the previous act tile
+    const int p = t >> nbsh, ho0 = (t & nbm) * THO;
+    const int hi0 = ho0 * S - 1;
+    // ---- BN1 + SiLU pass: raw bf16 -> act fp32 (zero rows outside the image: padding applies after the activation)
+    {
+      const bf16* rp = cur + tid * 8;
+      float* dst = act + act_off0;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int hi = hi0 + r_first + it * RPI;
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+        if ((unsigned)hi < (unsigned)H) {
+          const uint4 q = *reinterpret_cast<const uint4*>(rp + it * 2048);
+          const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float lo, hi2;
+            unpack_bf16x2(qq[j], lo, hi2);
+            f32x2 h = lp1[j];
+            ffma2(h, pk2(lo, hi2), lp0[j]);        // h = x*p0 + p1
+            float h0, h1;
+            upk2(h, h0, h1);
+            f32x2 y = h;
+            ffma2(y, h, pk2(tanh_approx(h0), tanh_approx(h1)));  // y = h + h*tanh(h)
+            upk2(y, v[2 * j], v[2 * j + 1]);
+          }
+          o0 = make_float4(v[0], v[1], v[2], v[3]);
+          o1 = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        *reinterpret_cast<float4*>(dst + it * act_step) = o0;
+        *reinterpret_cast<float4*>(dst + it * act_step + 4) = o1;
+      }
+    }
+    __syncthreads();
+    // ---- stencil: sliding 3-row register window, packed fp32x2 FMAs
+    f32x2 R[3][3][2];
+    auto load_row = [&](int r) {
+      const float* src = act_rd + r * row_step;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(src + kw * CC);
+        R[r % 3][kw][0] = q.x;
+        R[r % 3][kw][1] = q.y;
+      }
+    };
+    bf16* op = out + (((long)p * Ho + ho0) * Wo + wo) * C + c0 + cq * 4;
+    const long ostep = (long)Wo * C;
+    if (S == 1) { load_row(0); load_row(1); } else { load_row(0); }
+#pragma unroll
+    for (int hl = 0; hl < THO; ++hl) {
+      if (S == 1) { load_row(hl + 2); } else { load_row(2 * hl + 1); load_row(2 * hl + 2); }
+      f32x2 a0 = 0ull, a1 = 0ull;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          ffma2(a0, R[(hl * S + kh) % 3][kw][0], w2[kh * 3 + kw][0]);
+          ffma2(a1, R[(hl * S + kh) % 3][kw][1], w2[kh * 3 + kw][1]);
+        }
+      float o[4];
+      upk2(a0, o[0], o[1]);
+      upk2(a1, o[2], o[3]);
+      stq(op + hl * ostep, o);
+      fadd2(st2[0][0], a0);
+      fadd2(st2[0][1], a1);
+      ffma2(st2[1][0], a0, a0);
+      ffma2(st2[1][1], a1, a1);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  if (partial) {
+    float st[2][4];
+    upk2(st2[0][0], st[0][0], st[0][1]); upk2(st2[0][1], st[0][2], st[0][3]);
+    upk2(st2[1][0], st[1][0], st[1][1]); upk2(st2[1][1], st[1][2], st[1][3]);
+    block_reduce_channels<2, 4>(st, act, cqn, Wo, partial + (long)worker * 2 * C, C, c0);
+  }
+}
+
+// =================================================================================================
+// backward: dE_pre = SiLU'(BN1 E) * dwconv3x3^T( BN2bwd(dS_pre) ), dw[9], BN1-backward partial sums
+//   partial[P][11][C] = { sum dehat, sum dehat*xhat1, dw[0..8] }
+// The staged (output-sized) tile is Wo*CC/8 = 128/S vectors per row, i.e. RPI = 2*S rows per 256-thread pass.
+// =================================================================================================
+template <int S, int THI>
+__global__ void __launch_bounds__(256, 2)
+sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, const bf16* __restrict__ e_raw,
+                  const float* __restrict__ coef2, const float* __restrict__ bcoef2, const float* __restrict__ coef1,
+                  const float* __restrict__ wgt, bf16* __restrict__ dE, float* __restrict__ partial, int NP, int H, int W,
+                  int C, int CC, int nchunks, int nbsh, int cvsh) {
+  constexpr int NR = S == 1 ? THI + 2 : THI / 2 + 1;
+  constexpr int RPI = 2 * S;
+  constexpr int NIT = (NR + RPI - 1) / RPI;
+  constexpr int VPR = 256 / RPI;  // vectors per staged row
+  extern __shared__ __align__(16) unsigned char smem_v3[];
+  const int Ho = H / S, Wo = W / S, WP = Wo + 2;
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x % nchunks, worker = blockIdx.x / nchunks, nworkers = gridDim.x / nchunks;
+  const int c0 = chunk * CC;
+  const int cvn = CC >> 3;
+  constexpr int NVEC = NIT * 256;
+  constexpr int EVEC = THI * 128;  // E tile: THI rows x (W*CC/8 = 128) 16-byte vectors
+  bf16* rawD = reinterpret_cast<bf16*>(smem_v3);
+  bf16* rawS = rawD + (size_t)NVEC * 8;
+  bf16* rawE = rawS + (size_t)NVEC * 8;
+  float* tile = reinterpret_cast<float*>(rawE + (size_t)EVEC * 8);
+  float* sco = tile + (size_t)NR * WP * CC;
+  const int r_first = tid / VPR;
+  const int two = (tid & (VPR - 1)) >> cvsh;  // output column handled in the staging passes
+  const int lcv = tid & (cvn - 1);
+  const int cqn = CC >> 2;
+  const int cq = tid % cqn, wi = tid / cqn;
+  const int cch = c0 + cq * 4;
+  for (int i = tid; i < CC; i += 256) {
+    const int cc = c0 + i;
+    const float sc = coef2[cc], mu = coef2[2 * C + cc], rs = coef2[3 * C + cc];
+    const float k1 = bcoef2[cc], k2 = bcoef2[C + cc];
+    sco[i] = sc;
+    sco[CC + i] = sc * (k1 - mu * rs * k2);
+    sco[2 * CC + i] = sc * rs * k2;
+    float q0, q1;
+    BnSilu<bf16>::prep(coef1[cc], coef1[C + cc], q0, q1);
+    sco[3 * CC + i] = q0;
+    sco[4 * CC + i] = q1;
+    sco[5 * CC + i] = coef1[2 * C + cc];
+    sco[6 * CC + i] = coef1[3 * C + cc];
+  }
+  for (int i = tid; i < NR * WP * CC; i += 256) tile[i] = 0.f;  // halo columns stay zero
+  f32x2 w2[9][2];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    w2[k][0] = pk2(wgt[(cch + 0) * 9 + k], wgt[(cch + 1) * 9 + k]);
+    w2[k][1] = pk2(wgt[(cch + 2) * 9 + k], wgt[(cch + 3) * 9 + k]);
+  }
+  const bool odd_w = (wi & 1) != 0;
+  const int colA = (S == 1) ? 0 : (odd_w ? (wi + 1) / 2 : wi / 2);
+  const int colB = (wi - 1) / 2;
+  f32x2 st2[11][2];
+#pragma unroll
+  for (int q = 0; q < 11; ++q) { st2[q][0] = 0ull; st2[q][1] = 0ull; }
+  const int nbm = (1 << nbsh) - 1;
+  const int ntiles = NP << nbsh;
+  const int row_step = WP * CC;
+  const int tile_off0 = (r_first * WP + two + (S == 1 ? 1 : 0)) * CC + lcv * 8;
+  const long g_off0 = (long)two * C + c0 + lcv * 8;
+  const long orow = (long)Wo * C;
+  const long erow = (long)W * C;
+  auto issue = [&](int t) {
+    const int p = t >> nbsh, hi0 = (t & nbm) * THI;
+    const int ho_first = (S == 1) ? hi0 - 1 : hi0 / 2;
+    const long base = (long)p * Ho * orow + g_off0;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int r = r_first + it * RPI;
+      const int ho = ho_first + r;
+      const bool ok = (r < NR) && ((unsigned)ho < (unsigned)Ho);
+      const long off = ok ? base + (long)ho * orow : 0;
+      cp_async16(rawD + (size_t)(tid + it * 256) * 8, dsh + off, ok);
+      cp_async16(rawS + (size_t)(tid + it * 256) * 8, s_raw + off, ok);
+    }
+  };
+  // E tile staging: vector i = tid + it*256 -> row 2*it + (tid>>7), column vector tid&127
+  const int e_r0 = tid >> 7;
+  const long e_goff = (long)((tid & 127) >> cvsh) * C + c0 + lcv * 8;
+  int t = worker;
+  if (t < ntiles) issue(t);
+  cp_async_commit();
+  for (; t < ntiles; t += nworkers) {
+    const int p = t >> nbsh, hi0 = (t & nbm) * THI;
+    const int ho_first = (S == 1) ? hi0 - 1 : hi0 / 2;
+    bf16* dp = dE + (((long)p * H + hi0) * W + wi) * C + cch;
+    cp_async_wait<0>();
+    __syncthreads();  // raw dS/S tiles landed; previous stencil finished with `tile` and `rawE`
+    {  // E rows of this tile: in flight while the dS tile is transformed
+      const bf16* eb = e_raw + ((long)p * H + hi0 + e_r0) * erow + e_goff;
+#pragma unroll
+      for (int it = 0; it < THI / 2; ++it) cp_async16(rawE + (size_t)(tid + it * 256) * 8, eb + (long)(2 * it) * erow, true);
+      cp_async_commit();
+    }
+    // ---- BN2 backward on the staged tile: dS_raw = a*g - d*x - b (zero outside the image)
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int r = r_first + it * RPI;
+      if (r < NR) {
+        const int ho = ho_first + r;
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+        if ((unsigned)ho < (unsigned)Ho) {
+          const uint4 qg = *reinterpret_cast<const uint4*>(rawD + (size_t)(tid + it * 256) * 8);
+          const uint4 qx = *reinterpret_cast<const uint4*>(rawS + (size_t)(tid + it * 256) * 8);
+          const uint32_t gg[4] = {qg.x, qg.y, qg.z, qg.w}, xx[4] = {qx.x, qx.y, qx.z, qx.w};
+          const float* ca = sco + lcv * 8;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float g0, g1, x0, x1;
+            unpack_bf16x2(gg[j], g0, g1);
+            unpack_bf16x2(xx[j], x0, x1);
+            v[2 * j] = fmaf(ca[2 * j], g0, -fmaf(ca[2 * CC + 2 * j], x0, ca[CC + 2 * j]));
+            v[2 * j + 1] = fmaf(ca[2 * j + 1], g1, -fmaf(ca[2 * CC + 2 * j + 1], x1, ca[CC + 2 * j + 1]));
+          }
+          o0 = make_float4(v[0], v[1], v[2], v[3]);
+          o1 = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        float* dst = tile + tile_off0 + it * RPI * row_step;
+        *reinterpret_cast<float4*>(dst) = o0;
+        *reinterpret_cast<float4*>(dst + 4) = o1;
+      }
+    }
+    cp_async_wait<0>();  // E tile landed
+    __syncthreads();     // tile + E ready, raw dS/S buffers free
+    if (t + nworkers < ntiles) issue(t + nworkers);
+    cp_async_commit();
+    const bf16* esm = rawE + (size_t)wi * CC + cq * 4;  // row hl at + hl*W*CC
+    // ---- transposed stencil + weight gradient, one input row at a time (E row prefetched one ahead)
+    const float4 qa0 = *reinterpret_cast<const float4*>(sco + 3 * CC + cq * 4);
+    const float4 qa1 = *reinterpret_cast<const float4*>(sco + 4 * CC + cq * 4);
+    const float pa0[4] = {qa0.x, qa0.y, qa0.z, qa0.w}, pa1[4] = {qa1.x, qa1.y, qa1.z, qa1.w};
+    const float* tbase = tile + cq * 4 + ((S == 1) ? (wi + 2) * CC : 0);
+    auto row_body = [&](const int hl, auto par_c) {
+      constexpr int PAR = decltype(par_c)::value;
+      float e[4], ea[4], sg[4];
+      ldq(esm + hl * (W * CC), e);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ea[j] = BnSilu<bf16>::act_grad(e[j], pa0[j], pa1[j], sg[j]);
+      const f32x2 ea0 = pk2(ea[0], ea[1]), ea1 = pk2(ea[2], ea[3]);
+      f32x2 acc0 = 0ull, acc1 = 0ull;
+      if (S == 1) {
+        const float* trow = tbase + hl * row_step;  // tap (kh,kw) sits at trow + (2-kh)*row_step - kw*CC
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const float* tr = trow + (2 - kh) * row_step;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(tr - kw * CC);
+            ffma2(acc0, w2[kh * 3 + kw][0], q.x);
+            ffma2(acc1, w2[kh * 3 + kw][1], q.y);
+            ffma2(st2[2 + kh * 3 + kw][0], ea0, q.x);
+            ffma2(st2[2 + kh * 3 + kw][1], ea1, q.y);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          if ((PAR == 0) != (kh == 1)) continue;
+          const int r = (kh == 1) ? hl / 2 : (kh == 0 ? (hl + 1) / 2 : (hl - 1) / 2);
+          const float* tr = tbase + r * row_step;
+          {
+            const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(tr + colA * CC);
+            const f32x2 wa0 = odd_w ? w2[kh * 3 + 0][0] : w2[kh * 3 + 1][0];
+            const f32x2 wa1 = odd_w ? w2[kh * 3 + 0][1] : w2[kh * 3 + 1][1];
+            ffma2(acc0, wa0, q.x);
+            ffma2(acc1, wa1, q.y);
+            const f32x2 p0 = fmul2(ea0, q.x), p1 = fmul2(ea1, q.y);
+            fadd2(st2[2 + kh * 3 + 0][0], odd_w ? p0 : 0ull);
+            fadd2(st2[2 + kh * 3 + 0][1], odd_w ? p1 : 0ull);
+            fadd2(st2[2 + kh * 3 + 1][0], odd_w ? 0ull : p0);
+            fadd2(st2[2 + kh * 3 + 1][1], odd_w ? 0ull : p1);
+          }
+          if (odd_w) {
+            const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(tr + colB * CC);
+            ffma2(acc0, w2[kh * 3 + 2][0], q.x);
+            ffma2(acc1, w2[kh * 3 + 2][1], q.y);
+            ffma2(st2[2 + kh * 3 + 2][0], ea0, q.x);
+            ffma2(st2[2 + kh * 3 + 2][1], ea1, q.y);
+          }
+        }
+      }
+      float a[4], o[4];
+      upk2(acc0, a[0], a[1]);
+      upk2(acc1, a[2], a[3]);
+      const float4 qm = *reinterpret_cast<const float4*>(sco + 5 * CC + cq * 4);
+      const float4 qr = *reinterpret_cast<const float4*>(sco + 6 * CC + cq * 4);
+      const float mu1[4] = {qm.x, qm.y, qm.z, qm.w}, rs1[4] = {qr.x, qr.y, qr.z, qr.w};
+      float xh[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[j] = a[j] * sg[j];
+        xh[j] = (e[j] - mu1[j]) * rs1[j];
+      }
+      stq(dp + hl * erow, o);
+      const f32x2 o0 = pk2(o[0], o[1]), o1 = pk2(o[2], o[3]);
+      fadd2(st2[0][0], o0);
+      fadd2(st2[0][1], o1);
+      ffma2(st2[1][0], o0, pk2(xh[0], xh[1]));
+      ffma2(st2[1][1], o1, pk2(xh[2], xh[3]));
+    };
+    if (S == 1) {
+#pragma unroll 1
+      for (int hl = 0; hl < THI; ++hl) row_body(hl, std::integral_constant<int, 0>{});
+    } else {
+#pragma unroll 1
+      for (int hl = 0; hl < THI; hl += 2) {
+        row_body(hl, std::integral_constant<int, 0>{});
+        row_body(hl + 1, std::integral_constant<int, 1>{});
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  float st[11][4];
+#pragma unroll
+  for (int q = 0; q < 11; ++q) { upk2(st2[q][0], st[q][0], st[q][1]); upk2(st2[q][1], st[q][2], st[q][3]); }
+  block_reduce_channels<11, 4>(st, reinterpret_cast<float*>(smem_v3), cqn, W, partial + (long)worker * 11 * C, C, c0);
+}

@@ -99,12 +99,13 @@ def _colstats(x, M, ld, C, dcode, st, dev):
     return part
 
 
-def _drop_mask(shape, keep, dtype, dev):
-    # same torch calls (shape, dtype, order) as drop_path (dwiseneuro.py:46-54) so RNG streams agree
-    m = torch.empty(shape, dtype=dtype, device=dev).bernoulli_(keep)
+def _drop_mask(shape, keep, dtype, dev, rng_dev=None):
+    # same torch calls (shape, dtype, order) as drop_path (dwiseneuro.py:46-54) so RNG streams agree;
+    # rng_dev="cpu" draws from the CPU generator (parity tests against CPU-generated golden vectors)
+    m = torch.empty(shape, dtype=dtype, device=rng_dev or dev).bernoulli_(keep)
     if keep > 0.0:
         m.div_(keep)
-    return m.float().reshape(shape[0]).contiguous()
+    return m.float().reshape(shape[0]).contiguous().to(dev)
 
 
 def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training: bool, save: bool):
@@ -126,6 +127,8 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
     if cfg["spatial_kernel"] != 3 or cfg["temporal_kernel"] != 5:
         raise NotImplementedError("sensorium_b200 kernels are specialised for spatial_kernel=3, temporal_kernel=5")
     sv = SimpleNamespace(blocks=[], cortex=[], readouts=[], mode=mode, B=B, T=T, H=H, W=W, x=x) if save else None
+    rng_dev = getattr(mod, "_rng_device", None)        # test hooks: where / in which dtype the masks are drawn
+    mdt = getattr(mod, "_mask_dtype", None) or adt
 
     # ---------------- stem (dwiseneuro.py:306-309) + PE of block 0 -------------------------------
     stem_conv, stem_bn = mod.core.stem[0], mod.core.stem[1].bn
@@ -209,7 +212,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         # 6. residual epilogue (+ drop-path, + PE of the next block, + stats of the next shortcut)
         dp = None
         if training and blk.drop_path_rate > 0.0:
-            dp = _drop_mask((B, 1, 1, 1, 1), 1.0 - blk.drop_path_rate, adt, dev)
+            dp = _drop_mask((B, 1, 1, 1, 1), 1.0 - blk.drop_path_rate, mdt, dev, rng_dev)
         last = i == nb - 1
         pe = (None, None, None) if last else pe_tables(mod.core.blocks[2 * i + 2], co, T, Ho, Wo, dev)
         Xn = _empty((Mo, co), torch.float32, dev)
@@ -248,7 +251,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
                            training, st, dev)
         dp = None
         if training and layer.drop_path_rate > 0.0:
-            dp = _drop_mask((B, 1, 1), 1.0 - layer.drop_path_rate, adt, dev)
+            dp = _drop_mask((B, 1, 1), 1.0 - layer.drop_path_rate, mdt, dev, rng_dev)
         out = _empty((Mbt, O), torch.float32, dev)
         outb = _empty((Mbt, O), torch.bfloat16, dev) if bf else None
         call("dwn_cortex_out", Yc, coef, dp, cx, coef_sc, out, outb, Mbt, T, I, O, G, dcode, st)
@@ -269,7 +272,8 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         conv = mod.readouts[m].layer[1]
         mask = None
         if training and p_drop > 0.0:
-            mask = torch.empty((B, K, 1), dtype=torch.float32, device=dev).bernoulli_(1.0 - p_drop).div_(1.0 - p_drop)
+            mask = torch.empty((B, K, 1), dtype=torch.float32, device=rng_dev or dev).bernoulli_(1.0 - p_drop).div_(
+                1.0 - p_drop).to(dev)
         if mask is None and not save:
             xm, xt = (cxb if bf else cx), None
         else:
