@@ -107,8 +107,8 @@ int dwn_pool_bwd(const float* dP, float* dX, long BT, int HW, int C, void* strea
 int dwn_se_bwd(const float* Pp, const float* wt, const float* gate, const float* hpre, const float* mean,
                const float* w1, const float* w2, float* dpre2, float* dhpre, float* dmean, float* dwpwl, float* dw2,
                float* db2, float* dw1, float* db1, int B, int C, int Co, int RD, void* stream); /* dwiseneuro.py:25-43 */
-int dwn_tdw_bwd_reduce(void* da, const void* tm, const float* coef3, const float* dmean, int Nsp, float* partial, int P,
-                       long Mo, int C, int dtype, void* stream);                           /* dwiseneuro.py:105-111 */
+int dwn_tdw_bwd_reduce(void* da, const void* tm, const float* coef3, const float* dmean, int Nsp, float* partial, int J,
+                       int B, int C, int dtype, void* stream);    /* dwiseneuro.py:105-111; partial: B*J rows */
 int dwn_tdw_bwd(void* dth, const void* tm, const void* s_raw, const float* coef3, const float* bcoef3,
                 const float* coef2, const float* wgt, float* partial, int P, int B, int Tn, int HW, int C, int dtype,
                 void* stream);

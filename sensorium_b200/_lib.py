@@ -51,7 +51,7 @@ SIGNATURES = {
     "dwn_block_in_bwd": "pppppp" + "iiiiiii" + "p",
     "dwn_pool_bwd": "pp" + "lii" + "p",
     "dwn_se_bwd": "ppppppp" + "pppppppp" + "iiii" + "p",
-    "dwn_tdw_bwd_reduce": "pppp" + "i" + "p" + "i" + "l" + "ii" + "p",
+    "dwn_tdw_bwd_reduce": "pppp" + "i" + "p" + "iiii" + "p",
     "dwn_tdw_bwd": "pppppppp" + "iiiiii" + "p",
     "dwn_sdw_bwd": "ppppppppp" + "iiiiiii" + "p",
     "dwn_bn_bwd_apply": "pppp" + "lii" + "p",

@@ -143,6 +143,62 @@ template <> struct BnSilu<bf16> {
   }
 };
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on sm_100) --------------------------------------
+typedef unsigned long long f32x2;  // two packed fp32 (low word = first element)
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ void ffma2(f32x2& d, f32x2 a, f32x2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void fadd2(f32x2& d, f32x2 a) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(d) : "l"(a)); }
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// BN-affine + SiLU on a channel pair; (p0,p1) prepared with BnSilu<T>::prep per channel and packed
+template <typename T> __device__ __forceinline__ f32x2 bnsilu2(f32x2 x, f32x2 p0, f32x2 p1);
+template <> __device__ __forceinline__ f32x2 bnsilu2<bf16>(f32x2 x, f32x2 p0, f32x2 p1) {
+  f32x2 h = p1;
+  ffma2(h, x, p0);
+  float h0, h1;
+  upk2(h, h0, h1);
+  f32x2 y = h;
+  ffma2(y, h, pk2(tanh_approx(h0), tanh_approx(h1)));
+  return y;
+}
+template <> __device__ __forceinline__ f32x2 bnsilu2<float>(f32x2 x, f32x2 p0, f32x2 p1) {
+  float x0, x1, a0, a1, b0, b1;
+  upk2(x, x0, x1); upk2(p0, a0, a1); upk2(p1, b0, b1);
+  return pk2(BnSilu<float>::act(x0, a0, b0), BnSilu<float>::act(x1, a1, b1));
+}
+// 4 channels -> two packed pairs
+__device__ __forceinline__ void ldq2(const float* p, f32x2 (&o)[2]) {
+  const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(p);
+  o[0] = q.x; o[1] = q.y;
+}
+__device__ __forceinline__ void ldq2(const bf16* p, f32x2 (&o)[2]) {
+  const uint2 r = *reinterpret_cast<const uint2*>(p);
+  float a, b;
+  unpack_bf16x2(r.x, a, b); o[0] = pk2(a, b);
+  unpack_bf16x2(r.y, a, b); o[1] = pk2(a, b);
+}
+__device__ __forceinline__ void stq2(float* p, const f32x2 (&v)[2]) {
+  ulonglong2 q; q.x = v[0]; q.y = v[1];
+  *reinterpret_cast<ulonglong2*>(p) = q;
+}
+__device__ __forceinline__ void stq2(bf16* p, const f32x2 (&v)[2]) {
+  float a, b, c, d;
+  upk2(v[0], a, b); upk2(v[1], c, d);
+  uint2 r; r.x = pack_bf16x2(a, b); r.y = pack_bf16x2(c, d);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
 // ---- reductions ----------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

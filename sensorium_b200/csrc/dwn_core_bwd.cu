@@ -338,137 +338,170 @@ extern "C" int dwn_se_bwd(const float* Pp, const float* wt, const float* gate, c
 // partial[P][2][C] = { sum dthat, sum dthat*xhat3 }
 // =================================================================================================
 template <typename T>
-__global__ void tdw_bwd_reduce_kernel(T* __restrict__ da, const T* __restrict__ tm, const float* __restrict__ coef3,
-                                      const float* __restrict__ dmean, float inv_nsp, float* __restrict__ partial,
-                                      long Mo, long rows_per_b, int C, int cvc) {
+__global__ void __launch_bounds__(256)
+tdw_bwd_reduce_kernel(T* __restrict__ da, const T* __restrict__ tm, const float* __restrict__ coef3,
+                      const float* __restrict__ dmean, float inv_nsp, float* __restrict__ partial, int Nsp, int C,
+                      int cvc) {
+  // grid (J, channel chunks, B): the per-sample SE term dmean[b][c]/Nsp is a thread constant
   constexpr int V = VecT<T>::V;
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
   const int cv = tid % cvc, lane = tid / cvc, ln = blockDim.x / cvc;
   const int c = (blockIdx.y * cvc + cv) * V;
-  float sc[V], sh[V], mu[V], rs[V];
+  const int b = blockIdx.z;
+  float q0[V], q1[V], mu[V], rs[V], dm[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) {
-    sc[j] = coef3[c + j]; sh[j] = coef3[C + c + j]; mu[j] = coef3[2 * C + c + j]; rs[j] = coef3[3 * C + c + j];
+    BnSilu<T>::prep(coef3[c + j], coef3[C + c + j], q0[j], q1[j]);
+    mu[j] = coef3[2 * C + c + j];
+    rs[j] = coef3[3 * C + c + j];
+    dm[j] = dmean[(long)b * C + c + j] * inv_nsp;
   }
   float st[2][V] = {};
-  for (long m = (long)blockIdx.x * ln + lane; m < Mo; m += (long)gridDim.x * ln) {
-    const long b = m / rows_per_b;
+  T* gp = da + (long)b * Nsp * C + c;
+  const T* xp = tm + (long)b * Nsp * C + c;
+#pragma unroll 2
+  for (int r = blockIdx.x * ln + lane; r < Nsp; r += gridDim.x * ln) {
     float g[V], x[V];
-    ldv(da + m * C + c, g);
-    ldv(tm + m * C + c, x);
+    ldv(gp + (long)r * C, g);
+    ldv(xp + (long)r * C, x);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const float u = fmaf(x[j], sc[j], sh[j]);
-      const float d = rnd<T>((g[j] + dmean[b * C + c + j] * inv_nsp) * silu_grad_t<T>(u));
+      float sg;
+      BnSilu<T>::act_grad(x[j], q0[j], q1[j], sg);
+      const float d = (g[j] + dm[j]) * sg;
       g[j] = d;
       st[0][j] += d;
-      st[1][j] += d * ((x[j] - mu[j]) * rs[j]);
+      st[1][j] = fmaf(d, (x[j] - mu[j]) * rs[j], st[1][j]);
     }
-    stv(da + m * C + c, g);
+    stv(gp + (long)r * C, g);
   }
-  block_reduce_channels<2, V>(st, smem, cvc, ln, partial + (long)blockIdx.x * 2 * C, C, blockIdx.y * cvc * V);
+  block_reduce_channels<2, V>(st, smem, cvc, ln, partial + ((long)b * gridDim.x + blockIdx.x) * 2 * C, C,
+                              blockIdx.y * cvc * V);
 }
 
+// partial must hold B*J rows of [2][C]
 extern "C" int dwn_tdw_bwd_reduce(void* da, const void* tm, const float* coef3, const float* dmean, int Nsp,
-                                  float* partial, int P, long Mo, int C, int dtype, void* stream) {
+                                  float* partial, int J, int B, int C, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DWN_DT_F32) {
     int cvc = dwn_largest_divisor_le(C / 4, 64), ln = 256 / cvc;
-    dim3 grid(P, (C / 4) / cvc), block(cvc * ln);
+    dim3 grid(J, (C / 4) / cvc, B), block(cvc * ln);
     tdw_bwd_reduce_kernel<float><<<grid, block, block.x * 8 * sizeof(float), st>>>((float*)da, (const float*)tm, coef3,
-                                                                                  dmean, 1.0f / Nsp, partial, Mo, Nsp, C,
-                                                                                  cvc);
+                                                                                  dmean, 1.0f / Nsp, partial, Nsp, C, cvc);
   } else {
     int cvc = dwn_largest_divisor_le(C / 8, 64), ln = 256 / cvc;
-    dim3 grid(P, (C / 8) / cvc), block(cvc * ln);
+    dim3 grid(J, (C / 8) / cvc, B), block(cvc * ln);
     tdw_bwd_reduce_kernel<bf16><<<grid, block, block.x * 16 * sizeof(float), st>>>((bf16*)da, (const bf16*)tm, coef3,
-                                                                                  dmean, 1.0f / Nsp, partial, Mo, Nsp, C,
-                                                                                  cvc);
+                                                                                  dmean, 1.0f / Nsp, partial, Nsp, C, cvc);
   }
   DWN_LAUNCH_CHECK();
   return 0;
 }
 
 // =================================================================================================
-// temporal dw backward, pass 2 (thread = channel quad x position, whole T column in registers):
-//   dTm = gamma3*rstd3*(dthat - c1 - xhat3*c2)
+// temporal dw backward, pass 2 (thread = channel quad x position, whole T column in registers, packed fp32x2):
+//   dTm = gamma3*rstd3*(dthat - c1 - xhat3*c2) = a3*dthat - d3*x - b3
 //   dS_act[u] = sum_k w[k]*dTm[u-k+2] ;  dw[k] += s_act[u]*dTm[u-k+2]
 //   dshat[u] = dS_act[u]*SiLU'(BN2(S_raw[u]))  -> written in place over dthat
 //   partial[P][7][C] = { sum dshat, sum dshat*xhat2, dw[0..4] }
 // =================================================================================================
 template <typename T, int TT>
-__global__ void tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restrict__ s_raw,
-                               const float* __restrict__ coef3, const float* __restrict__ bcoef3,
-                               const float* __restrict__ coef2, const float* __restrict__ wgt,
-                               float* __restrict__ partial, int B, int Tn, int HW, int C, int cqc) {
+__global__ void __launch_bounds__(128, 3)
+tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restrict__ s_raw,
+               const float* __restrict__ coef3, const float* __restrict__ bcoef3, const float* __restrict__ coef2,
+               const float* __restrict__ wgt, float* __restrict__ partial, int B, int Tn, int HW, int C, int cqc) {
   constexpr int TA = TT > 0 ? TT : 32;
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
   const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
   const int c = (blockIdx.y * cqc + cq) * 4;
   const int tn = TT > 0 ? TT : Tn;
-  float sc3[4], mu3[4], rs3[4], k1[4], k2[4], sc2[4], sh2[4], mu2[4], rs2[4], wr[5][4];
+  f32x2 a3[2], b3[2], d3[2], w2[5][2];
+  float p0[4], p1[4], mu2[4], rs2[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    sc3[j] = coef3[c + j]; mu3[j] = coef3[2 * C + c + j]; rs3[j] = coef3[3 * C + c + j];
-    k1[j] = bcoef3[c + j]; k2[j] = bcoef3[C + c + j];
-    sc2[j] = coef2[c + j]; sh2[j] = coef2[C + c + j]; mu2[j] = coef2[2 * C + c + j]; rs2[j] = coef2[3 * C + c + j];
+  for (int h = 0; h < 2; ++h) {
+    float av[2], bv[2], dv[2];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) wr[k][j] = wgt[(c + j) * 5 + k];
+    for (int e = 0; e < 2; ++e) {
+      const int cc = c + 2 * h + e;
+      const float sc = coef3[cc], mu = coef3[2 * C + cc], rs = coef3[3 * C + cc];
+      const float k1 = bcoef3[cc], k2 = bcoef3[C + cc];
+      av[e] = sc;
+      dv[e] = -sc * rs * k2;
+      bv[e] = -sc * (k1 - mu * rs * k2);
+      BnSilu<T>::prep(coef2[cc], coef2[C + cc], p0[2 * h + e], p1[2 * h + e]);
+      mu2[2 * h + e] = coef2[2 * C + cc];
+      rs2[2 * h + e] = coef2[3 * C + cc];
+    }
+    a3[h] = pk2(av[0], av[1]);
+    b3[h] = pk2(bv[0], bv[1]);
+    d3[h] = pk2(dv[0], dv[1]);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w2[k][h] = pk2(wgt[(c + 2 * h) * 5 + k], wgt[(c + 2 * h + 1) * 5 + k]);
   }
-  float st[7][4] = {};
+  f32x2 st2[7][2];
+#pragma unroll
+  for (int q = 0; q < 7; ++q) { st2[q][0] = 0ull; st2[q][1] = 0ull; }
   const long npos = (long)B * HW;
   const long tstride = (long)HW * C;
+  const long bstride = (long)Tn * tstride;
   for (long pos = (long)blockIdx.x * ln + lane; pos < npos; pos += (long)gridDim.x * ln) {
     const long b = pos / HW, hw = pos - b * HW;
-    const long base = (b * Tn * HW + hw) * C + c;
-    float dT[TA][4];
+    const long base = b * bstride + hw * C + c;
+    T* gp = dth + base;
+    const T* xp = tm + base;
+    const T* sp = s_raw + base;
+    f32x2 dT[TA][2];
 #pragma unroll
     for (int t = 0; t < TA; ++t) {
       if (t < tn) {
-        float g[4], x[4];
-        ldq(dth + base + t * tstride, g);
-        ldq(tm + base + t * tstride, x);
+        f32x2 g[2], x[2];
+        ldq2(gp + t * tstride, g);
+        ldq2(xp + t * tstride, x);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dT[t][j] = sc3[j] * (g[j] - k1[j] - (x[j] - mu3[j]) * rs3[j] * k2[j]);
+        for (int h = 0; h < 2; ++h) {
+          f32x2 v = b3[h];          // dTm = a3*g + d3*x + b3   (d3, b3 carry the minus signs)
+          ffma2(v, a3[h], g[h]);
+          ffma2(v, d3[h], x[h]);
+          dT[t][h] = v;
+        }
       }
     }
 #pragma unroll
     for (int u = 0; u < TA; ++u) {
       if (u < tn) {
-        float s[4], o[4];
-        ldq(s_raw + base + u * tstride, s);
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        float sa[4], sg[4];
+        float s[4], sa[4], sg[4];
+        ldq(sp + u * tstride, s);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float v = fmaf(s[j], sc2[j], sh2[j]);
-          const float sig = Act<T>::sigmoid(v);
-          sa[j] = v * sig;
-          sg[j] = sig * (1.0f + v * (1.0f - sig));
-        }
+        for (int j = 0; j < 4; ++j) sa[j] = BnSilu<T>::act_grad(s[j], p0[j], p1[j], sg[j]);
+        const f32x2 sa2[2] = {pk2(sa[0], sa[1]), pk2(sa[2], sa[3])};
+        f32x2 acc[2] = {0ull, 0ull};
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
           const int t = u - k + 2;
           if (t >= 0 && t < tn) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              acc[j] = fmaf(wr[k][j], dT[t][j], acc[j]);
-              st[2 + k][j] = fmaf(sa[j], dT[t][j], st[2 + k][j]);
+            for (int h = 0; h < 2; ++h) {
+              ffma2(acc[h], w2[k][h], dT[t][h]);
+              ffma2(st2[2 + k][h], sa2[h], dT[t][h]);
             }
           }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          o[j] = rnd<T>(acc[j] * sg[j]);
-          st[0][j] += o[j];
-          st[1][j] += o[j] * ((s[j] - mu2[j]) * rs2[j]);
-        }
-        stq(dth + base + u * tstride, o);
+        f32x2 o[2];
+        o[0] = fmul2(acc[0], pk2(sg[0], sg[1]));
+        o[1] = fmul2(acc[1], pk2(sg[2], sg[3]));
+        stq2(gp + u * tstride, o);
+        fadd2(st2[0][0], o[0]);
+        fadd2(st2[0][1], o[1]);
+        ffma2(st2[1][0], o[0], pk2((s[0] - mu2[0]) * rs2[0], (s[1] - mu2[1]) * rs2[1]));
+        ffma2(st2[1][1], o[1], pk2((s[2] - mu2[2]) * rs2[2], (s[3] - mu2[3]) * rs2[3]));
       }
     }
   }
+  float st[7][4];
+#pragma unroll
+  for (int q = 0; q < 7; ++q) { upk2(st2[q][0], st[q][0], st[q][1]); upk2(st2[q][1], st[q][2], st[q][3]); }
   block_reduce_channels<7, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 7 * C, C, blockIdx.y * cqc * 4);
 }
 

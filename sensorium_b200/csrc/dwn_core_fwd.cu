@@ -461,100 +461,99 @@ extern "C" int dwn_sdw_fwd(const void* in, const float* coef, const float* wgt, 
 // thread = (channel quad, position); the whole T column lives in registers (TT = compile-time T).
 // =================================================================================================
 template <typename T, int TT>
-__global__ void tdw_fwd_kernel(const T* __restrict__ in, const float* __restrict__ coef, const float* __restrict__ wgt,
-                               T* __restrict__ out, float* __restrict__ partial, int B, int Tn, int HW, int C, int cqc) {
+__global__ void __launch_bounds__(256, 2)
+tdw_fwd_kernel(const T* __restrict__ in, const float* __restrict__ coef, const float* __restrict__ wgt,
+               T* __restrict__ out, float* __restrict__ partial, int B, int Tn, int HW, int C, int cqc) {
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
   const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
   const int c = (blockIdx.y * cqc + cq) * 4;
-  float sc[4], sh[4], wr[5][4];
+  f32x2 p0[2], p1[2], w2[5][2];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    sc[j] = coef[c + j];
-    sh[j] = coef[C + c + j];
+  for (int h = 0; h < 2; ++h) {
+    float a0, a1, b0, b1;
+    BnSilu<T>::prep(coef[c + 2 * h], coef[C + c + 2 * h], a0, b0);
+    BnSilu<T>::prep(coef[c + 2 * h + 1], coef[C + c + 2 * h + 1], a1, b1);
+    p0[h] = pk2(a0, a1);
+    p1[h] = pk2(b0, b1);
 #pragma unroll
-    for (int k = 0; k < 5; ++k) wr[k][j] = wgt[(c + j) * 5 + k];
+    for (int k = 0; k < 5; ++k) w2[k][h] = pk2(wgt[(c + 2 * h) * 5 + k], wgt[(c + 2 * h + 1) * 5 + k]);
   }
-  float st[2][4] = {};
+  f32x2 st2[2][2] = {{0ull, 0ull}, {0ull, 0ull}};
   const long npos = (long)B * HW;
   const long tstride = (long)HW * C;
+  const long bstride = (long)Tn * tstride;
   for (long pos = (long)blockIdx.x * ln + lane; pos < npos; pos += (long)gridDim.x * ln) {
-    long b = pos / HW, hw = pos - b * HW;
-    const long base = (b * Tn * HW + hw) * C + c;
+    const long b = pos / HW, hw = pos - b * HW;
+    const T* ip = in + b * bstride + hw * C + c;
+    T* op = out + b * bstride + hw * C + c;
     if (TT > 0) {
-      float a[TT > 0 ? TT : 1][4];
+      f32x2 a[TT > 0 ? TT : 1][2];
 #pragma unroll
-      for (int t = 0; t < TT; ++t) ldq(in + base + t * tstride, a[t]);
-#pragma unroll
-      for (int t = 0; t < TT; ++t)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) a[t][j] = silu_t<T>(fmaf(a[t][j], sc[j], sh[j]));
+      for (int t = 0; t < TT; ++t) ldq2(ip + t * tstride, a[t]);
 #pragma unroll
       for (int t = 0; t < TT; ++t) {
-        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        a[t][0] = bnsilu2<T>(a[t][0], p0[0], p1[0]);
+        a[t][1] = bnsilu2<T>(a[t][1], p0[1], p1[1]);
+      }
+#pragma unroll
+      for (int t = 0; t < TT; ++t) {
+        f32x2 o[2] = {0ull, 0ull};
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
           const int ts = t + k - 2;
           if (ts >= 0 && ts < TT) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = fmaf(a[ts][j], wr[k][j], o[j]);
+            ffma2(o[0], a[ts][0], w2[k][0]);
+            ffma2(o[1], a[ts][1], w2[k][1]);
           }
         }
-        stq(out + base + t * tstride, o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float r = rnd<T>(o[j]);
-          st[0][j] += r;
-          st[1][j] += r * r;
-        }
+        stq2(op + t * tstride, o);
+        fadd2(st2[0][0], o[0]);
+        fadd2(st2[0][1], o[1]);
+        ffma2(st2[1][0], o[0], o[0]);
+        ffma2(st2[1][1], o[1], o[1]);
       }
     } else {
-      float win[5][4];
+      f32x2 win[5][2];
 #pragma unroll
-      for (int k = 0; k < 5; ++k)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) win[k][j] = 0.f;
-      // preload t=0,1 into slots 3,4 (window covers t-2..t+2 for the *next* output)
+      for (int k = 0; k < 5; ++k) { win[k][0] = 0ull; win[k][1] = 0ull; }
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         if (t < Tn) {
-          float v[4];
-          ldq(in + base + t * tstride, v);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) win[3 + t][j] = silu_t<T>(fmaf(v[j], sc[j], sh[j]));
+          f32x2 v[2];
+          ldq2(ip + t * tstride, v);
+          win[3 + t][0] = bnsilu2<T>(v[0], p0[0], p1[0]);
+          win[3 + t][1] = bnsilu2<T>(v[1], p0[1], p1[1]);
         }
       }
       for (int t = 0; t < Tn; ++t) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) win[k][j] = win[k + 1][j];
+        for (int k = 0; k < 4; ++k) { win[k][0] = win[k + 1][0]; win[k][1] = win[k + 1][1]; }
         if (t + 2 < Tn) {
-          float v[4];
-          ldq(in + base + (t + 2) * tstride, v);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) win[4][j] = silu_t<T>(fmaf(v[j], sc[j], sh[j]));
+          f32x2 v[2];
+          ldq2(ip + (t + 2) * tstride, v);
+          win[4][0] = bnsilu2<T>(v[0], p0[0], p1[0]);
+          win[4][1] = bnsilu2<T>(v[1], p0[1], p1[1]);
         } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) win[4][j] = 0.f;
+          win[4][0] = 0ull; win[4][1] = 0ull;
         }
-        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        f32x2 o[2] = {0ull, 0ull};
 #pragma unroll
-        for (int k = 0; k < 5; ++k)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = fmaf(win[k][j], wr[k][j], o[j]);
-        stq(out + base + t * tstride, o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float r = rnd<T>(o[j]);
-          st[0][j] += r;
-          st[1][j] += r * r;
-        }
+        for (int k = 0; k < 5; ++k) { ffma2(o[0], win[k][0], w2[k][0]); ffma2(o[1], win[k][1], w2[k][1]); }
+        stq2(op + t * tstride, o);
+        fadd2(st2[0][0], o[0]);
+        fadd2(st2[0][1], o[1]);
+        ffma2(st2[1][0], o[0], o[0]);
+        ffma2(st2[1][1], o[1], o[1]);
       }
     }
   }
-  if (partial)
+  if (partial) {
+    float st[2][4];
+    upk2(st2[0][0], st[0][0], st[0][1]); upk2(st2[0][1], st[0][2], st[0][3]);
+    upk2(st2[1][0], st[1][0], st[1][1]); upk2(st2[1][1], st[1][2], st[1][3]);
     block_reduce_channels<2, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 2 * C, C, blockIdx.y * cqc * 4);
+  }
 }
 
 extern "C" int dwn_tdw_fwd(const void* in, const float* coef, const float* wgt, void* out, float* partial, int P, int B,
@@ -595,14 +594,18 @@ __global__ void se_pool_kernel(const T* __restrict__ in, const float* __restrict
   for (int j = 0; j < V; ++j) { sc[j] = coef[c + j]; sh[j] = coef[C + c + j]; }
   float st[1][V] = {};
   const long base = (long)b * Nsp * C + c;
+  float q0[V], q1[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) BnSilu<T>::prep(sc[j], sh[j], q0[j], q1[j]);
+#pragma unroll 4
   for (int r = blockIdx.x * ln + lane; r < Nsp; r += gridDim.x * ln) {
     float v[V];
     ldv(in + base + (long)r * C, v);
 #pragma unroll
-    for (int j = 0; j < V; ++j) v[j] = silu_t<T>(fmaf(v[j], sc[j], sh[j]));
+    for (int j = 0; j < V; ++j) v[j] = BnSilu<T>::act(v[j], q0[j], q1[j]);
     stv(act + base + (long)r * C, v);
 #pragma unroll
-    for (int j = 0; j < V; ++j) st[0][j] += rnd<T>(v[j]);
+    for (int j = 0; j < V; ++j) st[0][j] += v[j];
   }
   block_reduce_channels<1, V>(st, smem, cvc, ln, partial + ((long)b * gridDim.x + blockIdx.x) * C, C,
                               blockIdx.y * cvc * V);

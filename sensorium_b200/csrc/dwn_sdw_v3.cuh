@@ -19,23 +19,6 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-typedef unsigned long long f32x2;  // two packed fp32 (low word = first element)
-__device__ __forceinline__ f32x2 pk2(float a, float b) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ void ffma2(f32x2& d, f32x2 a, f32x2 b) {
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
-}
-__device__ __forceinline__ void fadd2(f32x2& d, f32x2 a) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(d) : "l"(a)); }
-__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-
 // =================================================================================================
 // forward:  S_raw = dwconv3x3_stride_S( SiLU(BN1(E_raw)) ),  + per-channel sum / sumsq partials
 //   RPI = tile rows covered by one pass of the 256 threads over the raw tile (256 / (W * CC/8), 1 or 2).

@@ -16,6 +16,7 @@ from ._lib import call, gemm
 from .engine import BF16, F32, _P, _P_SDW, _empty, _shadow, _stream
 
 _J_CORTEX = 32
+_J_TDW = 16
 
 
 def _bn_bwd(part, P, NQ, q0, count, bn, grads, C, st, dev):
@@ -167,10 +168,10 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
              b_zmode=1, M=Nsp, N=mid, K=co, Z=B, D=da, d_dtype=dcode, ldd=mid, d_zstride=Nsp * mid, _tag="pwl_dgrad",
              _bytes=(Mo * co + B * co * mid + Mo * mid) * es)
         # temporal dw backward
-        part = _empty((_P, 2, mid), torch.float32, dev)
-        call("dwn_tdw_bwd_reduce", da, b.Tm, b.coef3, dmean, Nsp, part, _P, Mo, mid, dcode, st, _tag="tdw_bwd_reduce",
+        part = _empty((B * _J_TDW, 2, mid), torch.float32, dev)
+        call("dwn_tdw_bwd_reduce", da, b.Tm, b.coef3, dmean, Nsp, part, _J_TDW, B, mid, dcode, st, _tag="tdw_bwd_reduce",
              _bytes=3 * Mo * mid * es)
-        bcoef3 = _bn_bwd(part, _P, 2, 0, Mo, blk.temp_covn_dw[1].bn, grads, mid, st, dev)
+        bcoef3 = _bn_bwd(part, B * _J_TDW, 2, 0, Mo, blk.temp_covn_dw[1].bn, grads, mid, st, dev)
         part7 = _empty((_P, 7, mid), torch.float32, dev)
         call("dwn_tdw_bwd", da, b.Tm, b.S, b.coef3, bcoef3, b.coef2, blk.temp_covn_dw[0].weight, part7, _P, B, T,
              b.Ho * b.Wo, mid, dcode, st, _tag="tdw_bwd", _bytes=4 * Mo * mid * es)
