@@ -46,6 +46,10 @@ typedef struct {
   int n_out_total;           /* epi 1: neurons of this readout */
   int row_offset_per_z;      /* epi 1: rows per group (ceil(n/groups)) */
   int block_n;               /* 0 = auto */
+  const void* A2;            /* optional second operand pair (bf16 only, same majors / z-modes): D += A2 (MxK2) * B2^T */
+  const void* B2;
+  long lda2, ldb2;
+  int K2;
   unsigned dbg_lbo_a, dbg_sbo_a, dbg_lbo_b, dbg_sbo_b; /* debug override of MN-major descriptor strides */
 } dwn_gemm_desc;
 int dwn_gemm(const dwn_gemm_desc* d, void* stream);
@@ -61,7 +65,7 @@ int dwn_stem_fwd(const float* x, const float* w, const float* coef, const float*
 /* ---- BatchNorm statistics (dwiseneuro.py:9-22) -------------------------------------------------------- */
 int dwn_bn_finalize(const float* partial, int P, double count, const float* gamma, const float* beta, float* rmean,
                     float* rvar, long long* nbt, float momentum, float eps, int training, float* coef, int C, int Cp,
-                    void* stream);
+                    int NQ, void* stream);   /* partial[P][NQ][Cp], quantities 0/1 = sum / sumsq */
 int dwn_colstats(const void* x, long M, int ld, int C, float* partial, int J, int dtype, void* stream);
 
 /* ---- depth-wise convolutions fused with BN+SiLU-on-load (dwiseneuro.py:96-111) ------------------------ */
@@ -102,7 +106,8 @@ int dwn_block_bwd_reduce(const float* dO, const void* y_raw, const float* coef4,
 int dwn_block_bwd_dy(const float* dO, const void* y_raw, const float* coef4, const float* bcoef4, const float* dp,
                      void* dY, long Mo, long rows_per_b, int Co, int dtype, void* stream);
 int dwn_block_in_bwd(const float* dXpw, const float* dO, const float* xin, const float* coef_sc, const float* bcoef_sc,
-                     float* dXin, int B, int Tn, int Hi, int Wi, int Ci, int Co, int stride, void* stream); /* :125-134 */
+                     const float* colbias, float* dXin, int B, int Tn, int Hi, int Wi, int Ci, int Co, int stride,
+                     void* stream);                                                        /* dwiseneuro.py:125-134 */
 int dwn_pool_bwd(const float* dP, float* dX, long BT, int HW, int C, void* stream);       /* dwiseneuro.py:374,400 */
 int dwn_se_bwd(const float* Pp, const float* wt, const float* gate, const float* hpre, const float* mean,
                const float* w1, const float* w2, float* dpre2, float* dhpre, float* dmean, float* dwpwl, float* dw2,
@@ -129,6 +134,18 @@ int dwn_cortex_bwd_dy(const float* dOut, const void* y, const float* coef, const
                       int M, int Tn, int O, int G, int dtype, void* stream);
 int dwn_cortex_in_bwd(const float* dXc, const float* dOut, const float* xin, const float* coef_sc,
                       const float* bcoef_sc, float* dX, int M, int I, int O, void* stream);
+
+/* ==== conv_pw algebra (dwiseneuro.py:90-93): BatchNorm statistics of E = X W^T from the Gram matrix of X, and the
+ * BatchNorm backward folded into the dgrad / wgrad GEMMs (no pass over E) ================================== */
+int dwn_partial_colsum(const float* partial, int P, int NQ, int q, int C, float* out, void* stream);
+int dwn_pw_stats(const float* gram, const float* sx, const void* w_bf16, double count, const float* gamma,
+                 const float* beta, float* rmean, float* rvar, long long* nbt, float momentum, float eps, float* coef,
+                 int mid, int ci, void* stream);
+int dwn_pw_bwd_prep(const float* coef, const float* bcoef, const void* w_bf16, void* wprime, void* negq, float* r,
+                    float* scratch, int mid, int ci, void* stream);   /* scratch: dwn_pw_bwd_prep_scratch() floats */
+int dwn_pw_bwd_prep_scratch(int mid, int ci);
+int dwn_pw_wgrad_finalize(const float* Psum, const float* coef, const float* bcoef, const void* w_bf16, const float* gram,
+                          const float* sx, float* dw, int mid, int ci, void* stream);
 
 /* ==== loss (src/losses.py:5-21), readout backward prep (dwiseneuro.py:266-287) ============================== */
 int dwn_poisson_fwd(const float* pred, const float* tgt, const float* wn, int wstride, int B, long per_b, float eps,

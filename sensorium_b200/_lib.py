@@ -21,6 +21,7 @@ class GemmDesc(C.Structure):
         ("epi", C.c_int), ("D", C.c_void_p), ("d_dtype", C.c_int), ("ldd", C.c_long), ("d_zstride", C.c_long),
         ("m_limit", C.c_int), ("n_limit", C.c_int), ("bias", C.c_void_p), ("beta", C.c_float), ("Tn", C.c_int),
         ("n_out_total", C.c_int), ("row_offset_per_z", C.c_int), ("block_n", C.c_int),
+        ("A2", C.c_void_p), ("B2", C.c_void_p), ("lda2", C.c_long), ("ldb2", C.c_long), ("K2", C.c_int),
         ("dbg_lbo_a", C.c_uint), ("dbg_sbo_a", C.c_uint), ("dbg_lbo_b", C.c_uint), ("dbg_sbo_b", C.c_uint),
     ]
 
@@ -32,7 +33,7 @@ SIGNATURES = {
     "dwn_input_moments": "piilpipp",
     "dwn_stem_coef": "pidppppppffpip",
     "dwn_stem_fwd": "ppppppppp" + "iiiiiiii" + "p",
-    "dwn_bn_finalize": "pidpppppffipiip",
+    "dwn_bn_finalize": "pidpppppffipiiip",
     "dwn_colstats": "pliipiip",
     "dwn_sdw_fwd": "ppppp" + "iiiiiii" + "p",
     "dwn_tdw_fwd": "ppppp" + "iiiiii" + "p",
@@ -48,7 +49,7 @@ SIGNATURES = {
     "dwn_bn_bwd_finalize": "piiidpppip",
     "dwn_block_bwd_reduce": "ppppppp" + "iiiiiiiii" + "p",
     "dwn_block_bwd_dy": "pppppp" + "llii" + "p",
-    "dwn_block_in_bwd": "pppppp" + "iiiiiii" + "p",
+    "dwn_block_in_bwd": "ppppppp" + "iiiiiii" + "p",
     "dwn_pool_bwd": "pp" + "lii" + "p",
     "dwn_se_bwd": "ppppppp" + "pppppppp" + "iiii" + "p",
     "dwn_tdw_bwd_reduce": "pppp" + "i" + "p" + "iiii" + "p",
@@ -71,6 +72,11 @@ SIGNATURES = {
     "dwn_distill_weights": "pppip",
     "dwn_window_blend": "ppp" + "iiiiii" + "l" + "p",
     "dwn_window_gather": "pp" + "ii" + "l" + "iiii" + "p",
+    # conv_pw algebra (Gram statistics, BN1-backward folded into GEMMs)
+    "dwn_partial_colsum": "piiiipp",
+    "dwn_pw_stats": "pppdpppppffpiip",
+    "dwn_pw_bwd_prep": "ppppppp" + "ii" + "p",
+    "dwn_pw_wgrad_finalize": "ppppppp" + "ii" + "p",
     # optimizer / EMA
     "dwn_adamw": "ppp" + "i" + "pp" + "i" + "ffffff" + "p",
     "dwn_ema": "ppp" + "i" + "f" + "p",
@@ -109,7 +115,7 @@ def _ptr(x):
 
 
 # kernels launched per C-ABI call (default 1) — used for the bench's gpu_launches claim
-_LAUNCHES_PER_CALL = {"dwn_input_moments": 2, "dwn_se_bwd": 2, "dwn_adamw": 2, "dwn_stem_bwd": 2}
+_LAUNCHES_PER_CALL = {"dwn_input_moments": 2, "dwn_se_bwd": 3, "dwn_adamw": 2, "dwn_stem_bwd": 2, "dwn_pw_bwd_prep": 3}
 LAUNCHES = 0
 PROF = None  # when set to a list, every call appends (name, tag, bytes, flops, start_event, end_event)
 

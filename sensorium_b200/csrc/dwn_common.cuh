@@ -216,6 +216,19 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // BN backward coefficient table: bcoef[2][C] = {c1 = sum(dy)/N, c2 = sum(dy*xhat)/N}
 //   dx = gamma*rstd*(dy - c1 - xhat*c2)
 
+// division / modulo by a launch constant: a shift when the divisor is a power of two (all real shapes),
+// a 32-bit division otherwise (row indices always fit in 31 bits)
+struct FastDiv {
+  int d, sh;
+  __host__ __device__ FastDiv() : d(1), sh(0) {}
+  __host__ explicit FastDiv(int dd) : d(dd), sh(-1) {
+    for (int s = 0; s < 31; ++s)
+      if ((1 << s) == dd) sh = s;
+  }
+  __device__ __forceinline__ int div(int x) const { return sh >= 0 ? (x >> sh) : (x / d); }
+  __device__ __forceinline__ int mod(int x) const { return sh >= 0 ? (x & (d - 1)) : (x % d); }
+};
+
 static inline int dwn_largest_divisor_le(int n, int cap) {
   int best = 1;
   for (int d = 1; d <= cap && d <= n; ++d)

@@ -54,7 +54,7 @@ __global__ void block_bwd_reduce_kernel(const float* __restrict__ dO, const T* _
                                         const float* __restrict__ coef4, const float* __restrict__ dp,
                                         const float* __restrict__ xin, const float* __restrict__ coef_sc,
                                         float* __restrict__ partial, int B, int Tn, int Ho, int Wo, int Ci, int Co,
-                                        int stride, int cqc) {
+                                        int stride, int cqc, FastDiv dw, FastDiv dh, FastDiv dt) {
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
   const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
@@ -70,23 +70,24 @@ __global__ void block_bwd_reduce_kernel(const float* __restrict__ dO, const T* _
   }
   float st[4][4] = {};
   const int Hi = Ho * stride, Wi = Wo * stride;
-  const long Mo = (long)B * Tn * Ho * Wo;
-  for (long m = (long)blockIdx.x * ln + lane; m < Mo; m += (long)gridDim.x * ln) {
-    int wq = (int)(m % Wo), hq = (int)((m / Wo) % Ho);
-    long bt = m / ((long)Wo * Ho);
-    int b = (int)(bt / Tn);
+  const int Mo = B * Tn * Ho * Wo;
+#pragma unroll 2
+  for (int m = blockIdx.x * ln + lane; m < Mo; m += gridDim.x * ln) {
+    const int wq = dw.mod(m), r1 = dw.div(m);
+    const int hq = dh.mod(r1), bt = dh.div(r1);
+    const int b = dt.div(bt);
     float g[4], y[4], x[4];
-    ldq(dO + m * Co + c, g);
-    ldq(y_raw + m * Co + c, y);
-    ldq(xin + ((bt * Hi + (long)hq * stride) * Wi + (long)wq * stride) * Ci + ci, x);
+    ldq(dO + (long)m * Co + c, g);
+    ldq(y_raw + (long)m * Co + c, y);
+    ldq(xin + (((long)bt * Hi + hq * stride) * Wi + wq * stride) * Ci + ci, x);
     const float d = dp ? dp[b] : 1.0f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float d4 = d * g[j];
       st[0][j] += d4;
-      st[1][j] += d4 * ((y[j] - m4[j]) * r4[j]);
+      st[1][j] = fmaf(d4, (y[j] - m4[j]) * r4[j], st[1][j]);
       st[2][j] += g[j];
-      st[3][j] += g[j] * ((x[j] - ms[j]) * rs[j]);
+      st[3][j] = fmaf(g[j], (x[j] - ms[j]) * rs[j], st[3][j]);
     }
   }
   block_reduce_channels<4, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 4 * Co, Co, blockIdx.y * cqc * 4);
@@ -101,11 +102,11 @@ extern "C" int dwn_block_bwd_reduce(const float* dO, const void* y_raw, const fl
   if (dtype == DWN_DT_F32)
     block_bwd_reduce_kernel<float><<<grid, block, sm, (cudaStream_t)stream>>>(dO, (const float*)y_raw, coef4, dp, xin,
                                                                               coef_sc, partial, B, Tn, Ho, Wo, Ci, Co,
-                                                                              stride, cqc);
+                                                                              stride, cqc, FastDiv(Wo), FastDiv(Ho), FastDiv(Tn));
   else
     block_bwd_reduce_kernel<bf16><<<grid, block, sm, (cudaStream_t)stream>>>(dO, (const bf16*)y_raw, coef4, dp, xin,
                                                                              coef_sc, partial, B, Tn, Ho, Wo, Ci, Co,
-                                                                             stride, cqc);
+                                                                             stride, cqc, FastDiv(Wo), FastDiv(Ho), FastDiv(Tn));
   DWN_LAUNCH_CHECK();
   return 0;
 }
@@ -114,35 +115,44 @@ extern "C" int dwn_block_bwd_reduce(const float* dO, const void* y_raw, const fl
 template <typename T>
 __global__ void block_bwd_dy_kernel(const float* __restrict__ dO, const T* __restrict__ y_raw,
                                     const float* __restrict__ coef4, const float* __restrict__ bcoef4,
-                                    const float* __restrict__ dp, T* __restrict__ dY, long Mo, long rows_per_b, int Co) {
-  const int cq4 = Co / 4;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < Mo * cq4; i += (long)gridDim.x * blockDim.x) {
-    const long m = i / cq4;
-    const int c = (int)(i % cq4) * 4;
-    float g[4], y[4], o[4];
-    ldq(dO + m * Co + c, g);
-    ldq(y_raw + m * Co + c, y);
-    const float d = dp ? dp[m / rows_per_b] : 1.0f;
+                                    const float* __restrict__ dp, T* __restrict__ dY, int Mo, FastDiv drows, int Co,
+                                    int cqc) {
+  const int tid = threadIdx.x;
+  const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
+  const int c = (blockIdx.y * cqc + cq) * 4;
+  float a[4], bb[4], dd[4];  // dY = a*(dp*g) - dd*y - bb
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float yh = (y[j] - coef4[2 * Co + c + j]) * coef4[3 * Co + c + j];
-      o[j] = coef4[c + j] * (d * g[j] - bcoef4[c + j] - yh * bcoef4[Co + c + j]);
-    }
-    stq(dY + m * Co + c, o);
+  for (int j = 0; j < 4; ++j) {
+    const float sc = coef4[c + j], mu = coef4[2 * Co + c + j], rs = coef4[3 * Co + c + j];
+    const float c1 = bcoef4[c + j], c2 = bcoef4[Co + c + j];
+    a[j] = sc;
+    dd[j] = sc * rs * c2;
+    bb[j] = sc * (c1 - mu * rs * c2);
+  }
+#pragma unroll 4
+  for (int m = blockIdx.x * ln + lane; m < Mo; m += gridDim.x * ln) {
+    float g[4], y[4], o[4];
+    ldq(dO + (long)m * Co + c, g);
+    ldq(y_raw + (long)m * Co + c, y);
+    const float d = dp ? dp[drows.div(m)] : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = fmaf(a[j], d * g[j], -fmaf(dd[j], y[j], bb[j]));
+    stq(dY + (long)m * Co + c, o);
   }
 }
 
 extern "C" int dwn_block_bwd_dy(const float* dO, const void* y_raw, const float* coef4, const float* bcoef4,
                                 const float* dp, void* dY, long Mo, long rows_per_b, int Co, int dtype, void* stream) {
-  long n = Mo * (Co / 4);
-  int gx = (int)((n + 255) / 256);
-  if (gx > 148 * 8) gx = 148 * 8;
+  int cqc = dwn_largest_divisor_le(Co / 4, 64), ln = 256 / cqc;
+  dim3 grid(592, (Co / 4) / cqc), block(cqc * ln);
   if (dtype == DWN_DT_F32)
-    block_bwd_dy_kernel<float><<<gx, 256, 0, (cudaStream_t)stream>>>(dO, (const float*)y_raw, coef4, bcoef4, dp,
-                                                                     (float*)dY, Mo, rows_per_b, Co);
+    block_bwd_dy_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(dO, (const float*)y_raw, coef4, bcoef4, dp,
+                                                                         (float*)dY, (int)Mo, FastDiv((int)rows_per_b), Co,
+                                                                         cqc);
   else
-    block_bwd_dy_kernel<bf16><<<gx, 256, 0, (cudaStream_t)stream>>>(dO, (const bf16*)y_raw, coef4, bcoef4, dp, (bf16*)dY,
-                                                                    Mo, rows_per_b, Co);
+    block_bwd_dy_kernel<bf16><<<grid, block, 0, (cudaStream_t)stream>>>(dO, (const bf16*)y_raw, coef4, bcoef4, dp,
+                                                                        (bf16*)dY, (int)Mo, FastDiv((int)rows_per_b), Co,
+                                                                        cqc);
   DWN_LAUNCH_CHECK();
   return 0;
 }
@@ -150,44 +160,66 @@ extern "C" int dwn_block_bwd_dy(const float* dO, const void* y_raw, const float*
 // gradient w.r.t. the block input: point-wise dgrad + shortcut path (nearest scatter, cyclic-tile sum, BN_sc bwd)
 __global__ void block_in_bwd_kernel(const float* __restrict__ dXpw, const float* __restrict__ dO,
                                     const float* __restrict__ xin, const float* __restrict__ coef_sc,
-                                    const float* __restrict__ bcoef_sc, float* __restrict__ dXin, int B, int Tn, int Hi,
-                                    int Wi, int Ci, int Co, int stride) {
-  const int cq4 = Ci / 4;
-  const long Mi = (long)B * Tn * Hi * Wi;
+                                    const float* __restrict__ bcoef_sc, const float* __restrict__ colbias,
+                                    float* __restrict__ dXin, int B, int Tn, int Hi, int Wi, int Ci, int Co, int stride,
+                                    int cqc, FastDiv dw, FastDiv dh) {
+  const int tid = threadIdx.x;
+  const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
+  const int c = (blockIdx.y * cqc + cq) * 4;
+  const int Mi = B * Tn * Hi * Wi;
   const int Ho = Hi / stride, Wo = Wi / stride;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < Mi * cq4; i += (long)gridDim.x * blockDim.x) {
-    const long m = i / cq4;
-    const int c = (int)(i % cq4) * 4;
-    float o[4];
-    ldq(dXpw + m * Ci + c, o);
-    const int wq = (int)(m % Wi), hq = (int)((m / Wi) % Hi);
-    if ((hq % stride) == 0 && (wq % stride) == 0) {
-      const long bt = m / ((long)Wi * Hi);
-      const long mo = (bt * Ho + hq / stride) * Wo + wq / stride;
-      float x[4];
-      ldq(xin + m * Ci + c, x);
-      for (int cc = c; cc < Co; cc += Ci) {
-        float g[4];
-        ldq(dO + mo * Co + cc, g);
+  const int nrep = (Co - c + Ci - 1) / Ci;  // output channels fed by input channel c: c, c+Ci, ...
+  // dx_sc = sum_rep a*g - dd*x - bb   (BN_sc backward, cyclic channel tile summed)
+  float a[2][4], bb[4] = {0.f, 0.f, 0.f, 0.f}, dd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float xh = (x[j] - coef_sc[2 * Co + cc + j]) * coef_sc[3 * Co + cc + j];
-          o[j] += coef_sc[cc + j] * (g[j] - bcoef_sc[cc + j] - xh * bcoef_sc[Co + cc + j]);
-        }
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a[r][j] = 0.f;
+      if (r < nrep) {
+        const int cc = c + r * Ci + j;
+        const float sc = coef_sc[cc], mu = coef_sc[2 * Co + cc], rs = coef_sc[3 * Co + cc];
+        const float c1 = bcoef_sc[cc], c2 = bcoef_sc[Co + cc];
+        a[r][j] = sc;
+        dd[j] += sc * rs * c2;
+        bb[j] += sc * (c1 - mu * rs * c2);
       }
     }
-    stq(dXin + m * Ci + c, o);
+  float cb[4] = {0.f, 0.f, 0.f, 0.f};
+  if (colbias) ldq(colbias + c, cb);
+#pragma unroll 2
+  for (int m = blockIdx.x * ln + lane; m < Mi; m += gridDim.x * ln) {
+    float o[4];
+    ldq(dXpw + (long)m * Ci + c, o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] -= cb[j];
+    const int wq = dw.mod(m), r1 = dw.div(m);
+    const int hq = dh.mod(r1), bt = dh.div(r1);
+    if ((hq % stride) == 0 && (wq % stride) == 0) {
+      const long mo = ((long)bt * Ho + hq / stride) * Wo + wq / stride;
+      float x[4], g[4];
+      ldq(xin + (long)m * Ci + c, x);
+      ldq(dO + mo * Co + c, g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] += fmaf(a[0][j], g[j], -fmaf(dd[j], x[j], bb[j]));
+      if (nrep > 1) {
+        ldq(dO + mo * Co + c + Ci, g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fmaf(a[1][j], g[j], o[j]);
+      }
+    }
+    stq(dXin + (long)m * Ci + c, o);
   }
 }
 
 extern "C" int dwn_block_in_bwd(const float* dXpw, const float* dO, const float* xin, const float* coef_sc,
-                                const float* bcoef_sc, float* dXin, int B, int Tn, int Hi, int Wi, int Ci, int Co,
-                                int stride, void* stream) {
-  long n = (long)B * Tn * Hi * Wi * (Ci / 4);
-  int gx = (int)((n + 255) / 256);
-  if (gx > 148 * 8) gx = 148 * 8;
-  block_in_bwd_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(dXpw, dO, xin, coef_sc, bcoef_sc, dXin, B, Tn, Hi, Wi, Ci, Co,
-                                                            stride);
+                                const float* bcoef_sc, const float* colbias, float* dXin, int B, int Tn, int Hi, int Wi,
+                                int Ci, int Co, int stride, void* stream) {
+  DWN_REQUIRE(Co <= 2 * Ci, "dwn_block_in_bwd: channel tiling factor > 2 unsupported (Co=%d Ci=%d)", Co, Ci);
+  int cqc = dwn_largest_divisor_le(Ci / 4, 64), ln = 256 / cqc;
+  dim3 grid(592, (Ci / 4) / cqc), block(cqc * ln);
+  block_in_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dXpw, dO, xin, coef_sc, bcoef_sc, colbias, dXin, B, Tn, Hi, Wi, Ci,
+                                                                Co, stride, cqc, FastDiv(Wi), FastDiv(Hi));
   DWN_LAUNCH_CHECK();
   return 0;
 }
@@ -410,7 +442,8 @@ template <typename T, int TT>
 __global__ void __launch_bounds__(128, 3)
 tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restrict__ s_raw,
                const float* __restrict__ coef3, const float* __restrict__ bcoef3, const float* __restrict__ coef2,
-               const float* __restrict__ wgt, float* __restrict__ partial, int B, int Tn, int HW, int C, int cqc) {
+               const float* __restrict__ wgt, float* __restrict__ partial, int B, int Tn, int HW, int C, int cqc,
+               FastDiv dhw) {
   constexpr int TA = TT > 0 ? TT : 32;
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
@@ -517,7 +550,7 @@ extern "C" int dwn_tdw_bwd(void* dth, const void* tm, const void* s_raw, const f
   size_t sm = (size_t)block.x * 28 * sizeof(float);
 #define GO(TY, TTV)                                                                                              \
   tdw_bwd_kernel<TY, TTV><<<grid, block, sm, st>>>((TY*)dth, (const TY*)tm, (const TY*)s_raw, coef3, bcoef3, coef2, wgt, \
-                                                   partial, B, Tn, HW, C, cqc)
+                                                   partial, B, Tn, HW, C, cqc, FastDiv(HW))
   if (dtype == DWN_DT_F32) {
     if (Tn == 16) GO(float, 16); else if (Tn == 8) GO(float, 8); else GO(float, 0);
   } else {
@@ -895,19 +928,20 @@ extern "C" int dwn_dw_wgrad_finalize(const float* partial, int P, int NQ, int q0
 // =================================================================================================
 template <int CIN>
 __global__ void stem_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                       float* __restrict__ partial, long plane, long M, int C0, int cqc) {
+                                       float* __restrict__ partial, int plane, int M, int C0, int cqc, FastDiv dplane) {
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
   const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
   const int c = (blockIdx.y * cqc + cq) * 4;
   float st[CIN + 1][4] = {};
-  for (long m = (long)blockIdx.x * ln + lane; m < M; m += (long)gridDim.x * ln) {
-    const long b = m / plane, pos = m - b * plane;
+#pragma unroll 2
+  for (int m = blockIdx.x * ln + lane; m < M; m += gridDim.x * ln) {
+    const int b = dplane.div(m), pos = m - b * plane;
     float g[4];
-    ldq(dy + m * C0 + c, g);
+    ldq(dy + (long)m * C0 + c, g);
 #pragma unroll
     for (int k = 0; k < CIN; ++k) {
-      const float xv = __ldg(&x[(b * CIN + k) * plane + pos]);
+      const float xv = __ldg(&x[((long)b * CIN + k) * plane + pos]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) st[k][j] = fmaf(g[j], xv, st[k][j]);
     }
@@ -961,7 +995,7 @@ extern "C" int dwn_stem_bwd(const float* dy, const float* x, float* partial, int
   size_t sm = (size_t)block.x * (cin + 1) * 4 * sizeof(float);
   const long M = (long)B * plane;
   switch (cin) {
-#define CASE(N) case N: stem_bwd_reduce_kernel<N><<<grid, block, sm, st>>>(dy, x, partial, plane, M, C0, cqc); break;
+#define CASE(N) case N: stem_bwd_reduce_kernel<N><<<grid, block, sm, st>>>(dy, x, partial, (int)plane, (int)M, C0, cqc, FastDiv((int)plane)); break;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     default: return dwn_fail("dwn_stem_bwd: in_channels=%d unsupported", cin);

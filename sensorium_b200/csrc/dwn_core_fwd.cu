@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float* __restrict__ rmean, float* __restrict__ rvar,
                                                           long long* __restrict__ nbt, float momentum, float eps,
-                                                          int training, float* __restrict__ coef, int C, int Cp) {
+                                                          int training, float* __restrict__ coef, int C, int Cp,
+                                                          int NQ) {
   // block = (32 channels, 32 slices); partial has Cp channels, channel c reads column c % Cp
   // (cyclic channel tiling of the shortcut, dwiseneuro.py:130-132)
   __shared__ double s_sum[32][33], s_sq[32][33];
@@ -143,8 +144,8 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
     if (c < C) {
       const int cp = c % Cp;
       for (int p = sl; p < P; p += 32) {
-        s += (double)partial[((long)p * 2) * Cp + cp];
-        q += (double)partial[((long)p * 2 + 1) * Cp + cp];
+        s += (double)partial[((long)p * NQ) * Cp + cp];
+        q += (double)partial[((long)p * NQ + 1) * Cp + cp];
       }
     }
     s_sum[sl][cl] = s;
@@ -176,9 +177,10 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
 
 extern "C" int dwn_bn_finalize(const float* partial, int P, double count, const float* gamma, const float* beta,
                                float* rmean, float* rvar, long long* nbt, float momentum, float eps, int training,
-                               float* coef, int C, int Cp, void* stream) {
+                               float* coef, int C, int Cp, int NQ, void* stream) {
   bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(partial, P, count, gamma, beta, rmean, rvar, nbt,
-                                                                      momentum, eps, training, coef, C, Cp > 0 ? Cp : C);
+                                                                      momentum, eps, training, coef, C, Cp > 0 ? Cp : C,
+                                                                      NQ > 0 ? NQ : 2);
   DWN_LAUNCH_CHECK();
   return 0;
 }
@@ -193,7 +195,7 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
                                 const float* __restrict__ pe_t, const float* __restrict__ pe_h,
                                 const float* __restrict__ pe_w, float* __restrict__ out, bf16* __restrict__ out_bf,
                                 float* __restrict__ partial, int next_stride, int B, int Tn, int H, int W, int C0,
-                                int cqc) {
+                                int cqc, FastDiv dw, FastDiv dh, FastDiv dplane) {
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
   const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
@@ -206,18 +208,19 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
 #pragma unroll
     for (int k = 0; k < CIN; ++k) wr[j][k] = w[(c + j) * CIN + k];
   }
-  float st[2][4] = {};
-  const long plane = (long)Tn * H * W, M = (long)B * plane;
-  for (long m = (long)blockIdx.x * ln + lane; m < M; m += (long)gridDim.x * ln) {
-    long b = m / plane, pos = m - b * plane;
-    int wq = (int)(pos % W), hq = (int)((pos / W) % H), tq = (int)(pos / ((long)W * H));
+  float st[3][4] = {};
+  const int plane = Tn * H * W, M = B * plane;
+#pragma unroll 2
+  for (int m = blockIdx.x * ln + lane; m < M; m += gridDim.x * ln) {
+    const int b = dplane.div(m), pos = m - b * plane;
+    const int wq = dw.mod(pos), hq = dh.mod(dw.div(pos)), tq = dh.div(dw.div(pos));
     float xv[CIN];
 #pragma unroll
-    for (int k = 0; k < CIN; ++k) xv[k] = __ldg(&x[(b * CIN + k) * plane + pos]);
+    for (int k = 0; k < CIN; ++k) xv[k] = __ldg(&x[((long)b * CIN + k) * plane + pos]);
     float pt[4], ph[4], pw[4], o[4];
-    ldq(pe_t + (long)tq * C0 + c, pt);
-    ldq(pe_h + (long)hq * C0 + c, ph);
-    ldq(pe_w + (long)wq * C0 + c, pw);
+    ldq(pe_t + tq * C0 + c, pt);
+    ldq(pe_h + hq * C0 + c, ph);
+    ldq(pe_w + wq * C0 + c, pw);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float a = 0.f;
@@ -225,15 +228,17 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
       for (int k = 0; k < CIN; ++k) a = fmaf(wr[j][k], xv[k], a);
       o[j] = fmaf(a, sc[j], sh[j]) + ((pt[j] + ph[j]) + pw[j]);
     }
-    stq(out + m * C0 + c, o);
-    if (out_bf) stq(out_bf + m * C0 + c, o);
+    stq(out + (long)m * C0 + c, o);
+    if (out_bf) stq(out_bf + (long)m * C0 + c, o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st[2][j] += o[j];
     if (partial && (hq % next_stride == 0) && (wq % next_stride == 0)) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { st[0][j] += o[j]; st[1][j] += o[j] * o[j]; }
+      for (int j = 0; j < 4; ++j) { st[0][j] += o[j]; st[1][j] = fmaf(o[j], o[j], st[1][j]); }
     }
   }
-  if (partial)
-    block_reduce_channels<2, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 2 * C0, C0, blockIdx.y * cqc * 4);
+  if (partial)  // [P][3][C0]: strided sum / sumsq (next shortcut BN) and the full column sum (Gram statistics)
+    block_reduce_channels<3, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 3 * C0, C0, blockIdx.y * cqc * 4);
 }
 
 extern "C" int dwn_stem_fwd(const float* x, const float* w, const float* coef, const float* pe_t, const float* pe_h,
@@ -243,12 +248,13 @@ extern "C" int dwn_stem_fwd(const float* x, const float* w, const float* coef, c
   int cqc = dwn_largest_divisor_le(C0 / 4, 64);
   int ln = 256 / cqc;
   dim3 grid(P, (C0 / 4) / cqc), block(cqc * ln);
-  size_t sm = (size_t)block.x * 2 * 4 * sizeof(float);
+  size_t sm = (size_t)block.x * 3 * 4 * sizeof(float);
   switch (cin) {
 #define CASE(N)                                                                                                   \
   case N:                                                                                                         \
     stem_fwd_kernel<N><<<grid, block, sm, (cudaStream_t)stream>>>(x, w, coef, pe_t, pe_h, pe_w, out, (bf16*)out_bf, \
-                                                                  partial, next_stride, B, Tn, H, W, C0, cqc);     \
+                                                                  partial, next_stride, B, Tn, H, W, C0, cqc,      \
+                                                                  FastDiv(W), FastDiv(H), FastDiv(Tn * H * W));        \
     break;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
@@ -463,7 +469,7 @@ extern "C" int dwn_sdw_fwd(const void* in, const float* coef, const float* wgt, 
 template <typename T, int TT>
 __global__ void __launch_bounds__(256, 2)
 tdw_fwd_kernel(const T* __restrict__ in, const float* __restrict__ coef, const float* __restrict__ wgt,
-               T* __restrict__ out, float* __restrict__ partial, int B, int Tn, int HW, int C, int cqc) {
+               T* __restrict__ out, float* __restrict__ partial, int B, int Tn, int HW, int C, int cqc, FastDiv dhw) {
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
   const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
@@ -480,13 +486,13 @@ tdw_fwd_kernel(const T* __restrict__ in, const float* __restrict__ coef, const f
     for (int k = 0; k < 5; ++k) w2[k][h] = pk2(wgt[(c + 2 * h) * 5 + k], wgt[(c + 2 * h + 1) * 5 + k]);
   }
   f32x2 st2[2][2] = {{0ull, 0ull}, {0ull, 0ull}};
-  const long npos = (long)B * HW;
+  const int npos = B * HW;
   const long tstride = (long)HW * C;
   const long bstride = (long)Tn * tstride;
-  for (long pos = (long)blockIdx.x * ln + lane; pos < npos; pos += (long)gridDim.x * ln) {
-    const long b = pos / HW, hw = pos - b * HW;
-    const T* ip = in + b * bstride + hw * C + c;
-    T* op = out + b * bstride + hw * C + c;
+  for (int pos = blockIdx.x * ln + lane; pos < npos; pos += gridDim.x * ln) {
+    const int b = dhw.div(pos), hw = pos - b * HW;
+    const T* ip = in + b * bstride + (long)hw * C + c;
+    T* op = out + b * bstride + (long)hw * C + c;
     if (TT > 0) {
       f32x2 a[TT > 0 ? TT : 1][2];
 #pragma unroll
@@ -565,7 +571,7 @@ extern "C" int dwn_tdw_fwd(const void* in, const float* coef, const float* wgt, 
   if (ln < 1) ln = 1;
   dim3 grid(P, (C / 4) / cqc), block(cqc * ln);
   size_t sm = (size_t)block.x * 2 * 4 * sizeof(float);
-#define GO(TY, TTV) tdw_fwd_kernel<TY, TTV><<<grid, block, sm, st>>>((const TY*)in, coef, wgt, (TY*)out, partial, B, Tn, HW, C, cqc)
+#define GO(TY, TTV) tdw_fwd_kernel<TY, TTV><<<grid, block, sm, st>>>((const TY*)in, coef, wgt, (TY*)out, partial, B, Tn, HW, C, cqc, FastDiv(HW))
   if (dtype == DWN_DT_F32) {
     if (Tn == 16) GO(float, 16); else GO(float, 0);
   } else {
@@ -716,7 +722,7 @@ __global__ void block_out_kernel(const T* __restrict__ y_raw, const float* __res
                                  const float* __restrict__ pe_t, const float* __restrict__ pe_h,
                                  const float* __restrict__ pe_w, float* __restrict__ out, bf16* __restrict__ out_bf,
                                  float* __restrict__ partial, int next_stride, int B, int Tn, int Ho, int Wo, int Ci,
-                                 int Co, int stride, int cqc) {
+                                 int Co, int stride, int cqc, FastDiv dw, FastDiv dh, FastDiv dt) {
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
   const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
@@ -730,36 +736,39 @@ __global__ void block_out_kernel(const T* __restrict__ y_raw, const float* __res
     ss[j] = coef_sc[c + j];
     hs[j] = coef_sc[Co + c + j];
   }
-  float st[2][4] = {};
+  float st[3][4] = {};
   const int Hi = Ho * stride, Wi = Wo * stride;
-  const long Mo = (long)B * Tn * Ho * Wo;
-  for (long m = (long)blockIdx.x * ln + lane; m < Mo; m += (long)gridDim.x * ln) {
-    int wq = (int)(m % Wo), hq = (int)((m / Wo) % Ho);
-    long bt = m / ((long)Wo * Ho);
-    int tq = (int)(bt % Tn), b = (int)(bt / Tn);
+  const int Mo = B * Tn * Ho * Wo;
+#pragma unroll 2
+  for (int m = blockIdx.x * ln + lane; m < Mo; m += gridDim.x * ln) {
+    const int wq = dw.mod(m), r1 = dw.div(m);
+    const int hq = dh.mod(r1), bt = dh.div(r1);
+    const int tq = dt.mod(bt), b = dt.div(bt);
     float y[4], x[4], o[4];
-    ldq(y_raw + m * Co + c, y);
-    ldq(xin + ((bt * Hi + (long)hq * stride) * Wi + (long)wq * stride) * Ci + ci, x);
+    ldq(y_raw + (long)m * Co + c, y);
+    ldq(xin + (((long)bt * Hi + hq * stride) * Wi + wq * stride) * Ci + ci, x);
     const float d = dp ? dp[b] : 1.0f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] = d * fmaf(y[j], s4[j], h4[j]) + fmaf(x[j], ss[j], hs[j]);
     if (pe_t) {
       float pt[4], ph[4], pw[4];
-      ldq(pe_t + (long)tq * Co + c, pt);
-      ldq(pe_h + (long)hq * Co + c, ph);
-      ldq(pe_w + (long)wq * Co + c, pw);
+      ldq(pe_t + tq * Co + c, pt);
+      ldq(pe_h + hq * Co + c, ph);
+      ldq(pe_w + wq * Co + c, pw);
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] += (pt[j] + ph[j]) + pw[j];
     }
-    stq(out + m * Co + c, o);
-    if (out_bf) stq(out_bf + m * Co + c, o);
+    stq(out + (long)m * Co + c, o);
+    if (out_bf) stq(out_bf + (long)m * Co + c, o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st[2][j] += o[j];
     if (partial && (hq % next_stride == 0) && (wq % next_stride == 0)) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { st[0][j] += o[j]; st[1][j] += o[j] * o[j]; }
+      for (int j = 0; j < 4; ++j) { st[0][j] += o[j]; st[1][j] = fmaf(o[j], o[j], st[1][j]); }
     }
   }
-  if (partial)
-    block_reduce_channels<2, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 2 * Co, Co, blockIdx.y * cqc * 4);
+  if (partial)  // [P][3][Co], see stem_fwd_kernel
+    block_reduce_channels<3, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 3 * Co, Co, blockIdx.y * cqc * 4);
 }
 
 extern "C" int dwn_block_out(const void* y_raw, const float* coef4, const float* dp, const float* xin,
@@ -769,15 +778,17 @@ extern "C" int dwn_block_out(const void* y_raw, const float* coef4, const float*
   DWN_REQUIRE(Ci % 4 == 0 && Co % 4 == 0, "dwn_block_out: channels must be multiples of 4");
   int cqc = dwn_largest_divisor_le(Co / 4, 64), ln = 256 / cqc;
   dim3 grid(P, (Co / 4) / cqc), block(cqc * ln);
-  size_t sm = (size_t)block.x * 8 * sizeof(float);
+  size_t sm = (size_t)block.x * 12 * sizeof(float);
   if (dtype == DWN_DT_F32)
     block_out_kernel<float><<<grid, block, sm, (cudaStream_t)stream>>>((const float*)y_raw, coef4, dp, xin, coef_sc, pe_t,
                                                                        pe_h, pe_w, out, (bf16*)out_bf, partial,
-                                                                       next_stride, B, Tn, Ho, Wo, Ci, Co, stride, cqc);
+                                                                       next_stride, B, Tn, Ho, Wo, Ci, Co, stride, cqc,
+                                                                       FastDiv(Wo), FastDiv(Ho), FastDiv(Tn));
   else
     block_out_kernel<bf16><<<grid, block, sm, (cudaStream_t)stream>>>((const bf16*)y_raw, coef4, dp, xin, coef_sc, pe_t,
                                                                       pe_h, pe_w, out, (bf16*)out_bf, partial,
-                                                                      next_stride, B, Tn, Ho, Wo, Ci, Co, stride, cqc);
+                                                                      next_stride, B, Tn, Ho, Wo, Ci, Co, stride, cqc,
+                                                                      FastDiv(Wo), FastDiv(Ho), FastDiv(Tn));
   DWN_LAUNCH_CHECK();
   return 0;
 }

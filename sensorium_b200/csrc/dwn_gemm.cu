@@ -128,7 +128,7 @@ constexpr int GT_STAGING_BYTES = 4 * 32 * GT_STAGE_PITCH;
 constexpr int GT_THREADS = 192;   // warp0 TMA, warp1 MMA, warps2-5 epilogue
 
 struct GemmTcParams {
-  int K, block_n, b_bytes, stages;
+  int K, K2, block_n, b_bytes, stages;  // K2 > 0: D += A2 (MxK2) * B2^T (second operand pair, same majors)
   int num_m_blocks, num_n_blocks, Z;
   int a_zmode, b_zmode, b_batch_rows;
   uint32_t lbo_a, lbo_b;  // debug override of MN-major LBO/SBO (0 = default)
@@ -138,7 +138,8 @@ struct GemmTcParams {
 
 template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(GT_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmTcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = GT_A_BYTES + p.b_bytes;
@@ -162,7 +163,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_k_blocks = (p.K + GT_BK - 1) / GT_BK;
+  const int nk1 = (p.K + GT_BK - 1) / GT_BK;
+  const int num_k_blocks = nk1 + (p.K2 + GT_BK - 1) / GT_BK;
   const int total_tiles = p.num_m_blocks * p.num_n_blocks * p.Z;
 
   if (warp == 0 && lane == 0) {
@@ -180,17 +182,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
         uint8_t* sb = sa + GT_A_BYTES;
         mbar_expect_tx(&full_bar[stage], (uint32_t)(GT_A_BYTES + p.block_n * GT_BK * 2));
+        const bool second = kb >= nk1;
+        const CUtensorMap* ma = second ? &mapA2 : &mapA;
+        const CUtensorMap* mb = second ? &mapB2 : &mapB;
+        const int k0 = (second ? kb - nk1 : kb) * GT_BK;
         if (A_MN) {
-          tma_load_3d(sa, &mapA, &full_bar[stage], m_blk * GT_BM, kb * GT_BK, za);
-          tma_load_3d(sa + 8192, &mapA, &full_bar[stage], m_blk * GT_BM + 64, kb * GT_BK, za);
+          tma_load_3d(sa, ma, &full_bar[stage], m_blk * GT_BM, k0, za);
+          tma_load_3d(sa + 8192, ma, &full_bar[stage], m_blk * GT_BM + 64, k0, za);
         } else {
-          tma_load_3d(sa, &mapA, &full_bar[stage], kb * GT_BK, m_blk * GT_BM, za);
+          tma_load_3d(sa, ma, &full_bar[stage], k0, m_blk * GT_BM, za);
         }
         if (B_MN) {
           for (int j = 0; j < p.block_n / 64; ++j)
-            tma_load_3d(sb + j * 8192, &mapB, &full_bar[stage], n_blk * p.block_n + j * 64, kb * GT_BK, zb);
+            tma_load_3d(sb + j * 8192, mb, &full_bar[stage], n_blk * p.block_n + j * 64, k0, zb);
         } else {
-          tma_load_3d(sb, &mapB, &full_bar[stage], kb * GT_BK, n_blk * p.block_n, zb);
+          tma_load_3d(sb, mb, &full_bar[stage], k0, n_blk * p.block_n, zb);
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
@@ -424,6 +430,7 @@ static int gemm_tc(const dwn_gemm_desc* d, cudaStream_t st) {
   GemmTcParams p;
   memset(&p, 0, sizeof(p));
   p.K = d->K;
+  p.K2 = d->A2 ? d->K2 : 0;
   p.block_n = d->block_n > 0 ? d->block_n : pick_block_n(d->N, d->b_mn, d->d_dtype == DWN_DT_BF16, d->epi);
   DWN_REQUIRE(p.block_n % 16 == 0 && p.block_n <= 256 && (!d->b_mn || p.block_n % 64 == 0), "dwn_gemm: bad block_n %d",
               p.block_n);
@@ -453,6 +460,12 @@ static int gemm_tc(const dwn_gemm_desc* d, cudaStream_t st) {
   if (d->b_zmode == 2) zb = (d->M + p.b_batch_rows - 1) / p.b_batch_rows;
   if (make_operand_map(&mapA, d->A, d->a_mn, d->M, d->K, d->lda, d->a_zstride, za, GT_BM)) return -1;
   if (make_operand_map(&mapB, d->B, d->b_mn, d->N, d->K, d->ldb, d->b_zstride, zb, p.block_n)) return -1;
+  CUtensorMap mapA2 = mapA, mapB2 = mapB;
+  if (p.K2 > 0) {
+    DWN_REQUIRE(d->B2 != nullptr, "dwn_gemm: A2 given without B2");
+    if (make_operand_map(&mapA2, d->A2, d->a_mn, d->M, d->K2, d->lda2, d->a_zstride, za, GT_BM)) return -1;
+    if (make_operand_map(&mapB2, d->B2, d->b_mn, d->N, d->K2, d->ldb2, d->b_zstride, zb, p.block_n)) return -1;
+  }
 
   const int total = p.num_m_blocks * p.num_n_blocks * p.Z;
   int grid = dwn_num_sms();
@@ -461,7 +474,7 @@ static int gemm_tc(const dwn_gemm_desc* d, cudaStream_t st) {
   {                                                                                               \
     auto k = gemm_tc_kernel<AM, BM>;                                                              \
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
-    k<<<grid, GT_THREADS, smem, st>>>(mapA, mapB, p);                                             \
+    k<<<grid, GT_THREADS, smem, st>>>(mapA, mapB, mapA2, mapB2, p);                                             \
   }
   if (d->a_mn) { if (d->b_mn) LAUNCH(1, 1) else LAUNCH(1, 0) } else { if (d->b_mn) LAUNCH(0, 1) else LAUNCH(0, 0) }
 #undef LAUNCH
@@ -556,6 +569,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmSimtParams p) 
 }
 
 static int gemm_simt(const dwn_gemm_desc* d, cudaStream_t st) {
+  DWN_REQUIRE(d->A2 == nullptr, "dwn_gemm(simt): second operand pair unsupported");
   GemmSimtParams p;
   memset(&p, 0, sizeof(p));
   p.A = (const float*)d->A;

@@ -7,48 +7,72 @@
 //   wn = normalised weights column of this mouse (stride wstride); partial[J] doubles
 // =================================================================================================
 __global__ void __launch_bounds__(256) poisson_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
-                                                         const float* __restrict__ wn, int wstride, long per_b,
-                                                         long total, float eps, double* __restrict__ partial) {
-  double acc = 0.0;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const float w = wn[(i / per_b) * wstride];
-    if (w != 0.0f) acc += (double)(w * (pred[i] - tgt[i] * logf(pred[i] + eps)));
+                                                         const float* __restrict__ wn, int wstride, int per_b4, int B,
+                                                         float eps, double* __restrict__ partial) {
+  // grid (J, B): one sample per blockIdx.y (masked samples exit at once), float4 streaming, fp32 per-thread
+  // accumulation over <= a few hundred elements, double across threads
+  const int b = blockIdx.y;
+  const float w = wn[(long)b * wstride];
+  float acc = 0.f;
+  if (w != 0.0f) {
+    const float4* p4 = reinterpret_cast<const float4*>(pred) + (long)b * per_b4;
+    const float4* t4 = reinterpret_cast<const float4*>(tgt) + (long)b * per_b4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_b4; i += gridDim.x * blockDim.x) {
+      const float4 p = p4[i], y = t4[i];
+      acc += (p.x - y.x * logf(p.x + eps)) + (p.y - y.y * logf(p.y + eps)) + (p.z - y.z * logf(p.z + eps)) +
+             (p.w - y.w * logf(p.w + eps));
+    }
+    acc *= w;
   }
   __shared__ double red[8];
-  acc = warp_sum_d(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  double d = warp_sum_d((double)acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0;
     for (int i = 0; i < 8; ++i) s += red[i];
-    partial[blockIdx.x] = s;
+    partial[(long)b * gridDim.x + blockIdx.x] = s;
   }
 }
 
+// partial must hold B*J doubles
 extern "C" int dwn_poisson_fwd(const float* pred, const float* tgt, const float* wn, int wstride, int B, long per_b,
                                float eps, double* partial, int J, void* stream) {
-  poisson_fwd_kernel<<<J, 256, 0, (cudaStream_t)stream>>>(pred, tgt, wn, wstride, per_b, (long)B * per_b, eps, partial);
+  DWN_REQUIRE(per_b % 4 == 0, "dwn_poisson_fwd: n*T must be a multiple of 4");
+  dim3 grid(J, B);
+  poisson_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, tgt, wn, wstride, (int)(per_b / 4), B, eps, partial);
   DWN_LAUNCH_CHECK();
   return 0;
 }
 
 // d loss / d pred = gout * w[b] * (1 - y/(p+eps)), exactly 0 for masked samples
 __global__ void poisson_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
-                                   const float* __restrict__ wn, int wstride, const float* __restrict__ gout, long per_b,
-                                   long total, float eps, float* __restrict__ dpred) {
-  const float g = *gout;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const float w = wn[(i / per_b) * wstride];
-    dpred[i] = (w != 0.0f) ? g * w * (1.0f - tgt[i] / (pred[i] + eps)) : 0.0f;
+                                   const float* __restrict__ wn, int wstride, const float* __restrict__ gout, int per_b4,
+                                   float eps, float* __restrict__ dpred) {
+  const int b = blockIdx.y;
+  const float w = wn[(long)b * wstride];
+  const float gw = *gout * w;
+  const float4* p4 = reinterpret_cast<const float4*>(pred) + (long)b * per_b4;
+  const float4* t4 = reinterpret_cast<const float4*>(tgt) + (long)b * per_b4;
+  float4* d4 = reinterpret_cast<float4*>(dpred) + (long)b * per_b4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_b4; i += gridDim.x * blockDim.x) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (w != 0.0f) {
+      const float4 p = p4[i], y = t4[i];
+      o.x = gw * (1.0f - y.x / (p.x + eps));
+      o.y = gw * (1.0f - y.y / (p.y + eps));
+      o.z = gw * (1.0f - y.z / (p.z + eps));
+      o.w = gw * (1.0f - y.w / (p.w + eps));
+    }
+    d4[i] = o;
   }
 }
 
 extern "C" int dwn_poisson_bwd(const float* pred, const float* tgt, const float* wn, int wstride, const float* gout, int B,
                                long per_b, float eps, float* dpred, void* stream) {
-  long total = (long)B * per_b;
-  int gx = (int)((total + 255) / 256);
-  if (gx > 148 * 8) gx = 148 * 8;
-  poisson_bwd_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(pred, tgt, wn, wstride, gout, per_b, total, eps, dpred);
+  DWN_REQUIRE(per_b % 4 == 0, "dwn_poisson_bwd: n*T must be a multiple of 4");
+  dim3 grid(32, B);
+  poisson_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, tgt, wn, wstride, gout, (int)(per_b / 4), eps, dpred);
   DWN_LAUNCH_CHECK();
   return 0;
 }

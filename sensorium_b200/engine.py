@@ -82,15 +82,36 @@ def set_shadow(p: torch.Tensor, sh: torch.Tensor) -> None:
     p._dwn_shadow = (p._version, sh, p.data_ptr())
 
 
-def _bn_coef(bn, partial, P, count, C, Cp, training, st, dev):
+def _bn_coef(bn, partial, P, count, C, Cp, training, st, dev, NQ=2):
     coef = _empty((4, C), torch.float32, dev)
     if training:
         call("dwn_bn_finalize", partial, P, float(count), bn.weight, bn.bias, bn.running_mean, bn.running_var,
-             bn.num_batches_tracked, BN_MOM, BN_EPS, 1, coef, C, Cp, st)
+             bn.num_batches_tracked, BN_MOM, BN_EPS, 1, coef, C, Cp, NQ, st)
     else:
         call("dwn_bn_finalize", None, 0, 1.0, bn.weight, bn.bias, bn.running_mean, bn.running_var, None,
-             BN_MOM, BN_EPS, 0, coef, C, 0, st)
+             BN_MOM, BN_EPS, 0, coef, C, 0, 2, st)
     return coef
+
+
+def _split_k(rows: int, tiles: int) -> int:
+    z = 1
+    while z * 2 * tiles <= 160 and rows % (z * 2) == 0 and rows // (z * 2) >= 256:
+        z *= 2
+    return z
+
+
+def _gram(xb, M, ci, st, dev):
+    """Gx = X^T X (ci x ci, fp32) of the bf16 block input via a split-K (MN,MN) tcgen05 GEMM."""
+    tiles = math.ceil(ci / 128) * math.ceil(ci / 256)
+    zs = _split_k(M, tiles)
+    rows = M // zs
+    part = _empty((zs, ci, ci), torch.float32, dev)
+    gemm(st, dtype=BF16, A=xb, B=xb, a_mn=1, b_mn=1, lda=ci, ldb=ci, a_zstride=rows * ci, b_zstride=rows * ci,
+         a_zmode=1, b_zmode=1, M=ci, N=ci, K=rows, Z=zs, D=part, d_dtype=F32, ldd=ci, d_zstride=ci * ci, _tag="gram",
+         _bytes=M * ci * 2)
+    g = _empty((ci, ci), torch.float32, dev)
+    call("dwn_reduce_rows", part, zs, ci * ci, g, st)
+    return g
 
 
 def _colstats(x, M, ld, C, dcode, st, dev):
@@ -145,11 +166,11 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
              stem_bn.running_mean, stem_bn.running_var, stem_bn.num_batches_tracked, BN_MOM, BN_EPS, coef0, C0, st)
     else:
         call("dwn_bn_finalize", None, 0, 1.0, stem_bn.weight, stem_bn.bias, stem_bn.running_mean,
-             stem_bn.running_var, None, BN_MOM, BN_EPS, 0, coef0, C0, 0, st)
+             stem_bn.running_var, None, BN_MOM, BN_EPS, 0, coef0, C0, 0, 2, st)
     pe = pe_tables(mod.core.blocks[0], C0, T, H, W, dev)
     X = _empty((M0, C0), torch.float32, dev)
     Xb = _empty((M0, C0), torch.bfloat16, dev) if bf else None
-    sc_part = _empty((_P, 2, C0), torch.float32, dev) if training else None
+    sc_part = _empty((_P, 3, C0), torch.float32, dev) if training else None
     if H % strides[0] or W % strides[0]:
         raise NotImplementedError("spatial size must be divisible by the block stride")
     call("dwn_stem_fwd", x, stem_conv.weight, coef0, pe[0], pe[1], pe[2], X, Xb, sc_part, _P, strides[0], B, Cin, T, H,
@@ -174,8 +195,19 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         E = _empty((Mi, mid), adt, dev)
         gemm(st, dtype=dcode, A=Xb if bf else X, B=_shadow(wpw) if bf else wpw, lda=ci, ldb=ci, M=Mi, N=mid, K=ci, Z=1,
              D=E, d_dtype=dcode, ldd=mid, _tag="pw_fwd", _bytes=(Mi * ci + mid * ci + Mi * mid) * es)
-        coef1 = _bn_coef(blk.conv_pw[1].bn, _colstats(E, Mi, mid, mid, dcode, st, dev) if training else None, _P, Mi,
-                         mid, 0, training, st, dev)
+        gram = sx = None
+        if training and bf:
+            # BatchNorm statistics of E = X W^T from the Gram matrix of X (no pass over E), see dwn_pw_algebra.cu
+            gram = _gram(Xb, Mi, ci, st, dev)
+            sx = _empty((ci,), torch.float32, dev)
+            call("dwn_partial_colsum", sc_part, _P, 3, 2, ci, sx, st)
+            coef1 = _empty((4, mid), torch.float32, dev)
+            bn1 = blk.conv_pw[1].bn
+            call("dwn_pw_stats", gram, sx, _shadow(wpw), float(Mi), bn1.weight, bn1.bias, bn1.running_mean,
+                 bn1.running_var, bn1.num_batches_tracked, BN_MOM, BN_EPS, coef1, mid, ci, st)
+        else:
+            coef1 = _bn_coef(blk.conv_pw[1].bn, _colstats(E, Mi, mid, mid, dcode, st, dev) if training else None, _P,
+                             Mi, mid, 0, training, st, dev)
         # 2. spatial depth-wise (BN1+SiLU on load)
         S = _empty((Mo, mid), adt, dev)
         part = _empty((_P, 2, mid), torch.float32, dev) if training else None
@@ -208,7 +240,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
              _bytes=(Mo * mid + B * co * mid + Mo * co) * es)
         coef4 = _bn_coef(blk.conv_pwl[1].bn, _colstats(Y, Mo, co, co, dcode, st, dev) if training else None, _P, Mo, co,
                          0, training, st, dev)
-        coef_sc = _bn_coef(blk.bn_sc.bn, sc_part, _P, Mo, co, ci, training, st, dev)
+        coef_sc = _bn_coef(blk.bn_sc.bn, sc_part, _P, Mo, co, ci, training, st, dev, NQ=3)
         # 6. residual epilogue (+ drop-path, + PE of the next block, + stats of the next shortcut)
         dp = None
         if training and blk.drop_path_rate > 0.0:
@@ -217,7 +249,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         pe = (None, None, None) if last else pe_tables(mod.core.blocks[2 * i + 2], co, T, Ho, Wo, dev)
         Xn = _empty((Mo, co), torch.float32, dev)
         Xnb = _empty((Mo, co), torch.bfloat16, dev) if (bf and not last) else None
-        nsc_part = _empty((_P, 2, co), torch.float32, dev) if (training and not last) else None
+        nsc_part = _empty((_P, 3, co), torch.float32, dev) if (training and not last) else None
         call("dwn_block_out", Y, coef4, dp, X, coef_sc, pe[0], pe[1], pe[2], Xn, Xnb, nsc_part, _P,
              1 if last else strides[i + 1], B, T, Ho, Wo, ci, co, s, dcode, st, _tag="block_out",
              _bytes=Mo * (co * es + ci * 4 + co * (4 + (2 if bf else 0))))
@@ -225,7 +257,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
             sv.blocks.append(SimpleNamespace(X=X, Xb=Xb, E=E, S=S, Tm=Tm, A=A, Y=Y, Wb=Wb, coef1=coef1, coef2=coef2,
                                              coef3=coef3, coef4=coef4, coef_sc=coef_sc, gate=gate, hpre=hpre,
                                              mean=mean, dp=dp, ci=ci, co=co, mid=mid, s=s, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo,
-                                             rd=rd))
+                                             rd=rd, gram=gram, sx=sx))
         X, Xb, sc_part, Hi, Wi = Xn, Xnb, nsc_part, Ho, Wo
 
     # ---------------- pool (dwiseneuro.py:374,400) -----------------------------------------------

@@ -13,7 +13,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from ._lib import call, gemm
-from .engine import BF16, F32, _P, _P_SDW, _empty, _shadow, _stream
+from .engine import BF16, F32, _P, _P_SDW, _empty, _shadow, _split_k, _stream
 
 _J_CORTEX = 32
 _J_TDW = 16
@@ -27,13 +27,6 @@ def _bn_bwd(part, P, NQ, q0, count, bn, grads, C, st, dev):
     grads[bn.weight] = dgamma
     grads[bn.bias] = dbeta
     return bcoef
-
-
-def _split_k(rows: int, tiles: int) -> int:
-    z = 1
-    while z * 2 * tiles <= 160 and rows % (z * 2) == 0 and rows // (z * 2) >= 256:
-        z *= 2
-    return z
 
 
 def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[Optional[torch.Tensor]]:
@@ -189,25 +182,44 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         dws = torch.empty_like(blk.spat_covn_dw[0].weight)
         call("dwn_dw_wgrad_finalize", part11, _P_SDW, 11, 2, 9, dws, mid, st)
         grads[blk.spat_covn_dw[0].weight] = dws
-        call("dwn_bn_bwd_apply", dE, b.E, b.coef1, bcoef1, Mi, mid, dcode, st, _tag="bn_bwd_apply", _bytes=3 * Mi * mid * es)
-        # point-wise expansion: dgrad + split-K wgrad
         wpw = blk.conv_pw[0].weight
         dXpw = _empty((Mi, ci), torch.float32, dev)
-        gemm(st, dtype=dcode, A=dE, B=_shadow(wpw) if bf else wpw, b_mn=1, lda=mid, ldb=ci, M=Mi, N=ci, K=mid, Z=1,
-             D=dXpw, d_dtype=F32, ldd=ci, _tag="pw_dgrad", _bytes=Mi * mid * es + mid * ci * es + Mi * ci * 4)
         tiles = math.ceil(mid / 128) * math.ceil(ci / 256)
         Zs = _split_k(Mi, tiles)
         rows = Mi // Zs
         wpart = _empty((Zs, mid, ci), torch.float32, dev)
-        gemm(st, dtype=dcode, A=dE, B=b.Xb if bf else b.X, a_mn=1, b_mn=1, lda=mid, ldb=ci, a_zstride=rows * mid,
-             b_zstride=rows * ci, a_zmode=1, b_zmode=1, M=mid, N=ci, K=rows, Z=Zs, D=wpart, d_dtype=F32, ldd=ci,
-             d_zstride=mid * ci, _tag="pw_wgrad", _bytes=Mi * (mid + ci) * es + Zs * mid * ci * 4)
         dwpw = torch.empty_like(wpw)
-        call("dwn_reduce_rows", wpart, Zs, mid * ci, dwpw, st)
+        colbias = None
+        if bf and b.gram is not None:
+            # BN1 backward folded into the GEMMs (dE holds G = dE_pre; E is never read): dwn_pw_algebra.cu
+            wsh = _shadow(wpw)
+            wprime = _empty((mid, ci), torch.bfloat16, dev)
+            negq = _empty((ci, ci), torch.bfloat16, dev)
+            colbias = _empty((ci,), torch.float32, dev)
+            scratch = _empty((3 * mid + 8 * (ci + 1) * ci,), torch.float32, dev)
+            call("dwn_pw_bwd_prep", b.coef1, bcoef1, wsh, wprime, negq, colbias, scratch, mid, ci, st)
+            gemm(st, dtype=dcode, A=dE, B=wprime, b_mn=1, lda=mid, ldb=ci, M=Mi, N=ci, K=mid, Z=1, A2=b.Xb, B2=negq,
+                 lda2=ci, ldb2=ci, K2=ci, D=dXpw, d_dtype=F32, ldd=ci, _tag="pw_dgrad",
+                 _bytes=Mi * mid * es + mid * ci * es + Mi * ci * (4 + es))
+            gemm(st, dtype=dcode, A=dE, B=b.Xb, a_mn=1, b_mn=1, lda=mid, ldb=ci, a_zstride=rows * mid,
+                 b_zstride=rows * ci, a_zmode=1, b_zmode=1, M=mid, N=ci, K=rows, Z=Zs, D=wpart, d_dtype=F32, ldd=ci,
+                 d_zstride=mid * ci, _tag="pw_wgrad", _bytes=Mi * (mid + ci) * es + Zs * mid * ci * 4)
+            psum = _empty((mid, ci), torch.float32, dev)
+            call("dwn_reduce_rows", wpart, Zs, mid * ci, psum, st)
+            call("dwn_pw_wgrad_finalize", psum, b.coef1, bcoef1, wsh, b.gram, b.sx, dwpw, mid, ci, st)
+        else:
+            call("dwn_bn_bwd_apply", dE, b.E, b.coef1, bcoef1, Mi, mid, dcode, st, _tag="bn_bwd_apply",
+                 _bytes=3 * Mi * mid * es)
+            gemm(st, dtype=dcode, A=dE, B=_shadow(wpw) if bf else wpw, b_mn=1, lda=mid, ldb=ci, M=Mi, N=ci, K=mid, Z=1,
+                 D=dXpw, d_dtype=F32, ldd=ci, _tag="pw_dgrad", _bytes=Mi * mid * es + mid * ci * es + Mi * ci * 4)
+            gemm(st, dtype=dcode, A=dE, B=b.Xb if bf else b.X, a_mn=1, b_mn=1, lda=mid, ldb=ci, a_zstride=rows * mid,
+                 b_zstride=rows * ci, a_zmode=1, b_zmode=1, M=mid, N=ci, K=rows, Z=Zs, D=wpart, d_dtype=F32, ldd=ci,
+                 d_zstride=mid * ci, _tag="pw_wgrad", _bytes=Mi * (mid + ci) * es + Zs * mid * ci * 4)
+            call("dwn_reduce_rows", wpart, Zs, mid * ci, dwpw, st)
         grads[wpw] = dwpw
         del dE
         dXin = _empty((Mi, ci), torch.float32, dev)
-        call("dwn_block_in_bwd", dXpw, dO, b.X, b.coef_sc, bcoef_sc, dXin, B, T, b.Hi, b.Wi, ci, co, s, st,
+        call("dwn_block_in_bwd", dXpw, dO, b.X, b.coef_sc, bcoef_sc, colbias, dXin, B, T, b.Hi, b.Wi, ci, co, s, st,
              _tag="block_in_bwd", _bytes=Mi * ci * 12 + Mo * co * 4)
         dO = dXin
         if dp is not None:

@@ -11,7 +11,7 @@ from torch import nn
 
 from ._lib import call
 
-_J = 148
+_J = 16
 
 
 class _PoissonFn(torch.autograd.Function):
@@ -22,7 +22,8 @@ class _PoissonFn(torch.autograd.Function):
         st = torch.cuda.current_stream(dev).cuda_stream
         ctx.set_materialize_grads(False)
         idx = [m for m in range(n_mice) if live[m]]
-        partial = torch.zeros((max(len(idx), 1), _J), dtype=torch.float64, device=dev)
+        B0 = preds[0].shape[0]
+        partial = torch.zeros((max(len(idx), 1), B0 * _J), dtype=torch.float64, device=dev)
         saved = []
         for j, m in enumerate(idx):
             p = preds[m].detach().contiguous()

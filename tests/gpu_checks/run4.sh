@@ -1,6 +1,6 @@
 python tests/gpu_checks/check_layers.py > gpurun_out/layers.log 2>&1; echo "layers rc=$?"; grep -E "FAIL|LAYER" gpurun_out/layers.log | head -20
 python tests/gpu_checks/check_backward.py > gpurun_out/bwd.log 2>&1; echo "bwd rc=$?"; grep -E "FAIL|worst|BACKWARD|Error|error" gpurun_out/bwd.log | head -20
-timeout 900 python -m pytest tests -q -m gpu --tb=short 2>&1 | grep -E "^E  |^tests|Error|passed|failed" | cut -c1-250 | head -30
-python tests/gpu_checks/kbench.py sdw tdw se_pool > gpurun_out/kbench_v3.txt 2>&1; cat gpurun_out/kbench_v3.txt
+timeout 900 python -m pytest tests -q -m gpu --tb=short 2>&1 | grep -E "^E  [^ +]|^tests|Error|passed|failed" | cut -c1-250 | head -30
+python tests/gpu_checks/kbench.py blk0 blk1 > gpurun_out/kbench_v3.txt 2>&1; cat gpurun_out/kbench_v3.txt
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --profile-out gpurun_out/kernels_r1c.csv > gpurun_out/bench_r1c.json 2> gpurun_out/bench_r1c.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_r1c.err; python -c "
 import json; d=json.load(open('gpurun_out/bench_r1c.json')); print(d['value'], d['ms_per_step'], d['e2e']['value']); print(d['kernel_table_ms_per_step'])"

@@ -96,7 +96,7 @@ def test_tiny_golden_forward_loss_grads(dev, golden_dir):
                 noisy = torch.relu(ref_m * (1 + torch.randn(ref_m.shape, generator=gen)))  # single-trial-like target
                 gap = _corr_gap(ev[m].cpu(), ref_m, noisy)
                 gap_y = _corr_gap(yard[m].float().cpu(), ref_m, noisy)
-                assert gap < max(1e-3, 1.5 * gap_y), (m, gap, gap_y)
+                assert gap < max(1e-3, 2.0 * gap_y), (m, gap, gap_y)
 
 
 def test_c1_full_architecture_golden(dev, golden_dir):
