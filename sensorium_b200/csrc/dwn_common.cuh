@@ -199,6 +199,20 @@ __device__ __forceinline__ void stq2(bf16* p, const f32x2 (&v)[2]) {
   *reinterpret_cast<uint2*>(p) = r;
 }
 
+// one channel pair
+__device__ __forceinline__ f32x2 ldp2(const float* p) { return *reinterpret_cast<const f32x2*>(p); }
+__device__ __forceinline__ f32x2 ldp2(const bf16* p) {
+  float a, b;
+  unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p), a, b);
+  return pk2(a, b);
+}
+__device__ __forceinline__ void stp2(float* p, f32x2 v) { *reinterpret_cast<f32x2*>(p) = v; }
+__device__ __forceinline__ void stp2(bf16* p, f32x2 v) {
+  float a, b;
+  upk2(v, a, b);
+  *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(a, b);
+}
+
 // ---- reductions ----------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -370,35 +370,35 @@ extern "C" int dwn_se_bwd(const float* Pp, const float* wt, const float* gate, c
 // partial[P][2][C] = { sum dthat, sum dthat*xhat3 }
 // =================================================================================================
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 tdw_bwd_reduce_kernel(T* __restrict__ da, const T* __restrict__ tm, const float* __restrict__ coef3,
                       const float* __restrict__ dmean, float inv_nsp, float* __restrict__ partial, int Nsp, int C,
-                      int cvc) {
-  // grid (J, channel chunks, B): the per-sample SE term dmean[b][c]/Nsp is a thread constant
-  constexpr int V = VecT<T>::V;
+                      int cqc) {
+  // grid (J, channel chunks, B): the per-sample SE term dmean[b][c]/Nsp is a thread constant.
+  // 4 channels per thread keep the register count low enough for 4 CTAs / SM (latency hiding by occupancy).
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
-  const int cv = tid % cvc, lane = tid / cvc, ln = blockDim.x / cvc;
-  const int c = (blockIdx.y * cvc + cv) * V;
+  const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
+  const int c = (blockIdx.y * cqc + cq) * 4;
   const int b = blockIdx.z;
-  float q0[V], q1[V], mu[V], rs[V], dm[V];
+  float q0[4], q1[4], mu[4], rs[4], dm[4];
 #pragma unroll
-  for (int j = 0; j < V; ++j) {
+  for (int j = 0; j < 4; ++j) {
     BnSilu<T>::prep(coef3[c + j], coef3[C + c + j], q0[j], q1[j]);
     mu[j] = coef3[2 * C + c + j];
     rs[j] = coef3[3 * C + c + j];
     dm[j] = dmean[(long)b * C + c + j] * inv_nsp;
   }
-  float st[2][V] = {};
+  float st[2][4] = {};
   T* gp = da + (long)b * Nsp * C + c;
   const T* xp = tm + (long)b * Nsp * C + c;
-#pragma unroll 2
+#pragma unroll 4
   for (int r = blockIdx.x * ln + lane; r < Nsp; r += gridDim.x * ln) {
-    float g[V], x[V];
-    ldv(gp + (long)r * C, g);
-    ldv(xp + (long)r * C, x);
+    float g[4], x[4];
+    ldq(gp + (long)r * C, g);
+    ldq(xp + (long)r * C, x);
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
+    for (int j = 0; j < 4; ++j) {
       float sg;
       BnSilu<T>::act_grad(x[j], q0[j], q1[j], sg);
       const float d = (g[j] + dm[j]) * sg;
@@ -406,27 +406,26 @@ tdw_bwd_reduce_kernel(T* __restrict__ da, const T* __restrict__ tm, const float*
       st[0][j] += d;
       st[1][j] = fmaf(d, (x[j] - mu[j]) * rs[j], st[1][j]);
     }
-    stv(gp + (long)r * C, g);
+    stq(gp + (long)r * C, g);
   }
-  block_reduce_channels<2, V>(st, smem, cvc, ln, partial + ((long)b * gridDim.x + blockIdx.x) * 2 * C, C,
-                              blockIdx.y * cvc * V);
+  block_reduce_channels<2, 4>(st, smem, cqc, ln, partial + ((long)b * gridDim.x + blockIdx.x) * 2 * C, C,
+                              blockIdx.y * cqc * 4);
 }
 
 // partial must hold B*J rows of [2][C]
 extern "C" int dwn_tdw_bwd_reduce(void* da, const void* tm, const float* coef3, const float* dmean, int Nsp,
                                   float* partial, int J, int B, int C, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == DWN_DT_F32) {
-    int cvc = dwn_largest_divisor_le(C / 4, 64), ln = 256 / cvc;
-    dim3 grid(J, (C / 4) / cvc, B), block(cvc * ln);
+  DWN_REQUIRE(C % 4 == 0, "dwn_tdw_bwd_reduce: C %% 4 != 0");
+  int cqc = dwn_largest_divisor_le(C / 4, 128), ln = 256 / cqc;
+  if (ln < 1) ln = 1;
+  dim3 grid(J, (C / 4) / cqc, B), block(cqc * ln);
+  if (dtype == DWN_DT_F32)
     tdw_bwd_reduce_kernel<float><<<grid, block, block.x * 8 * sizeof(float), st>>>((float*)da, (const float*)tm, coef3,
-                                                                                  dmean, 1.0f / Nsp, partial, Nsp, C, cvc);
-  } else {
-    int cvc = dwn_largest_divisor_le(C / 8, 64), ln = 256 / cvc;
-    dim3 grid(J, (C / 8) / cvc, B), block(cvc * ln);
-    tdw_bwd_reduce_kernel<bf16><<<grid, block, block.x * 16 * sizeof(float), st>>>((bf16*)da, (const bf16*)tm, coef3,
-                                                                                  dmean, 1.0f / Nsp, partial, Nsp, C, cvc);
-  }
+                                                                                  dmean, 1.0f / Nsp, partial, Nsp, C, cqc);
+  else
+    tdw_bwd_reduce_kernel<bf16><<<grid, block, block.x * 8 * sizeof(float), st>>>((bf16*)da, (const bf16*)tm, coef3,
+                                                                                 dmean, 1.0f / Nsp, partial, Nsp, C, cqc);
   DWN_LAUNCH_CHECK();
   return 0;
 }
@@ -439,43 +438,43 @@ extern "C" int dwn_tdw_bwd_reduce(void* da, const void* tm, const float* coef3, 
 //   partial[P][7][C] = { sum dshat, sum dshat*xhat2, dw[0..4] }
 // =================================================================================================
 template <typename T, int TT>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, 4)
 tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restrict__ s_raw,
                const float* __restrict__ coef3, const float* __restrict__ bcoef3, const float* __restrict__ coef2,
-               const float* __restrict__ wgt, float* __restrict__ partial, int B, int Tn, int HW, int C, int cqc,
-               FastDiv dhw) {
+               const float* __restrict__ wgt, float* __restrict__ partial, int B, int Tn, int HW, int C, int cpc) {
+  // thread = one channel PAIR x position (2 channels keep the whole-T register column small enough for
+  // 4 CTAs / SM; a warp still covers 64 consecutive channels = 128 bytes per row)
   constexpr int TA = TT > 0 ? TT : 32;
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
-  const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
-  const int c = (blockIdx.y * cqc + cq) * 4;
+  const int cp = tid % cpc, lane = tid / cpc, ln = blockDim.x / cpc;
+  const int c = (blockIdx.y * cpc + cp) * 2;
   const int tn = TT > 0 ? TT : Tn;
-  f32x2 a3[2], b3[2], d3[2], w2[5][2];
-  float p0[4], p1[4], mu2[4], rs2[4];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
+  f32x2 a3, b3, d3, w2[5];
+  float p0[2], p1[2], mu2[2], rs2[2];
+  {
     float av[2], bv[2], dv[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int cc = c + 2 * h + e;
+      const int cc = c + e;
       const float sc = coef3[cc], mu = coef3[2 * C + cc], rs = coef3[3 * C + cc];
       const float k1 = bcoef3[cc], k2 = bcoef3[C + cc];
       av[e] = sc;
       dv[e] = -sc * rs * k2;
       bv[e] = -sc * (k1 - mu * rs * k2);
-      BnSilu<T>::prep(coef2[cc], coef2[C + cc], p0[2 * h + e], p1[2 * h + e]);
-      mu2[2 * h + e] = coef2[2 * C + cc];
-      rs2[2 * h + e] = coef2[3 * C + cc];
+      BnSilu<T>::prep(coef2[cc], coef2[C + cc], p0[e], p1[e]);
+      mu2[e] = coef2[2 * C + cc];
+      rs2[e] = coef2[3 * C + cc];
     }
-    a3[h] = pk2(av[0], av[1]);
-    b3[h] = pk2(bv[0], bv[1]);
-    d3[h] = pk2(dv[0], dv[1]);
+    a3 = pk2(av[0], av[1]);
+    b3 = pk2(bv[0], bv[1]);
+    d3 = pk2(dv[0], dv[1]);
 #pragma unroll
-    for (int k = 0; k < 5; ++k) w2[k][h] = pk2(wgt[(c + 2 * h) * 5 + k], wgt[(c + 2 * h + 1) * 5 + k]);
+    for (int k = 0; k < 5; ++k) w2[k] = pk2(wgt[c * 5 + k], wgt[(c + 1) * 5 + k]);
   }
-  f32x2 st2[7][2];
+  f32x2 st2[7];
 #pragma unroll
-  for (int q = 0; q < 7; ++q) { st2[q][0] = 0ull; st2[q][1] = 0ull; }
+  for (int q = 0; q < 7; ++q) st2[q] = 0ull;
   const long npos = (long)B * HW;
   const long tstride = (long)HW * C;
   const long bstride = (long)Tn * tstride;
@@ -485,57 +484,48 @@ tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restric
     T* gp = dth + base;
     const T* xp = tm + base;
     const T* sp = s_raw + base;
-    f32x2 dT[TA][2];
+    f32x2 dT[TA], sv[TA];
+#pragma unroll
+    for (int t = 0; t < TA; ++t)
+      if (t < tn) sv[t] = ldp2(sp + t * tstride);
 #pragma unroll
     for (int t = 0; t < TA; ++t) {
       if (t < tn) {
-        f32x2 g[2], x[2];
-        ldq2(gp + t * tstride, g);
-        ldq2(xp + t * tstride, x);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          f32x2 v = b3[h];          // dTm = a3*g + d3*x + b3   (d3, b3 carry the minus signs)
-          ffma2(v, a3[h], g[h]);
-          ffma2(v, d3[h], x[h]);
-          dT[t][h] = v;
-        }
+        const f32x2 g = ldp2(gp + t * tstride), x = ldp2(xp + t * tstride);
+        f32x2 v = b3;  // dTm = a3*g + d3*x + b3   (d3, b3 carry the minus signs)
+        ffma2(v, a3, g);
+        ffma2(v, d3, x);
+        dT[t] = v;
       }
     }
 #pragma unroll
     for (int u = 0; u < TA; ++u) {
       if (u < tn) {
-        float s[4], sa[4], sg[4];
-        ldq(sp + u * tstride, s);
+        float s[2], sa[2], sg[2];
+        upk2(sv[u], s[0], s[1]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sa[j] = BnSilu<T>::act_grad(s[j], p0[j], p1[j], sg[j]);
-        const f32x2 sa2[2] = {pk2(sa[0], sa[1]), pk2(sa[2], sa[3])};
-        f32x2 acc[2] = {0ull, 0ull};
+        for (int j = 0; j < 2; ++j) sa[j] = BnSilu<T>::act_grad(s[j], p0[j], p1[j], sg[j]);
+        const f32x2 sa2 = pk2(sa[0], sa[1]);
+        f32x2 acc = 0ull;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
           const int t = u - k + 2;
           if (t >= 0 && t < tn) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              ffma2(acc[h], w2[k][h], dT[t][h]);
-              ffma2(st2[2 + k][h], sa2[h], dT[t][h]);
-            }
+            ffma2(acc, w2[k], dT[t]);
+            ffma2(st2[2 + k], sa2, dT[t]);
           }
         }
-        f32x2 o[2];
-        o[0] = fmul2(acc[0], pk2(sg[0], sg[1]));
-        o[1] = fmul2(acc[1], pk2(sg[2], sg[3]));
-        stq2(gp + u * tstride, o);
-        fadd2(st2[0][0], o[0]);
-        fadd2(st2[0][1], o[1]);
-        ffma2(st2[1][0], o[0], pk2((s[0] - mu2[0]) * rs2[0], (s[1] - mu2[1]) * rs2[1]));
-        ffma2(st2[1][1], o[1], pk2((s[2] - mu2[2]) * rs2[2], (s[3] - mu2[3]) * rs2[3]));
+        const f32x2 o = fmul2(acc, pk2(sg[0], sg[1]));
+        stp2(gp + u * tstride, o);
+        fadd2(st2[0], o);
+        ffma2(st2[1], o, pk2((s[0] - mu2[0]) * rs2[0], (s[1] - mu2[1]) * rs2[1]));
       }
     }
   }
-  float st[7][4];
+  float st[7][2];
 #pragma unroll
-  for (int q = 0; q < 7; ++q) { upk2(st2[q][0], st[q][0], st[q][1]); upk2(st2[q][1], st[q][2], st[q][3]); }
-  block_reduce_channels<7, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 7 * C, C, blockIdx.y * cqc * 4);
+  for (int q = 0; q < 7; ++q) upk2(st2[q], st[q][0], st[q][1]);
+  block_reduce_channels<7, 2>(st, smem, cpc, ln, partial + (long)blockIdx.x * 7 * C, C, blockIdx.y * cpc * 2);
 }
 
 extern "C" int dwn_tdw_bwd(void* dth, const void* tm, const void* s_raw, const float* coef3, const float* bcoef3,
@@ -543,14 +533,15 @@ extern "C" int dwn_tdw_bwd(void* dth, const void* tm, const void* s_raw, const f
                            int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DWN_REQUIRE(Tn <= 32, "dwn_tdw_bwd: T > 32 unsupported");
-  int cqc = dwn_largest_divisor_le(C / 4, 64);
-  int ln = 128 / cqc;
+  DWN_REQUIRE(C % 2 == 0, "dwn_tdw_bwd: C %% 2 != 0");
+  int cpc = dwn_largest_divisor_le(C / 2, 128);
+  int ln = 128 / cpc;
   if (ln < 1) ln = 1;
-  dim3 grid(P, (C / 4) / cqc), block(cqc * ln);
-  size_t sm = (size_t)block.x * 28 * sizeof(float);
+  dim3 grid(P, (C / 2) / cpc), block(cpc * ln);
+  size_t sm = (size_t)block.x * 14 * sizeof(float);
 #define GO(TY, TTV)                                                                                              \
   tdw_bwd_kernel<TY, TTV><<<grid, block, sm, st>>>((TY*)dth, (const TY*)tm, (const TY*)s_raw, coef3, bcoef3, coef2, wgt, \
-                                                   partial, B, Tn, HW, C, cqc, FastDiv(HW))
+                                                   partial, B, Tn, HW, C, cpc)
   if (dtype == DWN_DT_F32) {
     if (Tn == 16) GO(float, 16); else if (Tn == 8) GO(float, 8); else GO(float, 0);
   } else {

@@ -124,8 +124,9 @@ constexpr int GT_BM = 128;        // UMMA M (cta_group::1)
 constexpr int GT_BK = 64;         // one 128-byte swizzle atom of bf16 along K
 constexpr int GT_A_BYTES = GT_BM * GT_BK * 2;
 constexpr int GT_STAGE_PITCH = 272;                    // staging row pitch (bytes): 64 fp32 + 16 pad
-constexpr int GT_STAGING_BYTES = 4 * 32 * GT_STAGE_PITCH;
-constexpr int GT_THREADS = 192;   // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int GT_EPI_WARPS = 8;   // two warps per TMEM lane quarter, interleaved over 64-column sub-tiles
+constexpr int GT_STAGING_BYTES = GT_EPI_WARPS * 32 * GT_STAGE_PITCH;
+constexpr int GT_THREADS = 64 + 32 * GT_EPI_WARPS;   // warp0 TMA, warp1 MMA, warps2.. epilogue
 
 struct GemmTcParams {
   int K, K2, block_n, b_bytes, stages;  // K2 > 0: D += A2 (MxK2) * B2^T (second operand pair, same majors)
@@ -154,7 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], GT_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -234,9 +235,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (warp >= 2) {
-    // ================= epilogue (4 warps; warp w owns TMEM lanes 32*(w%4)..+31) =================
+    // ================= epilogue (8 warps; warp w owns TMEM lanes 32*(w%4)..+31 and every other sub-tile) ======
     const int q = warp & 3;
-    uint8_t* my_stage = staging + (size_t)q * 32 * GT_STAGE_PITCH;
+    const int hsel = (warp - 2) >> 2;  // 0 / 1: which of the interleaved column sub-tiles this warp stores
+    uint8_t* my_stage = staging + (size_t)(warp - 2) * 32 * GT_STAGE_PITCH;
     const EpiParams& e = p.e;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -254,7 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int esz = e.d_bf16 ? 2 : 4;
         const int nvec = 64 * esz / 16;  // 16-byte vectors per 64-column row segment
         uint8_t* dbase = (uint8_t*)e.D + (size_t)z * e.d_zstride * esz;
-        for (int c0 = 0; c0 < p.block_n; c0 += 64) {
+        for (int c0 = hsel * 64; c0 < p.block_n; c0 += 128) {
           if (n0 + c0 >= e.n_limit) break;
           uint32_t v0[32], v1[32];
           tmem_ld32(taddr + c0, v0);
@@ -305,7 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int gn = z * e.row_offset_per_z + row;
         const float bias = row_ok ? e.bias[gn] : 0.f;
         float* out = (float*)e.D;
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        for (int c0 = hsel * 32; c0 < p.block_n; c0 += 64) {
           if (n0 + c0 >= e.n_limit) break;
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);

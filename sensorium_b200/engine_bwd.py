@@ -16,7 +16,7 @@ from ._lib import call, gemm
 from .engine import BF16, F32, _P, _P_SDW, _empty, _shadow, _split_k, _stream
 
 _J_CORTEX = 32
-_J_TDW = 16
+_J_TDW = 37
 
 
 def _bn_bwd(part, P, NQ, q0, count, bn, grads, C, st, dev):

@@ -71,7 +71,7 @@ for tag, ci, H, W, s in shapes:
     timeit(f"se_pool {tag}", lambda: call("dwn_se_pool", Tm, c3, A, pp, 16, B, T * Ho * Wo, mid, 1, st), 2 * Mo * mid * es)
     da = torch.randn(Mo, mid, device=dev).to(torch.bfloat16)
     dmean = torch.randn(B, mid, device=dev) * 0.01
-    timeit(f"tdw_bwd_reduce {tag}", lambda: call("dwn_tdw_bwd_reduce", da, Tm, c3, dmean, T * Ho * Wo, part, 16, B, mid, 1, st), 3 * Mo * mid * es)
+    timeit(f"tdw_bwd_reduce {tag}", lambda: call("dwn_tdw_bwd_reduce", da, Tm, c3, dmean, T * Ho * Wo, part, 37, B, mid, 1, st), 3 * Mo * mid * es)
     timeit(f"tdw_bwd {tag}", lambda: call("dwn_tdw_bwd", da, Tm, S, c3, b3, c2, wt, part, P, B, T, Ho * Wo, mid, 1, st), 4 * Mo * mid * es)
     dE = torch.empty_like(E)
     timeit(f"sdw_bwd {tag}", lambda: call("dwn_sdw_bwd", da, S, E, c2, b2, c1, ws, dE, part, PS, B * T, H, W, mid, s, 1, st), (2 * Mo + 2 * Mi) * mid * es)
