@@ -108,6 +108,11 @@ int dwn_block_bwd_dy(const float* dO, const void* y_raw, const float* coef4, con
 int dwn_block_in_bwd(const float* dXpw, const float* dO, const float* xin, const float* coef_sc, const float* bcoef_sc,
                      const float* colbias, float* dXin, int B, int Tn, int Hi, int Wi, int Ci, int Co, int stride,
                      void* stream);                                                        /* dwiseneuro.py:125-134 */
+int dwn_block_in_bwd_stem(const float* dXpw, const float* dO, const float* xin, const float* coef_sc,
+                          const float* bcoef_sc, const float* colbias, const float* x_in, float* stem_partial, int B, int Tn,
+                          int Hi, int Wi, int Ci, int Co, int stride, void* stream);  /* block 0 + stem reductions fused */
+int dwn_stem_bwd_finalize(const float* partial, int P, const double* mom, const float* w, const float* coef, float* dw,
+                          float* dgamma, float* dbeta, int B, int cin, long plane, int C0, void* stream);
 int dwn_pool_bwd(const float* dP, float* dX, long BT, int HW, int C, void* stream);       /* dwiseneuro.py:374,400 */
 int dwn_se_bwd(const float* Pp, const float* wt, const float* gate, const float* hpre, const float* mean,
                const float* w1, const float* w2, float* dpre2, float* dhpre, float* dmean, float* dwpwl, float* dw2,

@@ -50,6 +50,8 @@ SIGNATURES = {
     "dwn_block_bwd_reduce": "ppppppp" + "iiiiiiiii" + "p",
     "dwn_block_bwd_dy": "pppppp" + "llii" + "p",
     "dwn_block_in_bwd": "ppppppp" + "iiiiiii" + "p",
+    "dwn_block_in_bwd_stem": "pppppppp" + "iiiiiii" + "p",
+    "dwn_stem_bwd_finalize": "pi" + "pppppp" + "iili" + "p",
     "dwn_pool_bwd": "pp" + "lii" + "p",
     "dwn_se_bwd": "ppppppp" + "pppppppp" + "iiii" + "p",
     "dwn_tdw_bwd_reduce": "pppp" + "i" + "p" + "iiii" + "p",

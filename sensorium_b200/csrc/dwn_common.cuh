@@ -177,6 +177,23 @@ template <> __device__ __forceinline__ f32x2 bnsilu2<float>(f32x2 x, f32x2 p0, f
   upk2(x, x0, x1); upk2(p0, a0, a1); upk2(p1, b0, b1);
   return pk2(BnSilu<float>::act(x0, a0, b0), BnSilu<float>::act(x1, a1, b1));
 }
+// packed pair version of BnSilu<bf16>::act_grad: returns silu, writes d silu / d v
+__device__ __forceinline__ f32x2 bnsilu_grad2_bf16(f32x2 x, f32x2 p0, f32x2 p1, f32x2& g) {
+  f32x2 h = p1;
+  ffma2(h, x, p0);
+  float h0, h1;
+  upk2(h, h0, h1);
+  const f32x2 t = pk2(tanh_approx(h0), tanh_approx(h1));
+  f32x2 sa = h;
+  ffma2(sa, h, t);                                  // v*sigmoid(v)
+  f32x2 w = pk2(0.5f, 0.5f);
+  ffma2(w, t, pk2(-0.5f, -0.5f));                   // 1 - sigmoid(v)
+  f32x2 one_m_w = pk2(1.0f, 1.0f);
+  ffma2(one_m_w, w, pk2(-1.0f, -1.0f));             // sigmoid(v)
+  g = one_m_w;
+  ffma2(g, sa, w);                                  // sigmoid + silu*(1-sigmoid)
+  return sa;
+}
 // 4 channels -> two packed pairs
 __device__ __forceinline__ void ldq2(const float* p, f32x2 (&o)[2]) {
   const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(p);

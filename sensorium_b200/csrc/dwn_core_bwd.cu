@@ -8,6 +8,11 @@
 #include "dwn_sdw_v3.cuh"
 #include <type_traits>
 
+__global__ void stem_bwd_finalize_kernel(const float* __restrict__ partial, int P, int cin, const double* __restrict__ mom,
+                                         double count, const float* __restrict__ w, const float* __restrict__ coef,
+                                         float* __restrict__ dw, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                         int C0);
+
 // =================================================================================================
 // BN backward finalize: partial[P][NQ][C] (quantities q0, q0+1 = sum dy, sum dy*xhat)
 //   -> dgamma, dbeta (parameter gradients) and bcoef[2][C] = sums / N
@@ -20,11 +25,23 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
   const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   float a = 0.f, b = 0.f;
-  if (c < C)
-    for (int p = sl; p < P; p += 32) {
-      a += partial[((long)p * NQ + q0) * C + c];
-      b += partial[((long)p * NQ + q0 + 1) * C + c];
+  if (c < C) {
+    float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+    int p = sl;
+    for (; p + 96 < P; p += 128) {  // four independent partial rows in flight
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a4[u] += partial[((long)(p + 32 * u) * NQ + q0) * C + c];
+        b4[u] += partial[((long)(p + 32 * u) * NQ + q0 + 1) * C + c];
+      }
     }
+    for (; p < P; p += 32) {
+      a4[0] += partial[((long)p * NQ + q0) * C + c];
+      b4[0] += partial[((long)p * NQ + q0 + 1) * C + c];
+    }
+    a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    b = (b4[0] + b4[1]) + (b4[2] + b4[3]);
+  }
   s0[sl][cl] = a;
   s1[sl][cl] = b;
   __syncthreads();
@@ -158,11 +175,17 @@ extern "C" int dwn_block_bwd_dy(const float* dO, const void* y_raw, const float*
 }
 
 // gradient w.r.t. the block input: point-wise dgrad + shortcut path (nearest scatter, cyclic-tile sum, BN_sc bwd)
+template <int STEM_CIN>  // > 0: this is block 0 -> accumulate the stem reductions G[c][k], S[c] instead of storing dX0
 __global__ void block_in_bwd_kernel(const float* __restrict__ dXpw, const float* __restrict__ dO,
                                     const float* __restrict__ xin, const float* __restrict__ coef_sc,
                                     const float* __restrict__ bcoef_sc, const float* __restrict__ colbias,
                                     float* __restrict__ dXin, int B, int Tn, int Hi, int Wi, int Ci, int Co, int stride,
-                                    int cqc, FastDiv dw, FastDiv dh) {
+                                    int cqc, FastDiv dw, FastDiv dh, const float* __restrict__ x_in,
+                                    float* __restrict__ stem_partial) {
+  extern __shared__ float smem[];
+  constexpr int SQ = STEM_CIN > 0 ? STEM_CIN + 1 : 1;
+  float sst[SQ][4] = {};
+  const int plane = Tn * Hi * Wi;
   const int tid = threadIdx.x;
   const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
   const int c = (blockIdx.y * cqc + cq) * 4;
@@ -208,8 +231,22 @@ __global__ void block_in_bwd_kernel(const float* __restrict__ dXpw, const float*
         for (int j = 0; j < 4; ++j) o[j] = fmaf(a[1][j], g[j], o[j]);
       }
     }
-    stq(dXin + (long)m * Ci + c, o);
+    if (STEM_CIN > 0) {
+      const int b = bt / Tn, pos = m - b * plane;
+#pragma unroll
+      for (int k = 0; k < STEM_CIN; ++k) {
+        const float xv = __ldg(&x_in[((long)b * STEM_CIN + k) * plane + pos]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sst[k][j] = fmaf(o[j], xv, sst[k][j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sst[SQ - 1][j] += o[j];
+    } else {
+      stq(dXin + (long)m * Ci + c, o);
+    }
   }
+  if (STEM_CIN > 0)
+    block_reduce_channels<SQ, 4>(sst, smem, cqc, ln, stem_partial + (long)blockIdx.x * SQ * Ci, Ci, blockIdx.y * cqc * 4);
 }
 
 extern "C" int dwn_block_in_bwd(const float* dXpw, const float* dO, const float* xin, const float* coef_sc,
@@ -218,8 +255,33 @@ extern "C" int dwn_block_in_bwd(const float* dXpw, const float* dO, const float*
   DWN_REQUIRE(Co <= 2 * Ci, "dwn_block_in_bwd: channel tiling factor > 2 unsupported (Co=%d Ci=%d)", Co, Ci);
   int cqc = dwn_largest_divisor_le(Ci / 4, 64), ln = 256 / cqc;
   dim3 grid(592, (Ci / 4) / cqc), block(cqc * ln);
-  block_in_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dXpw, dO, xin, coef_sc, bcoef_sc, colbias, dXin, B, Tn, Hi, Wi, Ci,
-                                                                Co, stride, cqc, FastDiv(Wi), FastDiv(Hi));
+  block_in_bwd_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(dXpw, dO, xin, coef_sc, bcoef_sc, colbias, dXin, B, Tn,
+                                                                   Hi, Wi, Ci, Co, stride, cqc, FastDiv(Wi), FastDiv(Hi),
+                                                                   nullptr, nullptr);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// block 0 variant: the gradient w.r.t. the stem output is consumed on the fly by the stem reductions
+// (partial[592][6][Ci], same layout as dwn_stem_bwd) and never written to HBM.  in_channels == 5 only.
+extern "C" int dwn_block_in_bwd_stem(const float* dXpw, const float* dO, const float* xin, const float* coef_sc,
+                                     const float* bcoef_sc, const float* colbias, const float* x_in, float* stem_partial,
+                                     int B, int Tn, int Hi, int Wi, int Ci, int Co, int stride, void* stream) {
+  DWN_REQUIRE(Co <= 2 * Ci, "dwn_block_in_bwd_stem: channel tiling factor > 2 unsupported");
+  int cqc = dwn_largest_divisor_le(Ci / 4, 64), ln = 256 / cqc;
+  dim3 grid(592, (Ci / 4) / cqc), block(cqc * ln);
+  block_in_bwd_kernel<5><<<grid, block, block.x * 24 * sizeof(float), (cudaStream_t)stream>>>(
+      dXpw, dO, xin, coef_sc, bcoef_sc, colbias, nullptr, B, Tn, Hi, Wi, Ci, Co, stride, cqc, FastDiv(Wi), FastDiv(Hi), x_in,
+      stem_partial);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dwn_stem_bwd_finalize(const float* partial, int P, const double* mom, const float* w, const float* coef,
+                                     float* dw, float* dgamma, float* dbeta, int B, int cin, long plane, int C0,
+                                     void* stream) {
+  stem_bwd_finalize_kernel<<<(C0 + 7) / 8, 256, 0, (cudaStream_t)stream>>>(partial, P, cin, mom, (double)B * plane, w, coef,
+                                                                            dw, dgamma, dbeta, C0);
   DWN_LAUNCH_CHECK();
   return 0;
 }
@@ -797,14 +859,20 @@ static int sdw_bwd_v3_launch(const void* dsh, const void* s_raw, const void* e_r
   if (sm_red > sm) sm = sm_red;
   const int nchunks = C / CC;
   dim3 grid(P * nchunks), block(256);
-#define LAUNCH(THI_)                                                                                               \
+#define LAUNCH(THI_, CC_)                                                                                          \
   {                                                                                                                \
-    auto k = sdw_bwd_v3_kernel<S, THI_>;                                                                           \
+    auto k = sdw_bwd_v3_kernel<S, THI_, CC_>;                                                                      \
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                                 \
     k<<<grid, block, sm, st>>>((const bf16*)dsh, (const bf16*)s_raw, (const bf16*)e_raw, coef2, bcoef2, coef1, wgt, \
-                               (bf16*)dE, partial, NP, H, W, C, CC, nchunks, nbsh, cvsh);                          \
+                               (bf16*)dE, partial, NP, H, C, nchunks, nbsh);                                       \
   }
-  if (THI == 8) LAUNCH(8) else LAUNCH(4)
+  if (THI == 8) {
+    if (CC == 16) LAUNCH(8, 16) else if (CC == 32) LAUNCH(8, 32) else if (CC == 64) LAUNCH(8, 64)
+    else if (CC == 128) LAUNCH(8, 128) else return 1;
+  } else {
+    if (CC == 16) LAUNCH(4, 16) else if (CC == 32) LAUNCH(4, 32) else if (CC == 64) LAUNCH(4, 64)
+    else if (CC == 128) LAUNCH(4, 128) else return 1;
+  }
 #undef LAUNCH
   DWN_LAUNCH_CHECK();
   return 0;
@@ -943,19 +1011,23 @@ __global__ void stem_bwd_reduce_kernel(const float* __restrict__ dy, const float
                                     blockIdx.y * cqc * 4);
 }
 
-// one thread per output channel, double precision
+// one warp per output channel (lanes stride over the partial rows), double precision
 __global__ void stem_bwd_finalize_kernel(const float* __restrict__ partial, int P, int cin, const double* __restrict__ mom,
                                          double count, const float* __restrict__ w, const float* __restrict__ coef,
                                          float* __restrict__ dw, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                          int C0) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C0) return;
   double G[8], S = 0;
   for (int k = 0; k < cin; ++k) G[k] = 0;
-  for (int p = 0; p < P; ++p) {
+  for (int p = lane; p < P; p += 32) {
     for (int k = 0; k < cin; ++k) G[k] += (double)partial[((long)p * (cin + 1) + k) * C0 + c];
     S += (double)partial[((long)p * (cin + 1) + cin) * C0 + c];
   }
+  for (int k = 0; k < cin; ++k) G[k] = warp_sum_d(G[k]);
+  S = warp_sum_d(S);
+  if (lane != 0) return;
   // second moments X2[j][k] from the packed upper triangle
   double X1[8], X2[8][8];
   int q = cin;
@@ -992,7 +1064,7 @@ extern "C" int dwn_stem_bwd(const float* dy, const float* x, float* partial, int
     default: return dwn_fail("dwn_stem_bwd: in_channels=%d unsupported", cin);
   }
   DWN_LAUNCH_CHECK();
-  stem_bwd_finalize_kernel<<<(C0 + 63) / 64, 64, 0, st>>>(partial, P, cin, mom, (double)M, w, coef, dw, dgamma, dbeta, C0);
+  stem_bwd_finalize_kernel<<<(C0 + 7) / 8, 256, 0, st>>>(partial, P, cin, mom, (double)M, w, coef, dw, dgamma, dbeta, C0);
   DWN_LAUNCH_CHECK();
   return 0;
 }

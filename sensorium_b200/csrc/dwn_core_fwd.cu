@@ -143,10 +143,21 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
     double s = 0, q = 0;
     if (c < C) {
       const int cp = c % Cp;
-      for (int p = sl; p < P; p += 32) {
-        s += (double)partial[((long)p * NQ) * Cp + cp];
-        q += (double)partial[((long)p * NQ + 1) * Cp + cp];
+      float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+      int p = sl;
+      for (; p + 96 < P; p += 128) {  // four independent partial rows in flight
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          s4[u] += partial[((long)(p + 32 * u) * NQ) * Cp + cp];
+          q4[u] += partial[((long)(p + 32 * u) * NQ + 1) * Cp + cp];
+        }
       }
+      for (; p < P; p += 32) {
+        s4[0] += partial[((long)p * NQ) * Cp + cp];
+        q4[0] += partial[((long)p * NQ + 1) * Cp + cp];
+      }
+      s = ((double)s4[0] + (double)s4[1]) + ((double)s4[2] + (double)s4[3]);
+      q = ((double)q4[0] + (double)q4[1]) + ((double)q4[2] + (double)q4[3]);
     }
     s_sum[sl][cl] = s;
     s_sq[sl][cl] = q;
@@ -426,20 +437,26 @@ static int sdw_fwd_v3_launch(const void* in, const float* coef, const float* wgt
   const int nbsh = ilog2_exact(Ho / THO);
   if (nbsh < 0) return 1;
   const size_t nvec = (size_t)NR * vpr;
-  size_t sm = 2 * nvec * 16 + (size_t)NR * (W + 2) * CC * sizeof(float);
+  size_t sm = 2 * nvec * 16 + ((size_t)NR * (W + 2) + 2) * CC * sizeof(float);
   const int nchunks = C / CC;
   dim3 grid(P * nchunks), block(256);
-#define LAUNCH(THO_, RPI_)                                                                                     \
+#define LAUNCH(THO_, RPI_, CC_)                                                                                \
   {                                                                                                            \
-    auto k = sdw_fwd_v3_kernel<S, THO_, RPI_>;                                                                 \
+    auto k = sdw_fwd_v3_kernel<S, THO_, RPI_, CC_>;                                                            \
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                             \
-    k<<<grid, block, sm, st>>>((const bf16*)in, coef, wgt, (bf16*)out, partial, NP, H, W, C, CC, nchunks, nbsh, cvsh); \
+    k<<<grid, block, sm, st>>>((const bf16*)in, coef, wgt, (bf16*)out, partial, NP, H, C, nchunks, nbsh);      \
   }
+  // vpr = W*CC/8 = S*128 -> rpi = 2 for stride 1, 1 for stride 2
   if constexpr (S == 1) {
-    if (THO == 8) { if (rpi == 2) LAUNCH(8, 2) else LAUNCH(8, 1) } else { if (rpi == 2) LAUNCH(4, 2) else LAUNCH(4, 1) }
+    if (rpi != 2) return 1;
+    if (THO == 8) {
+      if (CC == 32) LAUNCH(8, 2, 32) else if (CC == 64) LAUNCH(8, 2, 64) else if (CC == 128) LAUNCH(8, 2, 128) else return 1;
+    } else {
+      if (CC == 32) LAUNCH(4, 2, 32) else if (CC == 64) LAUNCH(4, 2, 64) else if (CC == 128) LAUNCH(4, 2, 128) else return 1;
+    }
   } else {
     if (rpi != 1) return 1;
-    LAUNCH(2, 1)
+    if (CC == 32) LAUNCH(2, 1, 32) else if (CC == 64) LAUNCH(2, 1, 64) else if (CC == 128) LAUNCH(2, 1, 128) else return 1;
   }
 #undef LAUNCH
   DWN_LAUNCH_CHECK();

@@ -24,31 +24,35 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 //   RPI = tile rows covered by one pass of the 256 threads over the raw tile (256 / (W * CC/8), 1 or 2).
 //   All per-vector addresses are loop-invariant per thread plus a compile-time multiple of a per-row step.
 // =================================================================================================
-template <int S, int THO, int RPI>
+template <int S, int THO, int RPI, int CC>
 __global__ void __launch_bounds__(256, 2)
 sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, const float* __restrict__ wgt,
-                  bf16* __restrict__ out, float* __restrict__ partial, int NP, int H, int W, int C, int CC, int nchunks,
-                  int nbsh, int cvsh) {
+                  bf16* __restrict__ out, float* __restrict__ partial, int NP, int H, int C, int nchunks, int nbsh) {
+  // CC (channels per CTA) is a template parameter: with (CC/4)*Wo == 256 the tile geometry W, Wo, WP and every
+  // shared-memory offset become compile-time constants (immediate LDS/STS offsets, no per-tap integer adds)
+  constexpr int Wo = 1024 / CC, W = Wo * S, WP = W + 2;
+  constexpr int cvn = CC / 8, cvsh = (cvn == 2 ? 1 : cvn == 4 ? 2 : cvn == 8 ? 3 : 4);
   constexpr int NR = (THO - 1) * S + 3;
   constexpr int NIT = NR / RPI;
   static_assert(NR % RPI == 0, "tile rows must be a multiple of the rows per pass");
+  static_assert(W * cvn == 256 / RPI, "RPI must match the tile geometry");
   extern __shared__ __align__(16) unsigned char smem_v3[];
-  const int Ho = H / S, Wo = W / S, WP = W + 2;
+  const int Ho = H / S;
   const int tid = threadIdx.x;
   const int chunk = blockIdx.x % nchunks, worker = blockIdx.x / nchunks, nworkers = gridDim.x / nchunks;
   const int c0 = chunk * CC;
-  const int cvn = CC >> 3;
   constexpr int NVEC = NR * (256 / RPI);  // 16-byte vectors per raw tile (W*cvn == 256/RPI)
   bf16* raw0 = reinterpret_cast<bf16*>(smem_v3);
   bf16* raw1 = raw0 + (size_t)NVEC * 8;
   float* act = reinterpret_cast<float*>(raw1 + (size_t)NVEC * 8);
+  float* sco = act + (size_t)NR * WP * CC;  // [2][CC] BN1+SiLU constants (kept out of the register file)
   // ---- loop-invariant coordinates of this thread inside one pass
-  const int vpr = 256 / RPI;                       // vectors per tile row
+  constexpr int vpr = 256 / RPI;                   // vectors per tile row
   const int r_first = tid / vpr;                   // 0 (RPI=1) or 0/1 (RPI=2)
   const int wq = (tid & (vpr - 1)) >> cvsh;
   const int lcv = tid & (cvn - 1);
   const int act_off0 = (r_first * WP + wq + 1) * CC + lcv * 8;
-  const int act_step = RPI * WP * CC;
+  constexpr int act_step = RPI * WP * CC;
   const long g_off0 = ((long)r_first * W + wq) * C + c0 + lcv * 8;
   const long g_step = (long)RPI * W * C;
   f32x2 lp0[4], lp1[4];
@@ -60,10 +64,10 @@ sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, c
     lp0[j] = pk2(a0, a1);
     lp1[j] = pk2(b0, b1);
   }
-  const int cqn = CC >> 2;
+  constexpr int cqn = CC >> 2;
   const int cq = tid % cqn, wo = tid / cqn;
   const float* act_rd = act + (wo * S) * CC + cq * 4;
-  const int row_step = WP * CC;
+  constexpr int row_step = WP * CC;
   f32x2 w2[9][2];
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
@@ -183,22 +187,24 @@ sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, c
 //   partial[P][11][C] = { sum dehat, sum dehat*xhat1, dw[0..8] }
 // The staged (output-sized) tile is Wo*CC/8 = 128/S vectors per row, i.e. RPI = 2*S rows per 256-thread pass.
 // =================================================================================================
-template <int S, int THI>
+template <int S, int THI, int CC>
 __global__ void __launch_bounds__(256, 2)
 sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, const bf16* __restrict__ e_raw,
                   const float* __restrict__ coef2, const float* __restrict__ bcoef2, const float* __restrict__ coef1,
-                  const float* __restrict__ wgt, bf16* __restrict__ dE, float* __restrict__ partial, int NP, int H, int W,
-                  int C, int CC, int nchunks, int nbsh, int cvsh) {
+                  const float* __restrict__ wgt, bf16* __restrict__ dE, float* __restrict__ partial, int NP, int H,
+                  int C, int nchunks, int nbsh) {
+  // CC is a template parameter: (CC/4)*W == 256 makes W, Wo, WP and all smem offsets compile-time constants
+  constexpr int W = 1024 / CC, Wo = W / S, WP = Wo + 2;
+  constexpr int cvn = CC / 8, cvsh = (cvn == 2 ? 1 : cvn == 4 ? 2 : cvn == 8 ? 3 : 4);
   constexpr int NR = S == 1 ? THI + 2 : THI / 2 + 1;
   constexpr int RPI = 2 * S;
   constexpr int NIT = (NR + RPI - 1) / RPI;
   constexpr int VPR = 256 / RPI;  // vectors per staged row
   extern __shared__ __align__(16) unsigned char smem_v3[];
-  const int Ho = H / S, Wo = W / S, WP = Wo + 2;
+  const int Ho = H / S;
   const int tid = threadIdx.x;
   const int chunk = blockIdx.x % nchunks, worker = blockIdx.x / nchunks, nworkers = gridDim.x / nchunks;
   const int c0 = chunk * CC;
-  const int cvn = CC >> 3;
   constexpr int NVEC = NIT * 256;
   constexpr int EVEC = THI * 128;  // E tile: THI rows x (W*CC/8 = 128) 16-byte vectors
   bf16* rawD = reinterpret_cast<bf16*>(smem_v3);
@@ -209,7 +215,7 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
   const int r_first = tid / VPR;
   const int two = (tid & (VPR - 1)) >> cvsh;  // output column handled in the staging passes
   const int lcv = tid & (cvn - 1);
-  const int cqn = CC >> 2;
+  constexpr int cqn = CC >> 2;
   const int cq = tid % cqn, wi = tid / cqn;
   const int cch = c0 + cq * 4;
   for (int i = tid; i < CC; i += 256) {
@@ -217,8 +223,8 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
     const float sc = coef2[cc], mu = coef2[2 * C + cc], rs = coef2[3 * C + cc];
     const float k1 = bcoef2[cc], k2 = bcoef2[C + cc];
     sco[i] = sc;
-    sco[CC + i] = sc * (k1 - mu * rs * k2);
-    sco[2 * CC + i] = sc * rs * k2;
+    sco[CC + i] = -sc * (k1 - mu * rs * k2);
+    sco[2 * CC + i] = -sc * rs * k2;
     float q0, q1;
     BnSilu<bf16>::prep(coef1[cc], coef1[C + cc], q0, q1);
     sco[3 * CC + i] = q0;
@@ -241,8 +247,9 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
   for (int q = 0; q < 11; ++q) { st2[q][0] = 0ull; st2[q][1] = 0ull; }
   const int nbm = (1 << nbsh) - 1;
   const int ntiles = NP << nbsh;
-  const int row_step = WP * CC;
+  constexpr int row_step = WP * CC;
   const int tile_off0 = (r_first * WP + two + (S == 1 ? 1 : 0)) * CC + lcv * 8;
+  const int h0 = (tid & 4) ? 4 : 0;  // conflict-free order of the two 16-byte STS (see sdw_fwd_v3_kernel)
   const long g_off0 = (long)two * C + c0 + lcv * 8;
   const long orow = (long)Wo * C;
   const long erow = (long)W * C;
@@ -289,22 +296,26 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
           const uint4 qg = *reinterpret_cast<const uint4*>(rawD + (size_t)(tid + it * 256) * 8);
           const uint4 qx = *reinterpret_cast<const uint4*>(rawS + (size_t)(tid + it * 256) * 8);
           const uint32_t gg[4] = {qg.x, qg.y, qg.z, qg.w}, xx[4] = {qx.x, qx.y, qx.z, qx.w};
-          const float* ca = sco + lcv * 8;
+          const f32x2* ca = reinterpret_cast<const f32x2*>(sco + lcv * 8);            // a
+          const f32x2* cb = reinterpret_cast<const f32x2*>(sco + CC + lcv * 8);       // -b
+          const f32x2* cd = reinterpret_cast<const f32x2*>(sco + 2 * CC + lcv * 8);   // -d
           float v[8];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float g0, g1, x0, x1;
             unpack_bf16x2(gg[j], g0, g1);
             unpack_bf16x2(xx[j], x0, x1);
-            v[2 * j] = fmaf(ca[2 * j], g0, -fmaf(ca[2 * CC + 2 * j], x0, ca[CC + 2 * j]));
-            v[2 * j + 1] = fmaf(ca[2 * j + 1], g1, -fmaf(ca[2 * CC + 2 * j + 1], x1, ca[CC + 2 * j + 1]));
+            f32x2 r = cb[j];                    // dS_raw = a*g - d*x - b
+            ffma2(r, ca[j], pk2(g0, g1));
+            ffma2(r, cd[j], pk2(x0, x1));
+            upk2(r, v[2 * j], v[2 * j + 1]);
           }
           o0 = make_float4(v[0], v[1], v[2], v[3]);
           o1 = make_float4(v[4], v[5], v[6], v[7]);
         }
         float* dst = tile + tile_off0 + it * RPI * row_step;
-        *reinterpret_cast<float4*>(dst) = o0;
-        *reinterpret_cast<float4*>(dst + 4) = o1;
+        *reinterpret_cast<float4*>(dst + h0) = h0 ? o1 : o0;
+        *reinterpret_cast<float4*>(dst + (4 - h0)) = h0 ? o0 : o1;
       }
     }
     cp_async_wait<0>();  // E tile landed
@@ -313,17 +324,15 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
     cp_async_commit();
     const bf16* esm = rawE + (size_t)wi * CC + cq * 4;  // row hl at + hl*W*CC
     // ---- transposed stencil + weight gradient, one input row at a time (E row prefetched one ahead)
-    const float4 qa0 = *reinterpret_cast<const float4*>(sco + 3 * CC + cq * 4);
-    const float4 qa1 = *reinterpret_cast<const float4*>(sco + 4 * CC + cq * 4);
-    const float pa0[4] = {qa0.x, qa0.y, qa0.z, qa0.w}, pa1[4] = {qa1.x, qa1.y, qa1.z, qa1.w};
+    const ulonglong2 qa0 = *reinterpret_cast<const ulonglong2*>(sco + 3 * CC + cq * 4);
+    const ulonglong2 qa1 = *reinterpret_cast<const ulonglong2*>(sco + 4 * CC + cq * 4);
     const float* tbase = tile + cq * 4 + ((S == 1) ? (wi + 2) * CC : 0);
     auto row_body = [&](const int hl, auto par_c) {
       constexpr int PAR = decltype(par_c)::value;
-      float e[4], ea[4], sg[4];
-      ldq(esm + hl * (W * CC), e);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ea[j] = BnSilu<bf16>::act_grad(e[j], pa0[j], pa1[j], sg[j]);
-      const f32x2 ea0 = pk2(ea[0], ea[1]), ea1 = pk2(ea[2], ea[3]);
+      f32x2 e2[2], sg0, sg1;
+      ldq2(esm + hl * (W * CC), e2);
+      const f32x2 ea0 = bnsilu_grad2_bf16(e2[0], qa0.x, qa1.x, sg0);
+      const f32x2 ea1 = bnsilu_grad2_bf16(e2[1], qa0.y, qa1.y, sg1);
       f32x2 acc0 = 0ull, acc1 = 0ull;
       if (S == 1) {
         const float* trow = tbase + hl * row_step;  // tap (kh,kw) sits at trow + (2-kh)*row_step - kw*CC
@@ -366,24 +375,16 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
           }
         }
       }
-      float a[4], o[4];
-      upk2(acc0, a[0], a[1]);
-      upk2(acc1, a[2], a[3]);
-      const float4 qm = *reinterpret_cast<const float4*>(sco + 5 * CC + cq * 4);
-      const float4 qr = *reinterpret_cast<const float4*>(sco + 6 * CC + cq * 4);
-      const float mu1[4] = {qm.x, qm.y, qm.z, qm.w}, rs1[4] = {qr.x, qr.y, qr.z, qr.w};
-      float xh[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        o[j] = a[j] * sg[j];
-        xh[j] = (e[j] - mu1[j]) * rs1[j];
-      }
-      stq(dp + hl * erow, o);
-      const f32x2 o0 = pk2(o[0], o[1]), o1 = pk2(o[2], o[3]);
-      fadd2(st2[0][0], o0);
-      fadd2(st2[0][1], o1);
-      ffma2(st2[1][0], o0, pk2(xh[0], xh[1]));
-      ffma2(st2[1][1], o1, pk2(xh[2], xh[3]));
+      f32x2 o2[2];
+      o2[0] = fmul2(acc0, sg0);
+      o2[1] = fmul2(acc1, sg1);
+      stq2(dp + hl * erow, o2);
+      // statistics on the raw E: sum(o) and sum(o*e); sum(o*xhat) = rstd*(sum(o*e) - mean*sum(o)) is formed once
+      // per CTA after the tile loop
+      fadd2(st2[0][0], o2[0]);
+      fadd2(st2[0][1], o2[1]);
+      ffma2(st2[1][0], o2[0], e2[0]);
+      ffma2(st2[1][1], o2[1], e2[1]);
     };
     if (S == 1) {
 #pragma unroll 1
@@ -401,5 +402,9 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
   float st[11][4];
 #pragma unroll
   for (int q = 0; q < 11; ++q) { upk2(st2[q][0], st[q][0], st[q][1]); upk2(st2[q][1], st[q][2], st[q][3]); }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)  // sum(o*xhat1) from the raw-E sums
+    st[1][j] = coef1[3 * C + cch + j] * (st[1][j] - coef1[2 * C + cch + j] * st[0][j]);
   block_reduce_channels<11, 4>(st, reinterpret_cast<float*>(smem_v3), cqn, W, partial + (long)worker * 11 * C, C, c0);
 }
+

@@ -82,6 +82,43 @@ def set_shadow(p: torch.Tensor, sh: torch.Tensor) -> None:
     p._dwn_shadow = (p._version, sh, p.data_ptr())
 
 
+_side = {}
+
+
+class _nullctx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+def _side_streams(dev, njobs, n=3):
+    """Side streams for independent per-mouse launches (readout GEMMs)."""
+    if njobs < 2:
+        return []
+    key = (dev.index, n)
+    if key not in _side:
+        _side[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+    return _side[key]
+
+
+def _fork(side, dev):
+    if side:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        for s in side:
+            s.wait_event(ev)
+
+
+def _join(side, dev):
+    main = torch.cuda.current_stream(dev)
+    for s in side:
+        ev = torch.cuda.Event()
+        ev.record(s)
+        main.wait_event(ev)
+
+
 def _bn_coef(bn, partial, P, count, C, Cp, training, st, dev, NQ=2):
     coef = _empty((4, C), torch.float32, dev)
     if training:
@@ -298,29 +335,42 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
     mice = range(len(outs)) if index is None else [index]
     preds: List[torch.Tensor] = []
     p_drop = cfg["drop_rate"]
+    # phase 1 (main stream): RNG masks in the reference's order and every allocation
+    jobs = []
     for m in mice:
         n_out = outs[m]
-        half = math.ceil(n_out / G)
-        conv = mod.readouts[m].layer[1]
         mask = None
         if training and p_drop > 0.0:
             mask = torch.empty((B, K, 1), dtype=torch.float32, device=rng_dev or dev).bernoulli_(1.0 - p_drop).div_(
                 1.0 - p_drop).to(dev)
         if mask is None and not save:
             xm, xt = (cxb if bf else cx), None
+            prep = False
         else:
             xm = _empty((Mbt, K), adt, dev)
             xt = _empty((K, Mbt), adt, dev) if save else None
-            call("dwn_readout_prep", cx, mask, xm, xt, Mbt, K, T, dcode, st)
-        pred = _empty((B, n_out, T), torch.float32, dev)
+            prep = True
+        conv = mod.readouts[m].layer[1]
         wr = conv.weight
-        gemm(st, dtype=dcode, A=_shadow(wr) if bf else wr, B=xm, lda=Kg, ldb=K, a_zstride=half * Kg, b_zstride=Kg,
-             a_zmode=1, b_zmode=1, M=half, N=Mbt, K=Kg, Z=G, epi=1, D=pred, bias=conv.bias, beta=cfg["softplus_beta"],
-             Tn=T, n_out_total=n_out, row_offset_per_z=half, n_limit=Mbt, _tag="readout_fwd",
-             _bytes=G * half * Kg * es + Mbt * K * es + B * n_out * T * 4)
+        jobs.append((m, n_out, math.ceil(n_out / G), conv, _shadow(wr) if bf else wr, mask, xm, xt, prep,
+                     _empty((B, n_out, T), torch.float32, dev)))
+    # phase 2: the per-mouse GEMMs are independent and each fills well under half of the SMs (~62 CTAs), so they
+    # are issued round-robin on side streams and overlap on the device
+    side = _side_streams(dev, len(jobs))
+    _fork(side, dev)
+    for j, (m, n_out, half, conv, wq, mask, xm, xt, prep, pred) in enumerate(jobs):
+        with torch.cuda.stream(side[j % len(side)]) if side else _nullctx():
+            sst = _stream(dev)
+            if prep:
+                call("dwn_readout_prep", cx, mask, xm, xt, Mbt, K, T, dcode, sst)
+            gemm(sst, dtype=dcode, A=wq, B=xm, lda=Kg, ldb=K, a_zstride=half * Kg, b_zstride=Kg, a_zmode=1, b_zmode=1,
+                 M=half, N=Mbt, K=Kg, Z=G, epi=1, D=pred, bias=conv.bias, beta=cfg["softplus_beta"], Tn=T,
+                 n_out_total=n_out, row_offset_per_z=half, n_limit=Mbt, _tag="readout_fwd",
+                 _bytes=G * half * Kg * es + Mbt * K * es + B * n_out * T * 4)
         preds.append(pred)
         if save:
             sv.readouts.append(SimpleNamespace(m=m, mask=mask, xm=xm, xt=xt, pred=pred, n_out=n_out, half=half))
+    _join(side, dev)
     if save:
         sv.cx = cx
         sv.index = index

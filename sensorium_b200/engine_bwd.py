@@ -13,7 +13,8 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from ._lib import call, gemm
-from .engine import BF16, F32, _P, _P_SDW, _empty, _shadow, _split_k, _stream
+from .engine import (BF16, F32, _P, _P_SDW, _empty, _fork, _join, _nullctx, _shadow, _side_streams, _split_k,
+                     _stream)
 
 _J_CORTEX = 32
 _J_TDW = 37
@@ -57,27 +58,35 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         dxm = _empty((len(live), Mbt, K), torch.float32, dev)
         has_mask = live[0][0].mask is not None
         masks = torch.stack([r.mask.reshape(B, K) for r, _ in live]).contiguous() if has_mask else None
+        # allocations on the main stream, then the independent per-mouse kernels round-robin on side streams
+        jobs = []
         for j, (r, g) in enumerate(live):
             conv = mod.readouts[r.m].layer[1]
             half = r.half
             half_pad = ((half + 63) // 64) * 64
-            dz_nm = _empty((G * half, Mbt), adt, dev)
-            dz_mn = _empty((Mbt, G * half_pad), adt, dev)
-            db = _empty((G * half,), torch.float32, dev)
-            call("dwn_readout_bwd_prep", r.pred, g.contiguous(), cfg["softplus_beta"], dz_nm, dz_mn, db, B, T, r.n_out,
-                 half, half_pad, G, dcode, st)
-            dW = _empty((G * half, Kg, 1), torch.float32, dev)
-            gemm(st, dtype=dcode, A=dz_nm, B=r.xt, lda=Mbt, ldb=Mbt, a_zstride=half * Mbt, b_zstride=Kg * Mbt, a_zmode=1,
-                 b_zmode=1, M=half, N=Kg, K=Mbt, Z=G, D=dW, d_dtype=F32, ldd=Kg, d_zstride=half * Kg, _tag="readout_wgrad",
-                 _bytes=G * half * Mbt * es + K * Mbt * es + G * half * Kg * 4)
             wr = conv.weight
-            gemm(st, dtype=dcode, A=dz_mn, B=_shadow(wr) if bf else wr, b_mn=1, lda=G * half_pad, ldb=Kg,
-                 a_zstride=half_pad, b_zstride=half * Kg, a_zmode=1, b_zmode=1, M=Mbt, N=Kg, K=half, Z=G, D=dxm[j],
-                 d_dtype=F32, ldd=K, d_zstride=Kg, _tag="readout_dgrad",
-                 _bytes=Mbt * G * half_pad * es + G * half * Kg * es + Mbt * K * 4)
+            jobs.append((r, g.contiguous(), conv, half, half_pad, _empty((G * half, Mbt), adt, dev),
+                         _empty((Mbt, G * half_pad), adt, dev), _empty((G * half,), torch.float32, dev),
+                         _empty((G * half, Kg, 1), torch.float32, dev), _shadow(wr) if bf else wr))
+        side = _side_streams(dev, len(jobs))
+        _fork(side, dev)
+        for j, (r, g, conv, half, half_pad, dz_nm, dz_mn, db, dW, wq) in enumerate(jobs):
+            with torch.cuda.stream(side[j % len(side)]) if side else _nullctx():
+                sst = _stream(dev)
+                call("dwn_readout_bwd_prep", r.pred, g, cfg["softplus_beta"], dz_nm, dz_mn, db, B, T, r.n_out, half,
+                     half_pad, G, dcode, sst)
+                gemm(sst, dtype=dcode, A=dz_nm, B=r.xt, lda=Mbt, ldb=Mbt, a_zstride=half * Mbt, b_zstride=Kg * Mbt,
+                     a_zmode=1, b_zmode=1, M=half, N=Kg, K=Mbt, Z=G, D=dW, d_dtype=F32, ldd=Kg, d_zstride=half * Kg,
+                     _tag="readout_wgrad", _bytes=G * half * Mbt * es + K * Mbt * es + G * half * Kg * 4)
+                gemm(sst, dtype=dcode, A=dz_mn, B=wq, b_mn=1, lda=G * half_pad, ldb=Kg, a_zstride=half_pad,
+                     b_zstride=half * Kg, a_zmode=1, b_zmode=1, M=Mbt, N=Kg, K=half, Z=G, D=dxm[j], d_dtype=F32, ldd=K,
+                     d_zstride=Kg, _tag="readout_dgrad",
+                     _bytes=Mbt * G * half_pad * es + G * half * Kg * es + Mbt * K * 4)
             grads[conv.weight] = dW
             grads[conv.bias] = db
-            if dp is not None:
+        _join(side, dev)
+        if dp is not None:
+            for (r, g, conv, *_rest) in jobs:
                 dp.reduce(grads, [conv.weight, conv.bias])
         call("dwn_readout_dx_combine", dxm, masks, len(live), dX, Mbt, K, T, st)
     else:
@@ -218,10 +227,18 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
             call("dwn_reduce_rows", wpart, Zs, mid * ci, dwpw, st)
         grads[wpw] = dwpw
         del dE
-        dXin = _empty((Mi, ci), torch.float32, dev)
-        call("dwn_block_in_bwd", dXpw, dO, b.X, b.coef_sc, bcoef_sc, colbias, dXin, B, T, b.Hi, b.Wi, ci, co, s, st,
-             _tag="block_in_bwd", _bytes=Mi * ci * 12 + Mo * co * 4)
-        dO = dXin
+        stem_fused = i == 0 and mod.core.stem[0].weight.shape[1] == 5
+        if stem_fused:
+            # block 0: the gradient w.r.t. the stem output feeds the stem reductions directly (never stored)
+            stem_part = _empty((_P, 6, ci), torch.float32, dev)
+            call("dwn_block_in_bwd_stem", dXpw, dO, b.X, b.coef_sc, bcoef_sc, colbias, sv.x, stem_part, B, T, b.Hi, b.Wi,
+                 ci, co, s, st, _tag="block_in_bwd", _bytes=Mi * ci * 8 + Mo * co * 4 + Mi * 20)
+            dO = None
+        else:
+            dXin = _empty((Mi, ci), torch.float32, dev)
+            call("dwn_block_in_bwd", dXpw, dO, b.X, b.coef_sc, bcoef_sc, colbias, dXin, B, T, b.Hi, b.Wi, ci, co, s, st,
+                 _tag="block_in_bwd", _bytes=Mi * ci * 12 + Mo * co * 4)
+            dO = dXin
         if dp is not None:
             dp.reduce(grads, list(blk.parameters()))
 
@@ -229,11 +246,15 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
     stem_conv, stem_bn = mod.core.stem[0], mod.core.stem[1].bn
     cin = stem_conv.weight.shape[1]
     C0 = stem_conv.weight.shape[0]
-    part = _empty((_P, cin + 1, C0), torch.float32, dev)
     dw = torch.empty_like(stem_conv.weight)
     dgam, dbet = torch.empty_like(stem_bn.weight), torch.empty_like(stem_bn.bias)
-    call("dwn_stem_bwd", dO, sv.x, part, _P, sv.stem.mom, stem_conv.weight, sv.stem.coef, dw, dgam, dbet, B, cin,
-         sv.T * sv.H * sv.W, C0, st)
+    if dO is None:
+        call("dwn_stem_bwd_finalize", stem_part, _P, sv.stem.mom, stem_conv.weight, sv.stem.coef, dw, dgam, dbet, B, cin,
+             sv.T * sv.H * sv.W, C0, st)
+    else:
+        part = _empty((_P, cin + 1, C0), torch.float32, dev)
+        call("dwn_stem_bwd", dO, sv.x, part, _P, sv.stem.mom, stem_conv.weight, sv.stem.coef, dw, dgam, dbet, B, cin,
+             sv.T * sv.H * sv.W, C0, st)
     grads[stem_conv.weight], grads[stem_bn.weight], grads[stem_bn.bias] = dw, dgam, dbet
     if dp is not None:
         dp.reduce(grads, [stem_conv.weight, stem_bn.weight, stem_bn.bias])
