@@ -61,6 +61,43 @@ class MouseModel(_Base):
                 call("dwn_distill_fill", t, teacher[m].float().contiguous(), mask, nm, m, B, t.numel() // B, st)
             call("dwn_distill_weights", mice_weights, mask, dweight, B * nm, st)
 
+    def _to_device_overlapped(self, chunk_batch):
+        """deep_to(batch, device, non_blocking=True) (argus_models.py:49) with the target / weight copies (80 % of the
+        host->device bytes, not needed before the loss) issued on a side stream so they overlap the forward pass.
+        Returns (input, target, ready) where ready() makes the compute stream wait for the side-stream copies."""
+        x, target = chunk_batch
+        dev = self.device
+        if dev.type != "cuda" or not torch.is_tensor(x):
+            inp, tgt = deep_to(chunk_batch, dev, non_blocking=True)
+            return inp, tgt, (lambda: None)
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        inp = x.to(dev, non_blocking=True)
+        side = self._copy_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            tgt = deep_to(target, dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(side)
+
+        def _rec(o):
+            if torch.is_tensor(o):
+                o.record_stream(main)
+            elif isinstance(o, (list, tuple)):
+                for v in o:
+                    _rec(v)
+
+        _rec(tgt)
+        state = {"done": False}
+
+        def ready():
+            if not state["done"]:
+                main.wait_event(ev)
+                state["done"] = True
+
+        return inp, tgt, ready
+
     # argus_models.py:43-71
     def train_step(self, batch, state: State) -> dict:
         self.train()
@@ -71,10 +108,13 @@ class MouseModel(_Base):
             distill = self.distill_model is not None and self.distill_ratio
             if isinstance(self.loss, MicePoissonLoss) and not host_w.is_cuda:
                 self.loss.set_live_hint([True] * host_w.shape[1] if distill else (host_w != 0).any(0).tolist())
-            input, target = deep_to(chunk_batch, self.device, non_blocking=True)
+            input, target, ready = self._to_device_overlapped(chunk_batch)
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+                if self.distill_model is not None and self.distill_ratio:
+                    ready()
                 self.add_distill_predictions(input, target)
                 prediction = self.nn_module(input)
+                ready()  # targets / weights are only needed from here on
                 loss = self.loss(prediction, target)
                 loss = loss / self.iter_size
             self.grad_scaler.scale(loss).backward()

@@ -85,20 +85,11 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
             grads[conv.weight] = dW
             grads[conv.bias] = db
         _join(side, dev)
-        if dp is not None:
-            for (r, g, conv, *_rest) in jobs:
-                dp.reduce(grads, [conv.weight, conv.bias])
         call("dwn_readout_dx_combine", dxm, masks, len(live), dX, Mbt, K, T, st)
     else:
         dX.zero_()
     if dp is not None:
-        # mice without a local sample still take part in the exchange with a zero bucket
-        for r, g in zip(sv.readouts, grad_outs):
-            if g is None:
-                conv = mod.readouts[r.m].layer[1]
-                grads[conv.weight] = torch.zeros_like(conv.weight)
-                grads[conv.bias] = torch.zeros_like(conv.bias)
-                dp.reduce(grads, [conv.weight, conv.bias])
+        dp.reduce_readouts(grads)
 
     # ---------------- cortex ---------------------------------------------------------------------
     dOut = dX

@@ -77,6 +77,17 @@ class DataParallelGrads:
                 grads[k] = flat[off:off + n].view(grads[k].shape)
                 off += n
 
+    def reduce_readouts(self, grads: Dict[torch.Tensor, torch.Tensor]) -> None:
+        """Exchange the readout gradients.  Every rank must issue the SAME sequence of collectives, so the
+        readouts go in mouse order on all ranks; a mouse without a local sample contributes a zero bucket
+        (its has-grad flag was MAX-reduced in ``begin``)."""
+        for r in self.mod.readouts:
+            ps = list(r.parameters())
+            for p in ps:
+                if grads.get(p) is None:
+                    grads[p] = torch.zeros_like(p)
+            self.reduce(grads, ps)
+
     def _allreduce_mean(self, t):
         if self._avg:
             return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True)

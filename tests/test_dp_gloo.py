@@ -64,3 +64,51 @@ def test_bucketed_exchange_world2():
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res)
     assert torch.equal(res[0][2], res[1][2])  # attach() broadcast rank 0's weights
+
+
+def _worker_readouts(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sensorium_b200 import DwiseNeuro
+    from sensorium_b200.parallel import DataParallelGrads
+    net = DwiseNeuro(readout_outputs=(5, 4, 3), core_features=(8,), spatial_strides=(1,), expansion_ratio=2,
+                     se_reduce_ratio=4, cortex_features=(8,), groups=2)
+    dp = DataParallelGrads.attach(net)
+    # the set of mice with a local sample differs per rank (the usual case at N=8 with 10 mice in a batch of 32):
+    # rank 0 sees mice {0, 2}, rank 1 sees {1, 2}; the readout shapes differ, so any rank-dependent collective order
+    # would pair tensors of different sizes
+    live = [rank == 0, rank == 1, True]
+    g = torch.Generator().manual_seed(7 + rank)
+    grads, local = {}, {}
+    for m in reversed(range(3)):  # insertion order must not matter either
+        for p in net.readouts[m].parameters():
+            local[p] = torch.randn(p.shape, generator=g) if live[m] else torch.zeros_like(p)
+            if live[m]:
+                grads[p] = local[p].clone()
+    dp.begin(live, torch.device("cpu"))
+    dp.reduce_readouts(grads)
+    dp.finish(torch.device("cpu"))
+    ok = True
+    for p, v in local.items():
+        bucket = [torch.zeros_like(v) for _ in range(world)]
+        dist.all_gather(bucket, v)
+        ok &= torch.allclose(grads[p], sum(bucket) / world, atol=1e-6)
+    params = list(net.parameters())
+    idx = {id(p): i for i, p in enumerate(params)}
+    act = dp.active.tolist()
+    ok &= all(act[idx[id(p)]] == 1 for m in range(3) for p in net.readouts[m].parameters())
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_readout_exchange_with_rank_dependent_mice():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_readouts, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res)
