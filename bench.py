@@ -130,6 +130,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--profile-out", default="")
+    ap.add_argument("--cuda-profiler-step", action="store_true",
+                    help="after the timed region run ONE extra train step between cudaProfilerStart/Stop "
+                         "(for `ncu --profile-from-start off`: the launch list of exactly one step)")
     ap.add_argument("--seed-base", type=int, default=1000, help="rank r draws its synthetic batch with seed base+r")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -209,6 +212,11 @@ def main():
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    if args.cuda_profiler_step:
+        torch.cuda.profiler.start()
+        device_step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     # per-kernel CUDA-event accounting: the same step, right after the timed region, with one event pair around
     # every launch (kept out of the timed region so that the ~1.5k event records do not perturb `value`)
     prof_steps = max(2, min(4, args.steps))
@@ -266,6 +274,14 @@ def main():
                 "share_of_step": top_entry[0] / max(total_kernel_ms, 1e-9),
                 "launches_per_step": top[2], "ms_per_step": top[1],
                 "how": f"CUDA events around every launch of this kernel over {prof_steps} steps run right after the timed region"}
+    roofline["algorithmic_bytes_per_launch"] = top_entry[2] / max(top_entry[1], 1)
+    try:  # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/)
+        tr = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text())
+        if tr.get("kernel") == top[0]:
+            roofline["traffic"] = tr["traffic_bytes_per_launch"]
+            roofline["traffic_source"] = tr["source"]
+    except Exception:  # noqa: BLE001
+        pass
     if args.profile_out:
         with open(args.profile_out, "w") as f:
             f.write("kernel,ms_per_step,launches_per_step,GB/s,TFLOP/s,share\n")
