@@ -117,11 +117,11 @@ int dwn_pool_bwd(const float* dP, float* dX, long BT, int HW, int C, void* strea
 int dwn_se_bwd(const float* Pp, const float* wt, const float* gate, const float* hpre, const float* mean,
                const float* w1, const float* w2, float* dpre2, float* dhpre, float* dmean, float* dwpwl, float* dw2,
                float* db2, float* dw1, float* db1, int B, int C, int Co, int RD, void* stream); /* dwiseneuro.py:25-43 */
-int dwn_tdw_bwd_reduce(void* da, const void* tm, const float* coef3, const float* dmean, int Nsp, float* partial, int J,
-                       int B, int C, int dtype, void* stream);    /* dwiseneuro.py:105-111; partial: B*J rows */
+int dwn_tdw_bwd_reduce(const void* da, const void* tm, const float* coef3, const float* dmean, int Nsp, float* partial,
+                       int J, int B, int C, int dtype, void* stream); /* dwiseneuro.py:105-111; statistics only; partial: B*J rows */
 int dwn_tdw_bwd(void* dth, const void* tm, const void* s_raw, const float* coef3, const float* bcoef3,
-                const float* coef2, const float* wgt, float* partial, int P, int B, int Tn, int HW, int C, int dtype,
-                void* stream);
+                const float* coef2, const float* wgt, const float* dmean, float* partial, int P, int B, int Tn, int HW,
+                int C, int dtype, void* stream); /* dth holds da on entry (the SE/act backward is recomputed), d s_hat on exit */
 int dwn_sdw_bwd(const void* dsh, const void* s_raw, const void* e_raw, const float* coef2, const float* bcoef2,
                 const float* coef1, const float* wgt, void* dE, float* partial, int P, int NP, int H, int W, int C,
                 int stride, int dtype, void* stream);                                      /* dwiseneuro.py:96-102 */

@@ -55,7 +55,7 @@ SIGNATURES = {
     "dwn_pool_bwd": "pp" + "lii" + "p",
     "dwn_se_bwd": "ppppppp" + "pppppppp" + "iiii" + "p",
     "dwn_tdw_bwd_reduce": "pppp" + "i" + "p" + "iiii" + "p",
-    "dwn_tdw_bwd": "pppppppp" + "iiiiii" + "p",
+    "dwn_tdw_bwd": "ppppppppp" + "iiiiii" + "p",
     "dwn_sdw_bwd": "ppppppppp" + "iiiiiii" + "p",
     "dwn_bn_bwd_apply": "pppp" + "lii" + "p",
     "dwn_reduce_rows": "pilpp",

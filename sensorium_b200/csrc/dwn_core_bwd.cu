@@ -6,6 +6,7 @@
 #include "dwn_common.cuh"
 #include "dwn_reduce.cuh"
 #include "dwn_sdw_v3.cuh"
+#include "dwn_bulk.cuh"
 #include <type_traits>
 
 __global__ void stem_bwd_finalize_kernel(const float* __restrict__ partial, int P, int cin, const double* __restrict__ mom,
@@ -333,33 +334,44 @@ __global__ void __launch_bounds__(256) se_bwd_a1_kernel(const float* __restrict_
   }
 }
 
-// a2: one CTA per sample: dh -> dhpre -> dmean
-__global__ void se_bwd_a2_kernel(const float* __restrict__ dpre2, const float* __restrict__ hpre,
-                                 const float* __restrict__ w1, const float* __restrict__ w2,
-                                 float* __restrict__ dhpre, float* __restrict__ dmean, int C, int RD) {
-  extern __shared__ float sm[];  // dpre2[C], dhp[RD]
+// a2: one CTA (1024 threads) per sample: dh -> dhpre -> dmean.  All weight reads are coalesced (lanes run over the
+// contiguous index of w2 [C][RD] / w1 [RD][C]) and unrolled so that several loads are in flight per thread.
+__global__ void __launch_bounds__(1024) se_bwd_a2_kernel(const float* __restrict__ dpre2, const float* __restrict__ hpre,
+                                                        const float* __restrict__ w1, const float* __restrict__ w2,
+                                                        float* __restrict__ dhpre, float* __restrict__ dmean, int C,
+                                                        int RD) {
+  extern __shared__ float sm[];  // dpre2[C], dhp[RD], part[nw][RD]
   float* s_dp2 = sm;
   float* s_dhp = sm + C;
+  float* s_part = s_dhp + RD;
   const int b = blockIdx.x, tid = threadIdx.x;
   for (int k = tid; k < C; k += blockDim.x) s_dp2[k] = dpre2[(long)b * C + k];
   __syncthreads();
   const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-  for (int r = wid; r < RD; r += nw) {
+  for (int r0 = 0; r0 < RD; r0 += 32) {
+    const int r = r0 + lane;
     float s = 0.f;
-    for (int k = lane; k < C; k += 32) s = fmaf(s_dp2[k], w2[(long)k * RD + r], s);
-    s = warp_sum(s);
-    if (lane == 0) {
-      const float u = hpre[(long)b * RD + r];
-      const float sg = 1.0f / (1.0f + expf(-u));
-      const float d = s * sg * (1.0f + u * (1.0f - sg));
-      s_dhp[r] = d;
-      dhpre[(long)b * RD + r] = d;
+    if (r < RD) {
+#pragma unroll 8
+      for (int k = wid; k < C; k += nw) s = fmaf(s_dp2[k], __ldg(&w2[(long)k * RD + r]), s);
+      s_part[wid * RD + r] = s;
     }
+  }
+  __syncthreads();
+  for (int r = tid; r < RD; r += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += s_part[w * RD + r];
+    const float u = hpre[(long)b * RD + r];
+    const float sg = 1.0f / (1.0f + expf(-u));
+    const float d = s * sg * (1.0f + u * (1.0f - sg));
+    s_dhp[r] = d;
+    dhpre[(long)b * RD + r] = d;
   }
   __syncthreads();
   for (int k = tid; k < C; k += blockDim.x) {
     float s = 0.f;
-    for (int r = 0; r < RD; ++r) s = fmaf(s_dhp[r], w1[(long)r * C + k], s);
+#pragma unroll 8
+    for (int r = 0; r < RD; ++r) s = fmaf(s_dhp[r], __ldg(&w1[(long)r * C + k]), s);
     dmean[(long)b * C + k] = s;
   }
 }
@@ -417,7 +429,8 @@ extern "C" int dwn_se_bwd(const float* Pp, const float* wt, const float* gate, c
   dim3 g1((C + 7) / 8, B);
   se_bwd_a1_kernel<<<g1, 256, 0, st>>>(Pp, wt, gate, dpre2, C, Co);
   DWN_LAUNCH_CHECK();
-  se_bwd_a2_kernel<<<B, 256, (C + RD) * sizeof(float), st>>>(dpre2, hpre, w1, w2, dhpre, dmean, C, RD);
+  se_bwd_a2_kernel<<<B, 1024, ((size_t)C + RD + 32 * (size_t)RD) * sizeof(float), st>>>(dpre2, hpre, w1, w2, dhpre, dmean,
+                                                                                       C, RD);
   DWN_LAUNCH_CHECK();
   long total = (long)C * Co + (long)C * RD + C + (long)RD * C + RD;
   int gx = (int)((total + 255) / 256);
@@ -428,12 +441,13 @@ extern "C" int dwn_se_bwd(const float* Pp, const float* wt, const float* gate, c
 }
 
 // =================================================================================================
-// temporal dw backward, pass 1: dthat = (da + dmean[b]/Nsp) * SiLU'(BN3(Tm_raw)), written in place over da,
-// partial[P][2][C] = { sum dthat, sum dthat*xhat3 }
+// temporal dw backward, pass 1 (statistics only): dthat = (da + dmean[b]/Nsp) * SiLU'(BN3(Tm_raw)),
+// partial[P][2][C] = { sum dthat, sum dthat*xhat3 }.  dthat is NOT stored: pass 2 reads da and Tm_raw anyway and
+// recomputes it in registers, which saves one write + keeps the value in fp32.
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256, 4)
-tdw_bwd_reduce_kernel(T* __restrict__ da, const T* __restrict__ tm, const float* __restrict__ coef3,
+tdw_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ tm, const float* __restrict__ coef3,
                       const float* __restrict__ dmean, float inv_nsp, float* __restrict__ partial, int Nsp, int C,
                       int cqc) {
   // grid (J, channel chunks, B): the per-sample SE term dmean[b][c]/Nsp is a thread constant.
@@ -452,7 +466,7 @@ tdw_bwd_reduce_kernel(T* __restrict__ da, const T* __restrict__ tm, const float*
     dm[j] = dmean[(long)b * C + c + j] * inv_nsp;
   }
   float st[2][4] = {};
-  T* gp = da + (long)b * Nsp * C + c;
+  const T* gp = da + (long)b * Nsp * C + c;
   const T* xp = tm + (long)b * Nsp * C + c;
 #pragma unroll 4
   for (int r = blockIdx.x * ln + lane; r < Nsp; r += gridDim.x * ln) {
@@ -464,36 +478,130 @@ tdw_bwd_reduce_kernel(T* __restrict__ da, const T* __restrict__ tm, const float*
       float sg;
       BnSilu<T>::act_grad(x[j], q0[j], q1[j], sg);
       const float d = (g[j] + dm[j]) * sg;
-      g[j] = d;
       st[0][j] += d;
       st[1][j] = fmaf(d, (x[j] - mu[j]) * rs[j], st[1][j]);
     }
-    stq(gp + (long)r * C, g);
   }
   block_reduce_channels<2, 4>(st, smem, cqc, ln, partial + ((long)b * gridDim.x + blockIdx.x) * 2 * C, C,
                               blockIdx.y * cqc * 4);
 }
 
+// Bulk-staged variant (bf16/fp32, C/8 <= 256): CTA (j, b) streams contiguous chunks of R rows x C channels of da and
+// Tm_raw through a 3-stage cp.async.bulk ring and reduces them from shared memory with 16-byte LDS.  The statistics
+// are taken on the raw x (sum d, sum d*x); sum d*xhat = rstd*(sum d*x - mean*sum d) is formed once per CTA.
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+tdw_bwd_reduce_bulk_kernel(const T* __restrict__ da, const T* __restrict__ tm, const float* __restrict__ coef3,
+                           const float* __restrict__ dmean, float inv_nsp, float* __restrict__ partial, int Nsp, int C,
+                           int cvc, int R) {
+  constexpr int NS = 3;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int tid = threadIdx.x;
+  const size_t chunk_elems = (size_t)R * C;
+  T* buf = reinterpret_cast<T*>(smraw);  // [NS][2][R*C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + (size_t)NS * 2 * chunk_elems * sizeof(T));
+  const int cv = tid % cvc, lane = tid / cvc, ln = blockDim.x / cvc;
+  const int c = cv * 8;
+  const int b = blockIdx.y, j = blockIdx.x, J = gridDim.x;
+  const int nch = (Nsp + R - 1) / R;
+  const T* gbase = da + (long)b * Nsp * C;
+  const T* xbase = tm + (long)b * Nsp * C;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) bk_mbar_init(&bars[s], 1);
+    bk_mbar_init_fence();
+  }
+  __syncthreads();
+  auto issue = [&](int ch, int stage) {  // one thread
+    const int rows = min(R, Nsp - ch * R);
+    const uint32_t bytes = (uint32_t)((size_t)rows * C * sizeof(T));
+    bk_mbar_expect_tx(&bars[stage], 2 * bytes);
+    bk_bulk_g2s(buf + (size_t)(stage * 2) * chunk_elems, gbase + (long)ch * R * C, bytes, &bars[stage]);
+    bk_bulk_g2s(buf + (size_t)(stage * 2 + 1) * chunk_elems, xbase + (long)ch * R * C, bytes, &bars[stage]);
+  };
+  if (tid == 0)
+    for (int s = 0; s < NS; ++s)
+      if (j + s * J < nch) issue(j + s * J, s);
+  float q0[8], q1[8], dm[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    BnSilu<T>::prep(coef3[c + e], coef3[C + c + e], q0[e], q1[e]);
+    dm[e] = dmean[(long)b * C + c + e] * inv_nsp;
+  }
+  float st[2][8] = {};
+  int it = 0;
+  for (int ch = j; ch < nch; ch += J, ++it) {
+    const int stage = it % NS;
+    bk_mbar_wait(&bars[stage], (uint32_t)((it / NS) & 1));
+    const int rows = min(R, Nsp - ch * R);
+    const T* gs = buf + (size_t)(stage * 2) * chunk_elems + c;
+    const T* xs = gs + chunk_elems;
+#pragma unroll 2
+    for (int r = lane; r < rows; r += ln) {
+      float g[8], x[8];
+      ldv(gs + (size_t)r * C, g);
+      ldv(xs + (size_t)r * C, x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float sg;
+        BnSilu<T>::act_grad(x[e], q0[e], q1[e], sg);
+        const float d = (g[e] + dm[e]) * sg;
+        st[0][e] += d;
+        st[1][e] = fmaf(d, x[e], st[1][e]);
+      }
+    }
+    __syncthreads();  // everybody is done with this stage
+    if (tid == 0 && ch + NS * J < nch) issue(ch + NS * J, stage);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    st[1][e] = coef3[3 * C + c + e] * (st[1][e] - coef3[2 * C + c + e] * st[0][e]);
+  block_reduce_channels<2, 8>(st, reinterpret_cast<float*>(smraw), cvc, ln, partial + ((long)b * J + j) * 2 * C, C, 0);
+}
+
+template <typename T>
+static bool tdw_bwd_reduce_bulk_launch(const void* da, const void* tm, const float* coef3, const float* dmean, int Nsp,
+                                       float* partial, int J, int B, int C, cudaStream_t st) {
+  constexpr int V = 16 / (int)sizeof(T);  // elements per 16-byte vector: the kernel reads 8 channels per thread
+  if (V != 8 && V != 4) return false;
+  if (C % 8 != 0 || C / 8 > 256 || ((size_t)C * sizeof(T)) % 16 != 0) return false;
+  const int cvc = C / 8, ln = 256 / cvc;
+  int R = (int)(14336 / ((size_t)C * sizeof(T)));
+  if (R < 1) R = 1;
+  if (R > Nsp) R = Nsp;
+  size_t sm = (size_t)3 * 2 * R * C * sizeof(T) + 64;
+  const size_t sm_red = (size_t)cvc * ln * 16 * sizeof(float);
+  if (sm_red > sm) sm = sm_red;
+  auto k = tdw_bwd_reduce_bulk_kernel<T>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k<<<dim3(J, B), cvc * ln, sm, st>>>((const T*)da, (const T*)tm, coef3, dmean, 1.0f / Nsp, partial, Nsp, C, cvc, R);
+  return true;
+}
+
 // partial must hold B*J rows of [2][C]
-extern "C" int dwn_tdw_bwd_reduce(void* da, const void* tm, const float* coef3, const float* dmean, int Nsp,
+extern "C" int dwn_tdw_bwd_reduce(const void* da, const void* tm, const float* coef3, const float* dmean, int Nsp,
                                   float* partial, int J, int B, int C, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DWN_REQUIRE(C % 4 == 0, "dwn_tdw_bwd_reduce: C %% 4 != 0");
+  if (dtype == DWN_DT_BF16 && tdw_bwd_reduce_bulk_launch<bf16>(da, tm, coef3, dmean, Nsp, partial, J, B, C, st)) {
+    DWN_LAUNCH_CHECK();
+    return 0;
+  }
   int cqc = dwn_largest_divisor_le(C / 4, 128), ln = 256 / cqc;
   if (ln < 1) ln = 1;
   dim3 grid(J, (C / 4) / cqc, B), block(cqc * ln);
   if (dtype == DWN_DT_F32)
-    tdw_bwd_reduce_kernel<float><<<grid, block, block.x * 8 * sizeof(float), st>>>((float*)da, (const float*)tm, coef3,
+    tdw_bwd_reduce_kernel<float><<<grid, block, block.x * 8 * sizeof(float), st>>>((const float*)da, (const float*)tm, coef3,
                                                                                   dmean, 1.0f / Nsp, partial, Nsp, C, cqc);
   else
-    tdw_bwd_reduce_kernel<bf16><<<grid, block, block.x * 8 * sizeof(float), st>>>((bf16*)da, (const bf16*)tm, coef3,
+    tdw_bwd_reduce_kernel<bf16><<<grid, block, block.x * 8 * sizeof(float), st>>>((const bf16*)da, (const bf16*)tm, coef3,
                                                                                  dmean, 1.0f / Nsp, partial, Nsp, C, cqc);
   DWN_LAUNCH_CHECK();
   return 0;
 }
 
 // =================================================================================================
-// temporal dw backward, pass 2 (thread = channel quad x position, whole T column in registers, packed fp32x2):
+// temporal dw backward, pass 2 (thread = channel pair x position, whole T column in registers, packed fp32x2):
+//   dthat = (da + dmean[b]/Nsp) * SiLU'(BN3(Tm_raw))           (recomputed, see pass 1)
 //   dTm = gamma3*rstd3*(dthat - c1 - xhat3*c2) = a3*dthat - d3*x - b3
 //   dS_act[u] = sum_k w[k]*dTm[u-k+2] ;  dw[k] += s_act[u]*dTm[u-k+2]
 //   dshat[u] = dS_act[u]*SiLU'(BN2(S_raw[u]))  -> written in place over dthat
@@ -503,7 +611,8 @@ template <typename T, int TT>
 __global__ void __launch_bounds__(128, 4)
 tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restrict__ s_raw,
                const float* __restrict__ coef3, const float* __restrict__ bcoef3, const float* __restrict__ coef2,
-               const float* __restrict__ wgt, float* __restrict__ partial, int B, int Tn, int HW, int C, int cpc) {
+               const float* __restrict__ wgt, const float* __restrict__ dmean, float inv_nsp,
+               float* __restrict__ partial, int B, int Tn, int HW, int C, int cpc) {
   // thread = one channel PAIR x position (2 channels keep the whole-T register column small enough for
   // 4 CTAs / SM; a warp still covers 64 consecutive channels = 128 bytes per row)
   constexpr int TA = TT > 0 ? TT : 32;
@@ -513,7 +622,7 @@ tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restric
   const int c = (blockIdx.y * cpc + cp) * 2;
   const int tn = TT > 0 ? TT : Tn;
   f32x2 a3, b3, d3, w2[5];
-  float p0[2], p1[2], mu2[2], rs2[2];
+  float p0[2], p1[2], mu2[2], rs2[2], q0[2], q1[2];
   {
     float av[2], bv[2], dv[2];
 #pragma unroll
@@ -525,6 +634,7 @@ tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restric
       dv[e] = -sc * rs * k2;
       bv[e] = -sc * (k1 - mu * rs * k2);
       BnSilu<T>::prep(coef2[cc], coef2[C + cc], p0[e], p1[e]);
+      BnSilu<T>::prep(sc, coef3[C + cc], q0[e], q1[e]);
       mu2[e] = coef2[2 * C + cc];
       rs2[e] = coef2[3 * C + cc];
     }
@@ -546,6 +656,7 @@ tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restric
     T* gp = dth + base;
     const T* xp = tm + base;
     const T* sp = s_raw + base;
+    const float dm0 = dmean[b * C + c] * inv_nsp, dm1 = dmean[b * C + c + 1] * inv_nsp;
     f32x2 dT[TA], sv[TA];
 #pragma unroll
     for (int t = 0; t < TA; ++t)
@@ -554,8 +665,14 @@ tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restric
     for (int t = 0; t < TA; ++t) {
       if (t < tn) {
         const f32x2 g = ldp2(gp + t * tstride), x = ldp2(xp + t * tstride);
-        f32x2 v = b3;  // dTm = a3*g + d3*x + b3   (d3, b3 carry the minus signs)
-        ffma2(v, a3, g);
+        float g0, g1, x0, x1, s0, s1;
+        upk2(g, g0, g1);
+        upk2(x, x0, x1);
+        BnSilu<T>::act_grad(x0, q0[0], q1[0], s0);
+        BnSilu<T>::act_grad(x1, q0[1], q1[1], s1);
+        const f32x2 dth2 = pk2((g0 + dm0) * s0, (g1 + dm1) * s1);
+        f32x2 v = b3;  // dTm = a3*dthat + d3*x + b3   (d3, b3 carry the minus signs)
+        ffma2(v, a3, dth2);
         ffma2(v, d3, x);
         dT[t] = v;
       }
@@ -590,12 +707,184 @@ tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restric
   block_reduce_channels<7, 2>(st, smem, cpc, ln, partial + (long)blockIdx.x * 7 * C, C, blockIdx.y * cpc * 2);
 }
 
+// Bulk-staged variant of pass 2 (bf16): one work item = one (b, hw) position x CCH channels x all T.  The 3*T row
+// segments of an item (da, Tm_raw, S_raw; CCH*2 bytes each, contiguous in the channels-last layout) are fetched by
+// cp.async.bulk into a 2-stage shared-memory ring, so the bytes in flight do not depend on registers or occupancy;
+// thread = channel pair, whole-T column in registers, same arithmetic as tdw_bwd_kernel.
+template <int TT>
+__global__ void __launch_bounds__(256, 2)
+tdw_bwd_bulk_kernel(bf16* __restrict__ dth, const bf16* __restrict__ tm, const bf16* __restrict__ s_raw,
+                    const float* __restrict__ coef3, const float* __restrict__ bcoef3, const float* __restrict__ coef2,
+                    const float* __restrict__ wgt, const float* __restrict__ dmean, float inv_nsp,
+                    float* __restrict__ partial, int B, int Tn, int HW, int C, int CCH) {
+  constexpr int TA = TT > 0 ? TT : 32;
+  constexpr int NS = 2;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int tn = TT > 0 ? TT : Tn;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = blockIdx.y * CCH, c = c0 + tid * 2;
+  bf16* buf = reinterpret_cast<bf16*>(smraw);  // [NS][3][tn][CCH]
+  const size_t stage_elems = (size_t)3 * tn * CCH;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + NS * stage_elems * sizeof(bf16));
+  const long npos = (long)B * HW;
+  const long tstride = (long)HW * C;
+  const long bstride = (long)Tn * tstride;
+  const int G = gridDim.x;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) bk_mbar_init(&bars[s], 1);
+    bk_mbar_init_fence();
+  }
+  __syncthreads();
+  const uint32_t seg_bytes = (uint32_t)(CCH * sizeof(bf16));
+  auto issue = [&](long pos, int stage) {  // all lanes of warp 0
+    const long b = pos / HW, hw = pos - b * HW;
+    const long base = b * bstride + hw * C + c0;
+    if (lane == 0) bk_mbar_expect_tx(&bars[stage], 3u * (uint32_t)tn * seg_bytes);
+    __syncwarp();
+    bf16* dst = buf + (size_t)stage * stage_elems;
+    for (int i = lane; i < 3 * tn; i += 32) {
+      const int a = i / tn, t = i - a * tn;
+      const bf16* src = (a == 0 ? (const bf16*)dth : (a == 1 ? tm : s_raw)) + base + (long)t * tstride;
+      bk_bulk_g2s(dst + (size_t)i * CCH, src, seg_bytes, &bars[stage]);
+    }
+  };
+  long pos = blockIdx.x;
+  if (warp == 0) {
+    if (pos < npos) issue(pos, 0);
+    if (pos + G < npos) issue(pos + G, 1);
+  }
+  f32x2 a3, b3, d3, w2[5], p0_2, p1_2, q0_3, q1_3, mu2, rs2;
+  {
+    float av[2], bv[2], dv[2], p0[2], p1[2], q0[2], q1[2], m2[2], r2[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int cc = c + e;
+      const float sc = coef3[cc], mu = coef3[2 * C + cc], rs = coef3[3 * C + cc];
+      const float k1 = bcoef3[cc], k2 = bcoef3[C + cc];
+      av[e] = sc;
+      dv[e] = -sc * rs * k2;
+      bv[e] = -sc * (k1 - mu * rs * k2);
+      BnSilu<bf16>::prep(coef2[cc], coef2[C + cc], p0[e], p1[e]);
+      BnSilu<bf16>::prep(sc, coef3[C + cc], q0[e], q1[e]);
+      m2[e] = coef2[2 * C + cc];
+      r2[e] = coef2[3 * C + cc];
+    }
+    a3 = pk2(av[0], av[1]); b3 = pk2(bv[0], bv[1]); d3 = pk2(dv[0], dv[1]);
+    p0_2 = pk2(p0[0], p0[1]); p1_2 = pk2(p1[0], p1[1]);
+    q0_3 = pk2(q0[0], q0[1]); q1_3 = pk2(q1[0], q1[1]);
+    mu2 = pk2(-m2[0] * r2[0], -m2[1] * r2[1]);  // xhat2 = s*rs2 + (-mu2*rs2)
+    rs2 = pk2(r2[0], r2[1]);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w2[k] = pk2(wgt[c * 5 + k], wgt[(c + 1) * 5 + k]);
+  }
+  f32x2 st2[7];
+#pragma unroll
+  for (int q = 0; q < 7; ++q) st2[q] = 0ull;
+  // the per-sample SE term of the NEXT item is fetched one item ahead (no dependent global load per item)
+  f32x2 dm_next = 0ull;
+  if (pos < npos) {
+    const long b = pos / HW;
+    dm_next = pk2(dmean[b * C + c] * inv_nsp, dmean[b * C + c + 1] * inv_nsp);
+  }
+  int it = 0;
+  for (; pos < npos; pos += G, ++it) {
+    const int stage = it & 1;
+    const f32x2 dm = dm_next;
+    if (pos + G < npos) {
+      const long bn = (pos + G) / HW;
+      dm_next = pk2(dmean[bn * C + c] * inv_nsp, dmean[bn * C + c + 1] * inv_nsp);
+    }
+    const long b = pos / HW, hw = pos - b * HW;
+    bf16* gp = dth + b * bstride + hw * C + c;
+    bk_mbar_wait(&bars[stage], (uint32_t)((it >> 1) & 1));
+    const bf16* sg_ = buf + (size_t)stage * stage_elems + tid * 2;  // da rows
+    const bf16* sx_ = sg_ + (size_t)tn * CCH;                        // Tm_raw rows
+    const bf16* ss_ = sx_ + (size_t)tn * CCH;                        // S_raw rows
+    f32x2 dT[TA];
+#pragma unroll
+    for (int t = 0; t < TA; ++t) {
+      if (t < tn) {
+        const f32x2 g = ldp2(sg_ + (size_t)t * CCH), x = ldp2(sx_ + (size_t)t * CCH);
+        f32x2 s3;
+        bnsilu_grad2_bf16(x, q0_3, q1_3, s3);
+        f32x2 gd = g;
+        fadd2(gd, dm);
+        const f32x2 dth2 = fmul2(gd, s3);
+        f32x2 v = b3;  // dTm = a3*dthat + d3*x + b3   (d3, b3 carry the minus signs)
+        ffma2(v, a3, dth2);
+        ffma2(v, d3, x);
+        dT[t] = v;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < TA; ++u) {
+      if (u < tn) {
+        const f32x2 s = ldp2(ss_ + (size_t)u * CCH);
+        f32x2 sgr;
+        const f32x2 sa2 = bnsilu_grad2_bf16(s, p0_2, p1_2, sgr);
+        f32x2 acc = 0ull;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int t = u - k + 2;
+          if (t >= 0 && t < tn) {
+            ffma2(acc, w2[k], dT[t]);
+            ffma2(st2[2 + k], sa2, dT[t]);
+          }
+        }
+        const f32x2 o = fmul2(acc, sgr);
+        stp2(gp + (long)u * tstride, o);
+        fadd2(st2[0], o);
+        f32x2 xh = mu2;
+        ffma2(xh, s, rs2);
+        ffma2(st2[1], o, xh);
+      }
+    }
+    __syncthreads();  // everybody is done with this stage
+    if (warp == 0 && pos + 2L * G < npos) issue(pos + 2L * G, stage);
+  }
+  float st[7][2];
+#pragma unroll
+  for (int q = 0; q < 7; ++q) upk2(st2[q], st[q][0], st[q][1]);
+  block_reduce_channels<7, 2>(st, reinterpret_cast<float*>(smraw), CCH / 2, 1, partial + (long)blockIdx.x * 7 * C, C, c0);
+}
+
+static bool tdw_bwd_bulk_launch(void* dth, const void* tm, const void* s_raw, const float* coef3, const float* bcoef3,
+                                const float* coef2, const float* wgt, const float* dmean, float* partial, int P, int B,
+                                int Tn, int HW, int C, cudaStream_t st) {
+  if (C % 16 != 0) return false;
+  int CCH = 0;  // channels per CTA: a divisor of C, multiple of 64 (whole warps of channel pairs), <= 512
+  for (int cand = 512; cand >= 64; cand -= 64)
+    if (C % cand == 0) { CCH = cand; break; }
+  if (CCH == 0) return false;
+  const size_t stage = (size_t)3 * Tn * CCH * sizeof(bf16);
+  size_t sm = 2 * stage + 64;
+  const size_t sm_red = (size_t)(CCH / 2) * 14 * sizeof(float);
+  if (sm_red > sm) sm = sm_red;
+  if (sm > 110 * 1024) return false;
+  dim3 grid(P, C / CCH), block(CCH / 2);
+#define GOB(TTV)                                                                                                   \
+  {                                                                                                                \
+    auto k = tdw_bwd_bulk_kernel<TTV>;                                                                             \
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                                 \
+    k<<<grid, block, sm, st>>>((bf16*)dth, (const bf16*)tm, (const bf16*)s_raw, coef3, bcoef3, coef2, wgt, dmean,  \
+                               1.0f / ((float)Tn * (float)HW), partial, B, Tn, HW, C, CCH);                        \
+  }
+  if (Tn == 16) GOB(16) else if (Tn == 8) GOB(8) else GOB(0)
+#undef GOB
+  return true;
+}
+
 extern "C" int dwn_tdw_bwd(void* dth, const void* tm, const void* s_raw, const float* coef3, const float* bcoef3,
-                           const float* coef2, const float* wgt, float* partial, int P, int B, int Tn, int HW, int C,
-                           int dtype, void* stream) {
+                           const float* coef2, const float* wgt, const float* dmean, float* partial, int P, int B, int Tn,
+                           int HW, int C, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DWN_REQUIRE(Tn <= 32, "dwn_tdw_bwd: T > 32 unsupported");
   DWN_REQUIRE(C % 2 == 0, "dwn_tdw_bwd: C %% 2 != 0");
+  if (dtype == DWN_DT_BF16 &&
+      tdw_bwd_bulk_launch(dth, tm, s_raw, coef3, bcoef3, coef2, wgt, dmean, partial, P, B, Tn, HW, C, st)) {
+    DWN_LAUNCH_CHECK();
+    return 0;
+  }
   int cpc = dwn_largest_divisor_le(C / 2, 128);
   int ln = 128 / cpc;
   if (ln < 1) ln = 1;
@@ -603,7 +892,7 @@ extern "C" int dwn_tdw_bwd(void* dth, const void* tm, const void* s_raw, const f
   size_t sm = (size_t)block.x * 14 * sizeof(float);
 #define GO(TY, TTV)                                                                                              \
   tdw_bwd_kernel<TY, TTV><<<grid, block, sm, st>>>((TY*)dth, (const TY*)tm, (const TY*)s_raw, coef3, bcoef3, coef2, wgt, \
-                                                   partial, B, Tn, HW, C, cpc)
+                                                   dmean, 1.0f / ((float)Tn * (float)HW), partial, B, Tn, HW, C, cpc)
   if (dtype == DWN_DT_F32) {
     if (Tn == 16) GO(float, 16); else if (Tn == 8) GO(float, 8); else GO(float, 0);
   } else {
@@ -837,6 +1126,15 @@ static int sdw_bwd_launch(const void* dsh, const void* s_raw, const void* e_raw,
   return 0;
 }
 
+// stride 1 runs the register-window variant (v5), stride 2 the v3 kernel
+using sdw_bwd_fn = void (*)(const bf16*, const bf16*, const bf16*, const float*, const float*, const float*, const float*,
+                            bf16*, float*, int, int, int, int, int);
+template <int S, int THI, int CC>
+static sdw_bwd_fn sdw_bwd_pick() {
+  if constexpr (S == 1) return sdw_bwd_v5_kernel<THI, CC>;
+  else return sdw_bwd_v3_kernel<S, THI, CC>;
+}
+
 template <int S>
 static int sdw_bwd_v3_launch(const void* dsh, const void* s_raw, const void* e_raw, const float* coef2,
                              const float* bcoef2, const float* coef1, const float* wgt, void* dE, float* partial, int P,
@@ -861,7 +1159,7 @@ static int sdw_bwd_v3_launch(const void* dsh, const void* s_raw, const void* e_r
   dim3 grid(P * nchunks), block(256);
 #define LAUNCH(THI_, CC_)                                                                                          \
   {                                                                                                                \
-    auto k = sdw_bwd_v3_kernel<S, THI_, CC_>;                                                                      \
+    auto k = sdw_bwd_pick<S, THI_, CC_>();                                                                         \
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                                 \
     k<<<grid, block, sm, st>>>((const bf16*)dsh, (const bf16*)s_raw, (const bf16*)e_raw, coef2, bcoef2, coef1, wgt, \
                                (bf16*)dE, partial, NP, H, C, nchunks, nbsh);                                       \

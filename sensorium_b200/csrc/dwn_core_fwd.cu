@@ -2,6 +2,7 @@
 // Reference semantics: /root/reference/src/models/dwiseneuro.py (line numbers cited per kernel).
 #include "dwn_common.cuh"
 #include "dwn_reduce.cuh"
+#include "dwn_bulk.cuh"
 #include "dwn_sdw_v3.cuh"
 
 // =================================================================================================
@@ -634,9 +635,80 @@ __global__ void se_pool_kernel(const T* __restrict__ in, const float* __restrict
                               blockIdx.y * cvc * V);
 }
 
+// Bulk-staged variant (bf16, C/8 <= 256): CTA (j, b) streams contiguous chunks of R rows x C channels of Tm_raw through
+// a 3-stage cp.async.bulk ring (see dwn_bulk.cuh), activates them from shared memory and writes A with 16-byte stores.
+__global__ void __launch_bounds__(256, 3)
+se_pool_bulk_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, bf16* __restrict__ act,
+                    float* __restrict__ partial, int Nsp, int C, int cvc, int R) {
+  constexpr int NS = 3;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int tid = threadIdx.x;
+  const size_t chunk_elems = (size_t)R * C;
+  bf16* buf = reinterpret_cast<bf16*>(smraw);  // [NS][R*C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + (size_t)NS * chunk_elems * sizeof(bf16));
+  const int cv = tid % cvc, lane = tid / cvc, ln = blockDim.x / cvc;
+  const int c = cv * 8;
+  const int b = blockIdx.y, j = blockIdx.x, J = gridDim.x;
+  const int nch = (Nsp + R - 1) / R;
+  const bf16* xbase = in + (long)b * Nsp * C;
+  bf16* obase = act + (long)b * Nsp * C + c;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) bk_mbar_init(&bars[s], 1);
+    bk_mbar_init_fence();
+  }
+  __syncthreads();
+  auto issue = [&](int ch, int stage) {  // one thread
+    const int rows = min(R, Nsp - ch * R);
+    const uint32_t bytes = (uint32_t)((size_t)rows * C * sizeof(bf16));
+    bk_mbar_expect_tx(&bars[stage], bytes);
+    bk_bulk_g2s(buf + (size_t)stage * chunk_elems, xbase + (long)ch * R * C, bytes, &bars[stage]);
+  };
+  if (tid == 0)
+    for (int s = 0; s < NS; ++s)
+      if (j + s * J < nch) issue(j + s * J, s);
+  float q0[8], q1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) BnSilu<bf16>::prep(coef[c + e], coef[C + c + e], q0[e], q1[e]);
+  float st[1][8] = {};
+  int it = 0;
+  for (int ch = j; ch < nch; ch += J, ++it) {
+    const int stage = it % NS;
+    bk_mbar_wait(&bars[stage], (uint32_t)((it / NS) & 1));
+    const int rows = min(R, Nsp - ch * R);
+    const bf16* xs = buf + (size_t)stage * chunk_elems + c;
+    bf16* op = obase + (long)ch * R * C;
+#pragma unroll 2
+    for (int r = lane; r < rows; r += ln) {
+      float v[8];
+      ldv(xs + (size_t)r * C, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = BnSilu<bf16>::act(v[e], q0[e], q1[e]);
+      stv(op + (long)r * C, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) st[0][e] += v[e];
+    }
+    __syncthreads();  // everybody is done with this stage
+    if (tid == 0 && ch + NS * J < nch) issue(ch + NS * J, stage);
+  }
+  block_reduce_channels<1, 8>(st, reinterpret_cast<float*>(smraw), cvc, ln, partial + ((long)b * J + j) * C, C, 0);
+}
+
 extern "C" int dwn_se_pool(const void* in, const float* coef, void* act, float* partial, int J, int B, int Nsp, int C,
                            int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DWN_DT_BF16 && C % 8 == 0 && C / 8 <= 256) {
+    const int cvc = C / 8, ln = 256 / cvc;
+    int R = (int)(14336 / ((size_t)C * sizeof(bf16)));
+    if (R < 1) R = 1;
+    if (R > Nsp) R = Nsp;
+    size_t sm = (size_t)3 * R * C * sizeof(bf16) + 64;
+    const size_t sm_red = (size_t)cvc * ln * 8 * sizeof(float);
+    if (sm_red > sm) sm = sm_red;
+    cudaFuncSetAttribute(se_pool_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    se_pool_bulk_kernel<<<dim3(J, B), cvc * ln, sm, st>>>((const bf16*)in, coef, (bf16*)act, partial, Nsp, C, cvc, R);
+    DWN_LAUNCH_CHECK();
+    return 0;
+  }
   if (dtype == DWN_DT_F32) {
     int cvc = dwn_largest_divisor_le(C / 4, 64), ln = 256 / cvc;
     dim3 grid(J, (C / 4) / cvc, B), block(cvc * ln);
@@ -653,17 +725,20 @@ extern "C" int dwn_se_pool(const void* in, const float* coef, void* act, float* 
   return 0;
 }
 
-// SE excitation MLP, one CTA per sample (dwiseneuro.py:40-43): mean -> reduce(+b) -> SiLU -> expand(+b) -> sigmoid
-__global__ void se_mlp_kernel(const float* __restrict__ partial, int J, float inv_n, const float* __restrict__ w1,
-                              const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-                              float* __restrict__ mean_out, float* __restrict__ hpre_out, float* __restrict__ gate_out,
-                              int C, int RD) {
+// SE excitation MLP, one CTA (1024 threads) per sample (dwiseneuro.py:40-43):
+// mean -> reduce(+b) -> SiLU -> expand(+b) -> sigmoid.  Loops are unrolled so that several loads are in flight.
+__global__ void __launch_bounds__(1024) se_mlp_kernel(const float* __restrict__ partial, int J, float inv_n,
+                                                     const float* __restrict__ w1, const float* __restrict__ b1,
+                                                     const float* __restrict__ w2, const float* __restrict__ b2,
+                                                     float* __restrict__ mean_out, float* __restrict__ hpre_out,
+                                                     float* __restrict__ gate_out, int C, int RD) {
   extern __shared__ float sm[];  // mean[C], h[RD]
   float* s_mean = sm;
   float* s_h = sm + C;
   const int b = blockIdx.x, tid = threadIdx.x;
   for (int c = tid; c < C; c += blockDim.x) {
     float s = 0.f;
+#pragma unroll 8
     for (int j = 0; j < J; ++j) s += partial[((long)b * J + j) * C + c];
     s *= inv_n;
     s_mean[c] = s;
@@ -673,7 +748,8 @@ __global__ void se_mlp_kernel(const float* __restrict__ partial, int J, float in
   const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
   for (int r = wid; r < RD; r += nw) {
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(w1[(long)r * C + c], s_mean[c], s);
+#pragma unroll 8
+    for (int c = lane; c < C; c += 32) s = fmaf(__ldg(&w1[(long)r * C + c]), s_mean[c], s);
     s = warp_sum(s);
     if (lane == 0) {
       s += b1[r];
@@ -684,7 +760,8 @@ __global__ void se_mlp_kernel(const float* __restrict__ partial, int J, float in
   __syncthreads();
   for (int c = tid; c < C; c += blockDim.x) {
     float s = b2[c];
-    for (int r = 0; r < RD; ++r) s = fmaf(w2[(long)c * RD + r], s_h[r], s);
+#pragma unroll 8
+    for (int r = 0; r < RD; ++r) s = fmaf(__ldg(&w2[(long)c * RD + r]), s_h[r], s);
     gate_out[(long)b * C + c] = 1.0f / (1.0f + expf(-s));
   }
 }
@@ -692,8 +769,8 @@ __global__ void se_mlp_kernel(const float* __restrict__ partial, int J, float in
 extern "C" int dwn_se_mlp(const float* partial, int J, int Nsp, const float* w1, const float* b1, const float* w2,
                           const float* b2, float* mean_out, float* hpre_out, float* gate_out, int B, int C, int RD,
                           void* stream) {
-  se_mlp_kernel<<<B, 256, (C + RD) * sizeof(float), (cudaStream_t)stream>>>(partial, J, 1.0f / (float)Nsp, w1, b1, w2, b2,
-                                                                            mean_out, hpre_out, gate_out, C, RD);
+  se_mlp_kernel<<<B, 1024, (C + RD) * sizeof(float), (cudaStream_t)stream>>>(partial, J, 1.0f / (float)Nsp, w1, b1, w2, b2,
+                                                                             mean_out, hpre_out, gate_out, C, RD);
   DWN_LAUNCH_CHECK();
   return 0;
 }

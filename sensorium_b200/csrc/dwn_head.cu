@@ -91,7 +91,10 @@ __global__ void __launch_bounds__(256) readout_bwd_prep_kernel(const float* __re
                                                                T* __restrict__ dz_nm, T* __restrict__ dz_mn,
                                                                float* __restrict__ dbias, int B, int Tn, int n_out,
                                                                int half, int half_pad, int G) {
-  __shared__ float tile[32][33];
+  // BG samples per round: all their loads are issued before the first use, so a round costs one DRAM latency
+  // instead of BG (the serial per-sample loop made this kernel pure latency: ~44 us for 48 MB)
+  constexpr int BG = 4;
+  __shared__ float tile[BG][32][33];
   const int g = blockIdx.y;
   const int n0 = blockIdx.x * 32;
   const int tid = threadIdx.x;
@@ -102,25 +105,41 @@ __global__ void __launch_bounds__(256) readout_bwd_prep_kernel(const float* __re
   const bool valid = nl < half && n < n_out;
   const int M = B * Tn;
   float db = 0.f;
-  for (int b = 0; b < B; ++b) {
+  for (int b0 = 0; b0 < B; b0 += BG) {
     for (int t0 = 0; t0 < Tn; t0 += 32) {
-      __syncthreads();
-      for (int t = t0 + tq; t < Tn && t < t0 + 32; t += 8) {
-        float dz = 0.f;
-        if (valid) {
-          const long idx = ((long)b * n_out + n) * Tn + t;
-          const float p = pred[idx];
-          const float bp = beta * p;
-          dz = dpred[idx] * (bp > 20.0f ? 1.0f : 1.0f - expf(-bp));
+      float p[BG][4], d[BG][4];
+#pragma unroll
+      for (int bb = 0; bb < BG; ++bb)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + tq + 8 * u;
+          const bool ok = valid && (b0 + bb < B) && t < Tn;
+          const long idx = ok ? ((long)(b0 + bb) * n_out + n) * Tn + t : 0;
+          p[bb][u] = ok ? pred[idx] : 0.f;
+          d[bb][u] = ok ? dpred[idx] : 0.f;
         }
-        if (nl < half) st1<T>(dz_nm + (long)(g * half + nl) * M + (long)b * Tn + t, dz);
-        db += rnd<T>(dz);
-        tile[t - t0][r] = dz;
-      }
+      __syncthreads();
+#pragma unroll
+      for (int bb = 0; bb < BG; ++bb)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + tq + 8 * u;
+          if (b0 + bb < B && t < Tn) {
+            const float bp = beta * p[bb][u];
+            const float dz = valid ? d[bb][u] * (bp > 20.0f ? 1.0f : 1.0f - expf(-bp)) : 0.f;
+            if (nl < half) st1<T>(dz_nm + (long)(g * half + nl) * M + (long)(b0 + bb) * Tn + t, dz);
+            db += rnd<T>(dz);
+            tile[bb][t - t0][r] = dz;
+          }
+        }
       __syncthreads();
       if (n0 + r2 < half_pad)
-        for (int t = t0 + tt; t < Tn && t < t0 + 32; t += 8)
-          st1<T>(dz_mn + ((long)b * Tn + t) * ((long)G * half_pad) + (long)g * half_pad + n0 + r2, tile[t - t0][r2]);
+#pragma unroll
+        for (int bb = 0; bb < BG; ++bb)
+          if (b0 + bb < B)
+            for (int t = t0 + tt; t < Tn && t < t0 + 32; t += 8)
+              st1<T>(dz_mn + ((long)(b0 + bb) * Tn + t) * ((long)G * half_pad) + (long)g * half_pad + n0 + r2,
+                     tile[bb][t - t0][r2]);
     }
   }
   db += __shfl_xor_sync(0xffffffffu, db, 4);

@@ -109,32 +109,46 @@ __global__ void pw_abd_kernel(const float* __restrict__ coef, const float* __res
     wprime[(long)c * ci + k] = __float2bfloat16_rn(a * __bfloat162float(w[(long)c * ci + k]));
 }
 
-// step B: partial[s][j][k] = sum_{c in split s} coeff(c,j) * W[c][k],  coeff = d_c*W[c][j] (j < ci) or b_c (j == ci)
-constexpr int PWQ_JT = 16, PWQ_SPLIT = 8;
+// step B: partial[s][j][k] = sum_{c in split s} coeff(c,j) * W[c][k],  coeff = d_c*W[c][j] (j < ci) or b_c (j == ci).
+// The split's W rows and the 16 coefficients per row are staged in shared memory once (one coalesced load phase),
+// so the accumulation loop has no dependent global loads.
+constexpr int PWQ_JT = 16, PWQ_SPLIT = 32;
 __global__ void pw_q_partial_kernel(const float* __restrict__ abd, const bf16* __restrict__ w,
                                     float* __restrict__ partial, int mid, int ci) {
+  extern __shared__ __align__(16) unsigned char pwq_sm[];
   const int k = threadIdx.x;
   const int j0 = blockIdx.x * PWQ_JT, sidx = blockIdx.y;
   const int cper = (mid + PWQ_SPLIT - 1) / PWQ_SPLIT;
   const int cbeg = sidx * cper, cend = min(mid, cbeg + cper);
+  const int cnt = max(cend - cbeg, 0);
+  float* scf = reinterpret_cast<float*>(pwq_sm);                       // [cper][PWQ_JT]
+  bf16* sw = reinterpret_cast<bf16*>(pwq_sm + (size_t)cper * PWQ_JT * sizeof(float));  // [cper][ci]
+  for (int i = k; i < cnt * ci; i += blockDim.x) sw[i] = w[(long)cbeg * ci + i];
+  for (int i = k; i < cnt * PWQ_JT; i += blockDim.x) {
+    const int cl = i / PWQ_JT, j = j0 + i % PWQ_JT, c = cbeg + cl;
+    scf[i] = j < ci ? abd[2 * mid + c] * __bfloat162float(w[(long)c * ci + j]) : (j == ci ? abd[mid + c] : 0.f);
+  }
+  __syncthreads();
+  if (k >= ci) return;
   float acc[PWQ_JT];
 #pragma unroll
   for (int jj = 0; jj < PWQ_JT; ++jj) acc[jj] = 0.f;
-  if (k < ci) {
-    for (int c = cbeg; c < cend; ++c) {
-      const float wk = __bfloat162float(w[(long)c * ci + k]);
-      const float bc = abd[mid + c], dc = abd[2 * mid + c];
+#pragma unroll 2
+  for (int cl = 0; cl < cnt; ++cl) {
+    const float wk = __bfloat162float(sw[cl * ci + k]);
+    const float4* cf = reinterpret_cast<const float4*>(scf + cl * PWQ_JT);
 #pragma unroll
-      for (int jj = 0; jj < PWQ_JT; ++jj) {
-        const int j = j0 + jj;
-        const float cf = j < ci ? dc * __bfloat162float(w[(long)c * ci + j]) : (j == ci ? bc : 0.f);
-        acc[jj] = fmaf(cf, wk, acc[jj]);
-      }
+    for (int q = 0; q < PWQ_JT / 4; ++q) {
+      const float4 f = cf[q];
+      acc[4 * q + 0] = fmaf(f.x, wk, acc[4 * q + 0]);
+      acc[4 * q + 1] = fmaf(f.y, wk, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(f.z, wk, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(f.w, wk, acc[4 * q + 3]);
     }
-#pragma unroll
-    for (int jj = 0; jj < PWQ_JT; ++jj)
-      if (j0 + jj <= ci) partial[((long)sidx * (ci + 1) + j0 + jj) * ci + k] = acc[jj];
   }
+#pragma unroll
+  for (int jj = 0; jj < PWQ_JT; ++jj)
+    if (j0 + jj <= ci) partial[((long)sidx * (ci + 1) + j0 + jj) * ci + k] = acc[jj];
 }
 
 // step C: -Q (bf16, ci x ci) and r (fp32, ci) from the split partials
@@ -159,7 +173,10 @@ extern "C" int dwn_pw_bwd_prep(const float* coef, const float* bcoef, const void
   pw_abd_kernel<<<mid, nt > 256 ? 256 : nt, 0, st>>>(coef, bcoef, (const bf16*)w_bf16, (bf16*)wprime, abd, mid, ci);
   DWN_LAUNCH_CHECK();
   dim3 gq((ci + 1 + PWQ_JT - 1) / PWQ_JT, PWQ_SPLIT);
-  pw_q_partial_kernel<<<gq, nt, 0, st>>>(abd, (const bf16*)w_bf16, partial, mid, ci);
+  const int cper = (mid + PWQ_SPLIT - 1) / PWQ_SPLIT;
+  const size_t qsm = (size_t)cper * PWQ_JT * sizeof(float) + (size_t)cper * ci * sizeof(bf16);
+  DWN_REQUIRE(qsm <= 48 * 1024, "dwn_pw_bwd_prep: shared memory");
+  pw_q_partial_kernel<<<gq, nt, qsm, st>>>(abd, (const bf16*)w_bf16, partial, mid, ci);
   DWN_LAUNCH_CHECK();
   pw_q_finalize_kernel<<<ci + 1, nt, 0, st>>>(partial, (bf16*)negq, r, ci);
   DWN_LAUNCH_CHECK();

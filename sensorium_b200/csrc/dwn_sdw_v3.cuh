@@ -408,3 +408,182 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
   block_reduce_channels<11, 4>(st, reinterpret_cast<float*>(smem_v3), cqn, W, partial + (long)worker * 11 * C, C, c0);
 }
 
+// =================================================================================================
+// backward, stride 1 (v5).  Same staging as sdw_bwd_v3_kernel<1,...>, different stencil mapping: the v3 stencil
+// re-read all nine fp32 taps of every output from shared memory (9 x LDS.128 per 4 channels) and ncu showed the
+// stride-1 launches limited by shared-memory load wavefronts (~80 % of peak, short-scoreboard stalls) at 47 % of HBM.
+// Here a thread owns ONE channel pair and two columns (wcol, wcol + W/2) in turn and keeps a sliding 3x3 register
+// window over the tile rows, so each output costs 3 x LDS.64: a third of the shared-memory traffic per channel.
+// =================================================================================================
+template <int THI, int CC>
+__global__ void __launch_bounds__(256, 2)
+sdw_bwd_v5_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, const bf16* __restrict__ e_raw,
+                  const float* __restrict__ coef2, const float* __restrict__ bcoef2, const float* __restrict__ coef1,
+                  const float* __restrict__ wgt, bf16* __restrict__ dE, float* __restrict__ partial, int NP, int H,
+                  int C, int nchunks, int nbsh) {
+  constexpr int W = 1024 / CC, WP = W + 2;
+  constexpr int cvn = CC / 8, cvsh = (cvn == 2 ? 1 : cvn == 4 ? 2 : cvn == 8 ? 3 : 4);
+  constexpr int NR = THI + 2;
+  constexpr int RPI = 2;
+  constexpr int NIT = (NR + RPI - 1) / RPI;
+  constexpr int VPR = 256 / RPI;  // vectors per staged row
+  extern __shared__ __align__(16) unsigned char smem_v3[];
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x % nchunks, worker = blockIdx.x / nchunks, nworkers = gridDim.x / nchunks;
+  const int c0 = chunk * CC;
+  constexpr int NVEC = NIT * 256;
+  constexpr int EVEC = THI * 128;  // E tile: THI rows x (W*CC/8 = 128) 16-byte vectors
+  bf16* rawD = reinterpret_cast<bf16*>(smem_v3);
+  bf16* rawS = rawD + (size_t)NVEC * 8;
+  bf16* rawE = rawS + (size_t)NVEC * 8;
+  float* tile = reinterpret_cast<float*>(rawE + (size_t)EVEC * 8);
+  float* sco = tile + (size_t)NR * WP * CC;
+  // staging coordinates (16-byte vectors of 8 channels)
+  const int r_first = tid / VPR;
+  const int two = (tid & (VPR - 1)) >> cvsh;
+  const int lcv = tid & (cvn - 1);
+  // stencil coordinates (one channel pair, two columns)
+  constexpr int cpn = CC / 2, NCOL = 256 / cpn;
+  static_assert(NCOL * 2 == W, "two column halves per thread");
+  const int cp = tid % cpn, wcol = tid / cpn;
+  const int cch = c0 + cp * 2;
+  for (int i = tid; i < CC; i += 256) {
+    const int cc = c0 + i;
+    const float sc = coef2[cc], mu = coef2[2 * C + cc], rs = coef2[3 * C + cc];
+    const float k1 = bcoef2[cc], k2 = bcoef2[C + cc];
+    sco[i] = sc;
+    sco[CC + i] = -sc * (k1 - mu * rs * k2);
+    sco[2 * CC + i] = -sc * rs * k2;
+    float q0, q1;
+    BnSilu<bf16>::prep(coef1[cc], coef1[C + cc], q0, q1);
+    sco[3 * CC + i] = q0;
+    sco[4 * CC + i] = q1;
+  }
+  for (int i = tid; i < NR * WP * CC; i += 256) tile[i] = 0.f;  // halo columns stay zero
+  f32x2 w2[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w2[k] = pk2(wgt[cch * 9 + k], wgt[(cch + 1) * 9 + k]);
+  f32x2 st2[11];
+#pragma unroll
+  for (int q = 0; q < 11; ++q) st2[q] = 0ull;
+  const int nbm = (1 << nbsh) - 1;
+  const int ntiles = NP << nbsh;
+  constexpr int row_step = WP * CC;
+  const int tile_off0 = (r_first * WP + two + 1) * CC + lcv * 8;
+  const int h0 = (tid & 4) ? 4 : 0;  // conflict-free order of the two 16-byte STS
+  const long g_off0 = (long)two * C + c0 + lcv * 8;
+  const long orow = (long)W * C;
+  auto issue = [&](int t) {
+    const int p = t >> nbsh, hi0 = (t & nbm) * THI;
+    const long base = (long)p * H * orow + g_off0;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int r = r_first + it * RPI;
+      const int ho = hi0 - 1 + r;
+      const bool ok = (r < NR) && ((unsigned)ho < (unsigned)H);
+      const long off = ok ? base + (long)ho * orow : 0;
+      cp_async16(rawD + (size_t)(tid + it * 256) * 8, dsh + off, ok);
+      cp_async16(rawS + (size_t)(tid + it * 256) * 8, s_raw + off, ok);
+    }
+  };
+  const int e_r0 = tid >> 7;
+  const long e_goff = (long)((tid & 127) >> cvsh) * C + c0 + lcv * 8;
+  int t = worker;
+  if (t < ntiles) issue(t);
+  cp_async_commit();
+  for (; t < ntiles; t += nworkers) {
+    const int p = t >> nbsh, hi0 = (t & nbm) * THI;
+    cp_async_wait<0>();
+    __syncthreads();  // raw dS/S tiles landed; previous stencil finished with `tile` and `rawE`
+    {  // E rows of this tile: in flight while the dS tile is transformed
+      const bf16* eb = e_raw + ((long)p * H + hi0 + e_r0) * orow + e_goff;
+#pragma unroll
+      for (int it = 0; it < THI / 2; ++it) cp_async16(rawE + (size_t)(tid + it * 256) * 8, eb + (long)(2 * it) * orow, true);
+      cp_async_commit();
+    }
+    // ---- BN2 backward on the staged tile: dS_raw = a*g - d*x - b (zero outside the image)
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int r = r_first + it * RPI;
+      if (r < NR) {
+        const int ho = hi0 - 1 + r;
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+        if ((unsigned)ho < (unsigned)H) {
+          const uint4 qg = *reinterpret_cast<const uint4*>(rawD + (size_t)(tid + it * 256) * 8);
+          const uint4 qx = *reinterpret_cast<const uint4*>(rawS + (size_t)(tid + it * 256) * 8);
+          const uint32_t gg[4] = {qg.x, qg.y, qg.z, qg.w}, xx[4] = {qx.x, qx.y, qx.z, qx.w};
+          const f32x2* ca = reinterpret_cast<const f32x2*>(sco + lcv * 8);            // a
+          const f32x2* cb = reinterpret_cast<const f32x2*>(sco + CC + lcv * 8);       // -b
+          const f32x2* cd = reinterpret_cast<const f32x2*>(sco + 2 * CC + lcv * 8);   // -d
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float g0, g1, x0, x1;
+            unpack_bf16x2(gg[j], g0, g1);
+            unpack_bf16x2(xx[j], x0, x1);
+            f32x2 rr = cb[j];
+            ffma2(rr, ca[j], pk2(g0, g1));
+            ffma2(rr, cd[j], pk2(x0, x1));
+            upk2(rr, v[2 * j], v[2 * j + 1]);
+          }
+          o0 = make_float4(v[0], v[1], v[2], v[3]);
+          o1 = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        float* dst = tile + tile_off0 + it * RPI * row_step;
+        *reinterpret_cast<float4*>(dst + h0) = h0 ? o1 : o0;
+        *reinterpret_cast<float4*>(dst + (4 - h0)) = h0 ? o0 : o1;
+      }
+    }
+    cp_async_wait<0>();  // E tile landed
+    __syncthreads();     // tile + E ready, raw dS/S buffers free
+    if (t + nworkers < ntiles) issue(t + nworkers);
+    cp_async_commit();
+    // ---- transposed stencil + weight gradient: sliding 3x3 register window down the tile rows
+    const f32x2 qa0 = ldp2(sco + 3 * CC + cp * 2);
+    const f32x2 qa1 = ldp2(sco + 4 * CC + cp * 2);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int wi = wcol + half * NCOL;
+      const bf16* esm = rawE + (size_t)wi * CC + cp * 2;  // row hl at + hl*W*CC
+      const float* tb = tile + (wi + 2) * CC + cp * 2;    // tap (kh,kw) of input row hl: tile row hl+2-kh, column -kw
+      bf16* dp = dE + (((long)p * H + hi0) * W + wi) * C + cch;
+      f32x2 R[3][3];
+      auto load_row = [&](const int r) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) R[r % 3][kw] = ldp2(tb + r * row_step - kw * CC);
+      };
+      load_row(0);
+      load_row(1);
+#pragma unroll
+      for (int hl = 0; hl < THI; ++hl) {
+        load_row(hl + 2);
+        const f32x2 e2 = ldp2(esm + hl * (W * CC));
+        f32x2 sg;
+        const f32x2 ea = bnsilu_grad2_bf16(e2, qa0, qa1, sg);
+        f32x2 acc = 0ull;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const f32x2 q = R[(hl + 2 - kh) % 3][kw];
+            ffma2(acc, w2[kh * 3 + kw], q);
+            ffma2(st2[2 + kh * 3 + kw], ea, q);
+          }
+        const f32x2 o = fmul2(acc, sg);
+        stp2(dp + hl * orow, o);
+        // statistics on the raw E: sum(o) and sum(o*e); sum(o*xhat) is formed once per CTA after the tile loop
+        fadd2(st2[0], o);
+        ffma2(st2[1], o, e2);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  float st[11][2];
+#pragma unroll
+  for (int q = 0; q < 11; ++q) upk2(st2[q], st[q][0], st[q][1]);
+#pragma unroll
+  for (int j = 0; j < 2; ++j)  // sum(o*xhat1) from the raw-E sums
+    st[1][j] = coef1[3 * C + cch + j] * (st[1][j] - coef1[2 * C + cch + j] * st[0][j]);
+  block_reduce_channels<11, 2>(st, reinterpret_cast<float*>(smem_v3), cpn, NCOL, partial + (long)worker * 11 * C, C, c0);
+}

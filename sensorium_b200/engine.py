@@ -14,7 +14,7 @@ from __future__ import annotations
 import math
 import weakref
 from types import SimpleNamespace
-from typing import List, Optional
+from typing import Dict, List, Optional
 
 import torch
 
@@ -137,7 +137,7 @@ def _split_k(rows: int, tiles: int) -> int:
     return z
 
 
-def _gram(xb, M, ci, st, dev):
+def _gram(xb, M, ci, st, dev, out=None):
     """Gx = X^T X (ci x ci, fp32) of the bf16 block input via a split-K (MN,MN) tcgen05 GEMM."""
     tiles = math.ceil(ci / 128) * math.ceil(ci / 256)
     zs = _split_k(M, tiles)
@@ -146,9 +146,20 @@ def _gram(xb, M, ci, st, dev):
     gemm(st, dtype=BF16, A=xb, B=xb, a_mn=1, b_mn=1, lda=ci, ldb=ci, a_zstride=rows * ci, b_zstride=rows * ci,
          a_zmode=1, b_zmode=1, M=ci, N=ci, K=rows, Z=zs, D=part, d_dtype=F32, ldd=ci, d_zstride=ci * ci, _tag="gram",
          _bytes=M * ci * 2)
-    g = _empty((ci, ci), torch.float32, dev)
+    g = _empty((ci, ci), torch.float32, dev) if out is None else out
     call("dwn_reduce_rows", part, zs, ci * ci, g, st)
     return g
+
+
+_stats_side: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _stats_stream(dev):
+    """Side stream for the Gram-matrix BatchNorm statistics of conv_pw (they depend only on the block input and
+    run next to the expansion GEMM)."""
+    if dev.index not in _stats_side:
+        _stats_side[dev.index] = torch.cuda.Stream(device=dev)
+    return _stats_side[dev.index]
 
 
 def _colstats(x, M, ld, C, dcode, st, dev):
@@ -230,18 +241,29 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         # 1. point-wise expansion (tcgen05 GEMM / SIMT fp32)
         wpw = blk.conv_pw[0].weight
         E = _empty((Mi, mid), adt, dev)
-        gemm(st, dtype=dcode, A=Xb if bf else X, B=_shadow(wpw) if bf else wpw, lda=ci, ldb=ci, M=Mi, N=mid, K=ci, Z=1,
-             D=E, d_dtype=dcode, ldd=mid, _tag="pw_fwd", _bytes=(Mi * ci + mid * ci + Mi * mid) * es)
+        wsh = _shadow(wpw) if bf else wpw
         gram = sx = None
+        stats_side = []
         if training and bf:
-            # BatchNorm statistics of E = X W^T from the Gram matrix of X (no pass over E), see dwn_pw_algebra.cu
-            gram = _gram(Xb, Mi, ci, st, dev)
+            # BatchNorm statistics of E = X W^T from the Gram matrix of X (no pass over E), see dwn_pw_algebra.cu.
+            # They depend only on X: outputs are allocated here (main stream), the small kernels run on a side
+            # stream next to the expansion GEMM and are joined before the spatial depth-wise kernel reads coef1.
+            gram = _empty((ci, ci), torch.float32, dev)
             sx = _empty((ci,), torch.float32, dev)
-            call("dwn_partial_colsum", sc_part, _P, 3, 2, ci, sx, st)
             coef1 = _empty((4, mid), torch.float32, dev)
             bn1 = blk.conv_pw[1].bn
-            call("dwn_pw_stats", gram, sx, _shadow(wpw), float(Mi), bn1.weight, bn1.bias, bn1.running_mean,
-                 bn1.running_var, bn1.num_batches_tracked, BN_MOM, BN_EPS, coef1, mid, ci, st)
+            stats_side = [_stats_stream(dev)]
+            _fork(stats_side, dev)
+            with torch.cuda.stream(stats_side[0]):
+                sst = _stream(dev)
+                _gram(Xb, Mi, ci, sst, dev, out=gram)
+                call("dwn_partial_colsum", sc_part, _P, 3, 2, ci, sx, sst)
+                call("dwn_pw_stats", gram, sx, wsh, float(Mi), bn1.weight, bn1.bias, bn1.running_mean,
+                     bn1.running_var, bn1.num_batches_tracked, BN_MOM, BN_EPS, coef1, mid, ci, sst)
+        gemm(st, dtype=dcode, A=Xb if bf else X, B=wsh, lda=ci, ldb=ci, M=Mi, N=mid, K=ci, Z=1,
+             D=E, d_dtype=dcode, ldd=mid, _tag="pw_fwd", _bytes=(Mi * ci + mid * ci + Mi * mid) * es)
+        if stats_side:
+            _join(stats_side, dev)
         else:
             coef1 = _bn_coef(blk.conv_pw[1].bn, _colstats(E, Mi, mid, mid, dcode, st, dev) if training else None, _P,
                              Mi, mid, 0, training, st, dev)

@@ -12,6 +12,7 @@ from typing import Dict, List, Optional, Sequence
 
 import torch
 
+from . import _lib
 from ._lib import call, gemm
 from .engine import (BF16, F32, _P, _P_SDW, _empty, _fork, _join, _nullctx, _shadow, _side_streams, _split_k,
                      _stream)
@@ -163,10 +164,10 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         # temporal dw backward
         part = _empty((B * _J_TDW, 2, mid), torch.float32, dev)
         call("dwn_tdw_bwd_reduce", da, b.Tm, b.coef3, dmean, Nsp, part, _J_TDW, B, mid, dcode, st, _tag="tdw_bwd_reduce",
-             _bytes=3 * Mo * mid * es)
+             _bytes=2 * Mo * mid * es)
         bcoef3 = _bn_bwd(part, B * _J_TDW, 2, 0, Mo, blk.temp_covn_dw[1].bn, grads, mid, st, dev)
         part7 = _empty((_P, 7, mid), torch.float32, dev)
-        call("dwn_tdw_bwd", da, b.Tm, b.S, b.coef3, bcoef3, b.coef2, blk.temp_covn_dw[0].weight, part7, _P, B, T,
+        call("dwn_tdw_bwd", da, b.Tm, b.S, b.coef3, bcoef3, b.coef2, blk.temp_covn_dw[0].weight, dmean, part7, _P, B, T,
              b.Ho * b.Wo, mid, dcode, st, _tag="tdw_bwd", _bytes=4 * Mo * mid * es)
         bcoef2 = _bn_bwd(part7, _P, 7, 0, Mo, blk.spat_covn_dw[1].bn, grads, mid, st, dev)
         dwt = torch.empty_like(blk.temp_covn_dw[0].weight)
@@ -196,7 +197,7 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
             wprime = _empty((mid, ci), torch.bfloat16, dev)
             negq = _empty((ci, ci), torch.bfloat16, dev)
             colbias = _empty((ci,), torch.float32, dev)
-            scratch = _empty((3 * mid + 8 * (ci + 1) * ci,), torch.float32, dev)
+            scratch = _empty((_lib.lib().dwn_pw_bwd_prep_scratch(mid, ci),), torch.float32, dev)
             call("dwn_pw_bwd_prep", b.coef1, bcoef1, wsh, wprime, negq, colbias, scratch, mid, ci, st)
             gemm(st, dtype=dcode, A=dE, B=wprime, b_mn=1, lda=mid, ldb=ci, M=Mi, N=ci, K=mid, Z=1, A2=b.Xb, B2=negq,
                  lda2=ci, ldb2=ci, K2=ci, D=dXpw, d_dtype=F32, ldd=ci, _tag="pw_dgrad",
