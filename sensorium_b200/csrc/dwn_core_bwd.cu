@@ -89,15 +89,32 @@ __global__ void block_bwd_reduce_kernel(const float* __restrict__ dO, const T* _
   float st[4][4] = {};
   const int Hi = Ho * stride, Wi = Wo * stride;
   const int Mo = B * Tn * Ho * Wo;
-#pragma unroll 2
-  for (int m = blockIdx.x * ln + lane; m < Mo; m += gridDim.x * ln) {
-    const int wq = dw.mod(m), r1 = dw.div(m);
-    const int hq = dh.mod(r1), bt = dh.div(r1);
-    const int b = dt.div(bt);
+  // the three streamed quads go through a per-thread cp.async pipeline (ThreadPipe, dwn_sdw_v3.cuh)
+  constexpr int DEPTH = 8;
+  ThreadPipe<DEPTH, 3> pipe(smem, blockDim.x, tid);
+  const int m0 = blockIdx.x * ln + lane, mstep = gridDim.x * ln;
+  auto issue = [&](int k) {
+    const int m = m0 + k * mstep;
+    if (m < Mo) {
+      const int wq = dw.mod(m), r1 = dw.div(m);
+      const int hq = dh.mod(r1), bt = dh.div(r1);
+      cp_async16_ok(pipe.slot(k, 0), dO + (long)m * Co + c);
+      pipe_issue_quad<T>(pipe.slot(k, 1), y_raw + (long)m * Co + c);
+      cp_async16_ok(pipe.slot(k, 2), xin + (((long)bt * Hi + hq * stride) * Wi + wq * stride) * Ci + ci);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int k = 0; k < DEPTH; ++k) issue(k);
+  int kk = 0;
+  for (int m = m0; m < Mo; m += mstep, ++kk) {
+    const int b = dt.div(dh.div(dw.div(m)));
     float g[4], y[4], x[4];
-    ldq(dO + (long)m * Co + c, g);
-    ldq(y_raw + (long)m * Co + c, y);
-    ldq(xin + (((long)bt * Hi + hq * stride) * Wi + wq * stride) * Ci + ci, x);
+    cp_async_wait<DEPTH - 1>();
+    quad_from(*pipe.slot(kk, 0), g);
+    pipe_read_quad<T>(pipe.slot(kk, 1), y);
+    quad_from(*pipe.slot(kk, 2), x);
+    issue(kk + DEPTH);
     const float d = dp ? dp[b] : 1.0f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -108,6 +125,7 @@ __global__ void block_bwd_reduce_kernel(const float* __restrict__ dO, const T* _
       st[3][j] = fmaf(g[j], (x[j] - ms[j]) * rs[j], st[3][j]);
     }
   }
+  cp_async_wait<0>();
   block_reduce_channels<4, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 4 * Co, Co, blockIdx.y * cqc * 4);
 }
 
@@ -117,6 +135,9 @@ extern "C" int dwn_block_bwd_reduce(const float* dO, const void* y_raw, const fl
   int cqc = dwn_largest_divisor_le(Co / 4, 64), ln = 256 / cqc;
   dim3 grid(P, (Co / 4) / cqc), block(cqc * ln);
   size_t sm = (size_t)block.x * 16 * sizeof(float);
+  if (ThreadPipe<8, 3>::bytes(block.x) > sm) sm = ThreadPipe<8, 3>::bytes(block.x);
+  cudaFuncSetAttribute(block_bwd_reduce_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  cudaFuncSetAttribute(block_bwd_reduce_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (dtype == DWN_DT_F32)
     block_bwd_reduce_kernel<float><<<grid, block, sm, (cudaStream_t)stream>>>(dO, (const float*)y_raw, coef4, dp, xin,
                                                                               coef_sc, partial, B, Tn, Ho, Wo, Ci, Co,
@@ -211,32 +232,62 @@ __global__ void block_in_bwd_kernel(const float* __restrict__ dXpw, const float*
     }
   float cb[4] = {0.f, 0.f, 0.f, 0.f};
   if (colbias) ldq(colbias + c, cb);
-#pragma unroll 2
-  for (int m = blockIdx.x * ln + lane; m < Mi; m += gridDim.x * ln) {
+  // the streamed quads go through a per-thread cp.async pipeline (ThreadPipe, dwn_sdw_v3.cuh):
+  // slot = { dXpw quad, x quad, dO quad, dO quad of the second channel tile }.  The stem input scalars are shared by
+  // the threads of a pixel and stay plain (broadcast) loads.
+  constexpr int DEPTH = 4;
+  constexpr int NV = 4;
+  ThreadPipe<DEPTH, NV> pipe(smem, blockDim.x, tid);
+  const int m0 = blockIdx.x * ln + lane, mstep = gridDim.x * ln;
+  auto issue = [&](int k) {
+    const int m = m0 + k * mstep;
+    if (m < Mi) {
+      cp_async16_ok(pipe.slot(k, 0), dXpw + (long)m * Ci + c);
+      const int wq = dw.mod(m), r1 = dw.div(m);
+      const int hq = dh.mod(r1), bt = dh.div(r1);
+      if ((hq % stride) == 0 && (wq % stride) == 0) {
+        const long mo = ((long)bt * Ho + hq / stride) * Wo + wq / stride;
+        cp_async16_ok(pipe.slot(k, 1), xin + (long)m * Ci + c);
+        cp_async16_ok(pipe.slot(k, 2), dO + mo * Co + c);
+        if (nrep > 1) cp_async16_ok(pipe.slot(k, 3), dO + mo * Co + c + Ci);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int k = 0; k < DEPTH; ++k) issue(k);
+  int kk = 0;
+  for (int m = m0; m < Mi; m += mstep, ++kk) {
     float o[4];
-    ldq(dXpw + (long)m * Ci + c, o);
+    float xs[STEM_CIN > 0 ? STEM_CIN : 1];
+    if (STEM_CIN > 0) {  // issued before the wait so that their latency overlaps it
+      const int b = m / plane, pos = m - b * plane;
+#pragma unroll
+      for (int q = 0; q < STEM_CIN; ++q) xs[q] = __ldg(&x_in[((long)b * STEM_CIN + q) * plane + pos]);
+    }
+    cp_async_wait<DEPTH - 1>();
+    quad_from(*pipe.slot(kk, 0), o);
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] -= cb[j];
     const int wq = dw.mod(m), r1 = dw.div(m);
     const int hq = dh.mod(r1), bt = dh.div(r1);
     if ((hq % stride) == 0 && (wq % stride) == 0) {
-      const long mo = ((long)bt * Ho + hq / stride) * Wo + wq / stride;
       float x[4], g[4];
-      ldq(xin + (long)m * Ci + c, x);
-      ldq(dO + mo * Co + c, g);
+      quad_from(*pipe.slot(kk, 1), x);
+      quad_from(*pipe.slot(kk, 2), g);
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] += fmaf(a[0][j], g[j], -fmaf(dd[j], x[j], bb[j]));
       if (nrep > 1) {
-        ldq(dO + mo * Co + c + Ci, g);
+        quad_from(*pipe.slot(kk, 3), g);
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = fmaf(a[1][j], g[j], o[j]);
       }
     }
+    issue(kk + DEPTH);
     if (STEM_CIN > 0) {
-      const int b = bt / Tn, pos = m - b * plane;
 #pragma unroll
       for (int k = 0; k < STEM_CIN; ++k) {
-        const float xv = __ldg(&x_in[((long)b * STEM_CIN + k) * plane + pos]);
+        const float xv = xs[k];
 #pragma unroll
         for (int j = 0; j < 4; ++j) sst[k][j] = fmaf(o[j], xv, sst[k][j]);
       }
@@ -246,6 +297,7 @@ __global__ void block_in_bwd_kernel(const float* __restrict__ dXpw, const float*
       stq(dXin + (long)m * Ci + c, o);
     }
   }
+  cp_async_wait<0>();
   if (STEM_CIN > 0)
     block_reduce_channels<SQ, 4>(sst, smem, cqc, ln, stem_partial + (long)blockIdx.x * SQ * Ci, Ci, blockIdx.y * cqc * 4);
 }
@@ -256,7 +308,9 @@ extern "C" int dwn_block_in_bwd(const float* dXpw, const float* dO, const float*
   DWN_REQUIRE(Co <= 2 * Ci, "dwn_block_in_bwd: channel tiling factor > 2 unsupported (Co=%d Ci=%d)", Co, Ci);
   int cqc = dwn_largest_divisor_le(Ci / 4, 64), ln = 256 / cqc;
   dim3 grid(592, (Ci / 4) / cqc), block(cqc * ln);
-  block_in_bwd_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(dXpw, dO, xin, coef_sc, bcoef_sc, colbias, dXin, B, Tn,
+  const size_t sm = ThreadPipe<4, 4>::bytes(block.x);
+  cudaFuncSetAttribute(block_in_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  block_in_bwd_kernel<0><<<grid, block, sm, (cudaStream_t)stream>>>(dXpw, dO, xin, coef_sc, bcoef_sc, colbias, dXin, B, Tn,
                                                                    Hi, Wi, Ci, Co, stride, cqc, FastDiv(Wi), FastDiv(Hi),
                                                                    nullptr, nullptr);
   DWN_LAUNCH_CHECK();
@@ -271,7 +325,10 @@ extern "C" int dwn_block_in_bwd_stem(const float* dXpw, const float* dO, const f
   DWN_REQUIRE(Co <= 2 * Ci, "dwn_block_in_bwd_stem: channel tiling factor > 2 unsupported");
   int cqc = dwn_largest_divisor_le(Ci / 4, 64), ln = 256 / cqc;
   dim3 grid(592, (Ci / 4) / cqc), block(cqc * ln);
-  block_in_bwd_kernel<5><<<grid, block, block.x * 24 * sizeof(float), (cudaStream_t)stream>>>(
+  size_t sm = (size_t)block.x * 24 * sizeof(float);
+  if (ThreadPipe<4, 4>::bytes(block.x) > sm) sm = ThreadPipe<4, 4>::bytes(block.x);
+  cudaFuncSetAttribute(block_in_bwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  block_in_bwd_kernel<5><<<grid, block, sm, (cudaStream_t)stream>>>(
       dXpw, dO, xin, coef_sc, bcoef_sc, colbias, nullptr, B, Tn, Hi, Wi, Ci, Co, stride, cqc, FastDiv(Wi), FastDiv(Hi), x_in,
       stem_partial);
   DWN_LAUNCH_CHECK();

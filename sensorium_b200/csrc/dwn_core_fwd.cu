@@ -222,6 +222,8 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
   }
   float st[3][4] = {};
   const int plane = Tn * H * W, M = B * plane;
+  // (a per-thread cp.async prefetch of the CIN input scalars was tried here and was 2x slower: the 16 threads of a
+  // pixel share the same scalars, which plain loads broadcast but LDGSTS copies once per thread)
 #pragma unroll 2
   for (int m = blockIdx.x * ln + lane; m < M; m += gridDim.x * ln) {
     const int b = dplane.div(m), pos = m - b * plane;
@@ -833,14 +835,33 @@ __global__ void block_out_kernel(const T* __restrict__ y_raw, const float* __res
   float st[3][4] = {};
   const int Hi = Ho * stride, Wi = Wo * stride;
   const int Mo = B * Tn * Ho * Wo;
-#pragma unroll 2
-  for (int m = blockIdx.x * ln + lane; m < Mo; m += gridDim.x * ln) {
+  // the two streamed operands (Y_raw quad, shortcut quad) go through a per-thread cp.async pipeline (see ThreadPipe):
+  // with ~90 registers only 2 CTAs fit per SM and plain loads kept < 25 KB in flight per SM
+  constexpr int DEPTH = 8;
+  ThreadPipe<DEPTH, 2> pipe(smem, blockDim.x, tid);
+  const int m0 = blockIdx.x * ln + lane, mstep = gridDim.x * ln;
+  auto issue = [&](int k) {
+    const int m = m0 + k * mstep;
+    if (m < Mo) {
+      const int wq = dw.mod(m), r1 = dw.div(m);
+      const int hq = dh.mod(r1), bt = dh.div(r1);
+      pipe_issue_quad<T>(pipe.slot(k, 0), y_raw + (long)m * Co + c);
+      cp_async16_ok(pipe.slot(k, 1), xin + (((long)bt * Hi + hq * stride) * Wi + wq * stride) * Ci + ci);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int k = 0; k < DEPTH; ++k) issue(k);
+  int kk = 0;
+  for (int m = m0; m < Mo; m += mstep, ++kk) {
     const int wq = dw.mod(m), r1 = dw.div(m);
     const int hq = dh.mod(r1), bt = dh.div(r1);
     const int tq = dt.mod(bt), b = dt.div(bt);
     float y[4], x[4], o[4];
-    ldq(y_raw + (long)m * Co + c, y);
-    ldq(xin + (((long)bt * Hi + hq * stride) * Wi + wq * stride) * Ci + ci, x);
+    cp_async_wait<DEPTH - 1>();
+    pipe_read_quad<T>(pipe.slot(kk, 0), y);
+    quad_from(*pipe.slot(kk, 1), x);
+    issue(kk + DEPTH);
     const float d = dp ? dp[b] : 1.0f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] = d * fmaf(y[j], s4[j], h4[j]) + fmaf(x[j], ss[j], hs[j]);
@@ -861,6 +882,7 @@ __global__ void block_out_kernel(const T* __restrict__ y_raw, const float* __res
       for (int j = 0; j < 4; ++j) { st[0][j] += o[j]; st[1][j] = fmaf(o[j], o[j], st[1][j]); }
     }
   }
+  cp_async_wait<0>();
   if (partial)  // [P][3][Co], see stem_fwd_kernel
     block_reduce_channels<3, 4>(st, smem, cqc, ln, partial + (long)blockIdx.x * 3 * Co, Co, blockIdx.y * cqc * 4);
 }
@@ -873,6 +895,9 @@ extern "C" int dwn_block_out(const void* y_raw, const float* coef4, const float*
   int cqc = dwn_largest_divisor_le(Co / 4, 64), ln = 256 / cqc;
   dim3 grid(P, (Co / 4) / cqc), block(cqc * ln);
   size_t sm = (size_t)block.x * 12 * sizeof(float);
+  if (ThreadPipe<8, 2>::bytes(block.x) > sm) sm = ThreadPipe<8, 2>::bytes(block.x);
+  cudaFuncSetAttribute(block_out_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  cudaFuncSetAttribute(block_out_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (dtype == DWN_DT_F32)
     block_out_kernel<float><<<grid, block, sm, (cudaStream_t)stream>>>((const float*)y_raw, coef4, dp, xin, coef_sc, pe_t,
                                                                        pe_h, pe_w, out, (bf16*)out_bf, partial,

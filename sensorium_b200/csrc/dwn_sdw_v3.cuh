@@ -14,6 +14,48 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
   const int sz = valid ? 16 : 0;  // src-size 0 -> 16 bytes of zero fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
+// small always-valid copies (L1-allocating variant: .cg only exists for 16 bytes)
+__device__ __forceinline__ void cp_async16_ok(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+// Per-thread software pipeline through shared memory (trunk kernels): every thread owns DEPTH private slots of NV
+// 16-byte vectors and issues its own cp.async copies DEPTH loop iterations ahead, so the bytes in flight are
+// DEPTH x slot x threads instead of what fits in registers.  Layout [DEPTH][NV][nthr]: conflict-free 16-byte accesses.
+template <int DEPTH, int NV>
+struct ThreadPipe {
+  static_assert((DEPTH & (DEPTH - 1)) == 0, "DEPTH must be a power of two");
+  uint4* base;
+  int nthr;
+  __device__ __forceinline__ ThreadPipe(void* smem, int nthr_, int tid) : base(reinterpret_cast<uint4*>(smem) + tid), nthr(nthr_) {}
+  __device__ __forceinline__ uint4* slot(int k, int v) const { return base + ((k & (DEPTH - 1)) * NV + v) * nthr; }
+  static size_t bytes(int nthr) { return (size_t)DEPTH * NV * nthr * sizeof(uint4); }
+};
+__device__ __forceinline__ void quad_from(const uint4& q, float (&o)[4]) {
+  o[0] = __uint_as_float(q.x); o[1] = __uint_as_float(q.y); o[2] = __uint_as_float(q.z); o[3] = __uint_as_float(q.w);
+}
+__device__ __forceinline__ void quad_from_bf16(const uint4& q, float (&o)[4]) {  // first 8 bytes hold 4 bf16
+  unpack_bf16x2(q.x, o[0], o[1]);
+  unpack_bf16x2(q.y, o[2], o[3]);
+}
+template <typename T> __device__ __forceinline__ void pipe_issue_quad(uint4* dst, const T* src);
+template <> __device__ __forceinline__ void pipe_issue_quad<float>(uint4* dst, const float* src) { cp_async16_ok(dst, src); }
+template <> __device__ __forceinline__ void pipe_issue_quad<bf16>(uint4* dst, const bf16* src) { cp_async8(dst, src); }
+template <typename T> __device__ __forceinline__ void pipe_read_quad(const uint4* src, float (&o)[4]);
+template <> __device__ __forceinline__ void pipe_read_quad<float>(const uint4* src, float (&o)[4]) { quad_from(*src, o); }
+template <> __device__ __forceinline__ void pipe_read_quad<bf16>(const uint4* src, float (&o)[4]) {
+  const uint2 q = *reinterpret_cast<const uint2*>(src);
+  unpack_bf16x2(q.x, o[0], o[1]);
+  unpack_bf16x2(q.y, o[2], o[3]);
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
