@@ -171,6 +171,18 @@ int dwn_distill_weights(float* w, const void* mask, const float* dweight, int n,
 /* ==== sliding-window predictor (src/predictors.py:36-55, src/indexes.py:23-30) ============================== */
 int dwn_window_gather(const float* inp, float* clips, int Cn, int L, long HW, int size, int step, int first_index,
                       int nwin, void* stream);
+/* StackInputsProcessor (inputs.py:22-36) fused with the window gather of predict_trial
+ * (predictors.py:42-51).  video: (Hv, Wv, L) row-major fp32 (video_dtype 0) or uint8 (2); behavior, pupil: (2, L) fp32;
+ * clips: (nw, 5, size, H, W) fp32, window i ends at frame last0 + i. */
+int dwn_assemble_clips(const void* video, int video_dtype, const float* behavior, const float* pupil, float* clips,
+                       int L, int Hv, int Wv, int H, int W, float fill, int size, int step, int last0, int nw,
+                       void* stream);
+/* streaming CorrelationMetric (metrics.py:11-31, 49-74).  acc: (n, 5) doubles
+ * {sum x, sum y, sum xy, sum x^2, sum y^2}, cnt: 1 double; samples with weights[b*wstride] == 0 are skipped. */
+int dwn_corr_update(const float* pred, const float* target, const float* weights, int wstride, int B, int n, int T,
+                    double* acc, double* cnt, void* stream);
+int dwn_corr_finalize(const double* acc, const double* cnt, int n, double eps, float* out, float* out_mean,
+                      void* stream);
 int dwn_window_blend(const float* pred, const float* blend, float* out, int n_out, int L, int size, int step, int win0,
                      int nwin, long pred_wstride, void* stream);
 

@@ -74,6 +74,9 @@ SIGNATURES = {
     "dwn_distill_weights": "pppip",
     "dwn_window_blend": "ppp" + "iiiiii" + "l" + "p",
     "dwn_window_gather": "pp" + "ii" + "l" + "iiii" + "p",
+    "dwn_assemble_clips": "pippp" + "iiiii" + "f" + "iiii" + "p",
+    "dwn_corr_update": "ppp" + "iiii" + "pp" + "p",
+    "dwn_corr_finalize": "pp" + "i" + "d" + "pp" + "p",
     # conv_pw algebra (Gram statistics, BN1-backward folded into GEMMs)
     "dwn_partial_colsum": "piiiipp",
     "dwn_pw_stats": "pppdpppppffpiip",

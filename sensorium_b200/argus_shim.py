@@ -100,6 +100,30 @@ class Model:
                     "nn_state_dict": deep_to(self.nn_module.state_dict(), "cpu")}, file_path)
 
 
+class Metric:
+    """argus.metrics.Metric look-alike (reset / update / compute / epoch_complete protocol, metrics.py:34)."""
+    name: str = ""
+    better: str = "min"
+
+    def reset(self):
+        pass
+
+    def update(self, step_output: dict):
+        pass
+
+    def compute(self):
+        raise NotImplementedError
+
+    def epoch_start(self, state):
+        self.reset()
+
+    def iteration_complete(self, state):
+        self.update(state.step_output)
+
+    def epoch_complete(self, state):
+        state.metrics[self.name] = self.compute()
+
+
 _MODEL_REGISTRY = {}
 
 

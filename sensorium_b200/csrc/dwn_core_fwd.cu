@@ -949,6 +949,7 @@ __global__ void colstats_kernel(const T* __restrict__ x, long M, int ld, int C, 
   const int cv = tid % cvc, lane = tid / cvc, ln = blockDim.x / cvc;
   const int c = (blockIdx.y * cvc + cv) * V;
   float st[2][V] = {};
+#pragma unroll 4
   for (long r = (long)blockIdx.x * ln + lane; r < M; r += (long)gridDim.x * ln) {
     float v[V];
     ldv(x + r * ld + c, v);

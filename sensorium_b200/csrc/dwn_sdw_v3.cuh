@@ -258,7 +258,11 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
   const int two = (tid & (VPR - 1)) >> cvsh;  // output column handled in the staging passes
   const int lcv = tid & (cvn - 1);
   constexpr int cqn = CC >> 2;
-  const int cq = tid % cqn, wi = tid / cqn;
+  // stride 2: the first 128 threads take the even input columns, the last 128 the odd ones, so the column parity
+  // (which decides the taps: kw = 1 for even, kw = 0 and 2 for odd columns) is uniform per warp and is a branch
+  // instead of per-tap selects
+  const int cq = tid % cqn, widx = tid / cqn;
+  const int wi = (S == 1) ? widx : ((widx % (W / 2)) * 2 + widx / (W / 2));
   const int cch = c0 + cq * 4;
   for (int i = tid; i < CC; i += 256) {
     const int cc = c0 + i;
@@ -396,24 +400,23 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
           if ((PAR == 0) != (kh == 1)) continue;
           const int r = (kh == 1) ? hl / 2 : (kh == 0 ? (hl + 1) / 2 : (hl - 1) / 2);
           const float* tr = tbase + r * row_step;
-          {
+          if (odd_w) {  // warp-uniform
             const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(tr + colA * CC);
-            const f32x2 wa0 = odd_w ? w2[kh * 3 + 0][0] : w2[kh * 3 + 1][0];
-            const f32x2 wa1 = odd_w ? w2[kh * 3 + 0][1] : w2[kh * 3 + 1][1];
-            ffma2(acc0, wa0, q.x);
-            ffma2(acc1, wa1, q.y);
-            const f32x2 p0 = fmul2(ea0, q.x), p1 = fmul2(ea1, q.y);
-            fadd2(st2[2 + kh * 3 + 0][0], odd_w ? p0 : 0ull);
-            fadd2(st2[2 + kh * 3 + 0][1], odd_w ? p1 : 0ull);
-            fadd2(st2[2 + kh * 3 + 1][0], odd_w ? 0ull : p0);
-            fadd2(st2[2 + kh * 3 + 1][1], odd_w ? 0ull : p1);
-          }
-          if (odd_w) {
-            const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(tr + colB * CC);
-            ffma2(acc0, w2[kh * 3 + 2][0], q.x);
-            ffma2(acc1, w2[kh * 3 + 2][1], q.y);
-            ffma2(st2[2 + kh * 3 + 2][0], ea0, q.x);
-            ffma2(st2[2 + kh * 3 + 2][1], ea1, q.y);
+            ffma2(acc0, w2[kh * 3 + 0][0], q.x);
+            ffma2(acc1, w2[kh * 3 + 0][1], q.y);
+            ffma2(st2[2 + kh * 3 + 0][0], ea0, q.x);
+            ffma2(st2[2 + kh * 3 + 0][1], ea1, q.y);
+            const ulonglong2 q2 = *reinterpret_cast<const ulonglong2*>(tr + colB * CC);
+            ffma2(acc0, w2[kh * 3 + 2][0], q2.x);
+            ffma2(acc1, w2[kh * 3 + 2][1], q2.y);
+            ffma2(st2[2 + kh * 3 + 2][0], ea0, q2.x);
+            ffma2(st2[2 + kh * 3 + 2][1], ea1, q2.y);
+          } else {
+            const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(tr + colA * CC);
+            ffma2(acc0, w2[kh * 3 + 1][0], q.x);
+            ffma2(acc1, w2[kh * 3 + 1][1], q.y);
+            ffma2(st2[2 + kh * 3 + 1][0], ea0, q.x);
+            ffma2(st2[2 + kh * 3 + 1][1], ea1, q.y);
           }
         }
       }

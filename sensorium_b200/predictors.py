@@ -72,8 +72,48 @@ class Predictor:
         return out
 
     @torch.no_grad()
+    def predict_trial_raw_device(self, video: torch.Tensor, behavior: torch.Tensor, pupil_center: torch.Tensor,
+                                 mouse_index: int) -> torch.Tensor:
+        """Raw trial on the device -> responses (n, L) on the device.  video: (Hv, Wv, L) uint8 or fp32, behaviour and
+        pupil centre: (2, L) fp32.  The clips of every window batch are assembled straight from the raw arrays
+        (dwn_assemble_clips = StackInputsProcessor + window gather); the padded (5, L, H, W) tensor is never built."""
+        dev = video.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        if video.dtype not in (torch.uint8, torch.float32):
+            video = video.float()
+        video = video.contiguous()
+        behavior = behavior.float().contiguous()
+        pupil_center = pupil_center.float().contiguous()
+        Hv, Wv, L = video.shape
+        W, H = self.inputs_processor.size
+        fill = float(self.inputs_processor.pad_fill_value)
+        size, step = self.frame_stack_size, self.frame_stack_step
+        behind, ahead = self.indexes_generator.behind, self.indexes_generator.ahead
+        n_out = self.model.nn_module.cfg["readout_outputs"][mouse_index]
+        nwin = max(L - ahead - behind, 0)
+        preds = torch.empty((max(nwin, 1), n_out, size), dtype=torch.float32, device=dev)
+        vcode = 2 if video.dtype == torch.uint8 else 0
+        for w0 in range(0, nwin, self.window_batch):
+            nw = min(self.window_batch, nwin - w0)
+            clips = torch.empty((nw, 5, size, H, W), dtype=torch.float32, device=dev)
+            call("dwn_assemble_clips", video, vcode, behavior, pupil_center, clips, L, Hv, Wv, H, W, fill, size, step,
+                 behind + w0, nw, st)
+            preds[w0:w0 + nw] = self.model.predict(clips, mouse_index)
+        blend = torch.as_tensor(np.asarray(self.blend_weights, dtype=np.float32), device=dev)
+        out = torch.empty((n_out, L), dtype=torch.float32, device=dev)
+        call("dwn_window_blend", preds, blend, out, n_out, L, size, step, 0, nwin, n_out * size, st)
+        return out
+
+    @torch.no_grad()
     def predict_trial(self, video: np.ndarray, behavior: np.ndarray, pupil_center: np.ndarray,
                       mouse_index: int) -> np.ndarray:
-        inputs = self.inputs_processor(video, behavior, pupil_center).to(self.model.device)
-        assert constants.num_neurons[mouse_index] == self.model.nn_module.cfg["readout_outputs"][mouse_index] or True
-        return self.predict_trial_device(inputs, mouse_index).cpu().numpy()
+        # upload the raw arrays (uint8 video: ~36x fewer bytes than the padded fp32 stack) and assemble on the device;
+        # position == "last" is asserted in __init__, so every window ends at its own frame
+        dev = self.model.device
+        if video.dtype != np.uint8:
+            video = video.astype(np.float32, copy=False)
+        out = self.predict_trial_raw_device(torch.from_numpy(np.ascontiguousarray(video)).to(dev),
+                                            torch.from_numpy(np.ascontiguousarray(behavior, dtype=np.float32)).to(dev),
+                                            torch.from_numpy(np.ascontiguousarray(pupil_center, dtype=np.float32)).to(dev),
+                                            mouse_index)
+        return out.cpu().numpy()

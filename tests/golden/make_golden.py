@@ -72,9 +72,32 @@ def install_argus_stub():
     argus.engine, argus.loss, argus.utils, argus.callbacks, argus.metrics = engine, loss, utils, cb, metrics
 
 
+def gen_corr_metric():
+    """metrics.py:34-74 run by the real reference class on the batches above."""
+    from tests.shapes import corr_step_outputs
+    RM = importlib.import_module("src.metrics")
+    steps = corr_step_outputs()
+    metric = RM.CorrelationMetric()
+    metric.reset()
+    for s in steps:
+        metric.update(s)
+    res = metric.compute()
+    per_neuron = {}
+    for m in metric.predictions:
+        t = np.concatenate(metric.targets[m], axis=0)
+        p = np.concatenate(metric.predictions[m], axis=0)
+        per_neuron[int(m)] = torch.from_numpy(RM.corr(p, t, axis=0).astype(np.float64))
+    torch.save({"mice_corr": {int(k): float(v) for k, v in res.items()}, "per_neuron": per_neuron},
+               OUT / "corr_metric.pt")
+    print("corr_metric.pt:", {int(k): float(v) for k, v in res.items()})
+
+
 def main():
     install_argus_stub()
     sys.path.insert(0, str(REF))
+    if "--only-corr" in sys.argv:
+        gen_corr_metric()
+        return
     R = importlib.import_module("src.models.dwiseneuro")
     RL = importlib.import_module("src.losses")
     RU = importlib.import_module("src.utils")
@@ -245,6 +268,7 @@ def main():
     torch.save({"video": torch.from_numpy(video), "behavior": torch.from_numpy(beh), "pupil": torch.from_numpy(pup),
                 "stacked_checksum": float(stacked.double().sum()), "stacked_slice": stacked[:, 5, 10:54:7, ::9].clone(),
                 "responses": res, "n_out": n_out}, OUT / "predictor_blend.pt")
+    gen_corr_metric()
     print("golden fixtures written to", OUT)
     for f in sorted(OUT.glob("*")):
         print(f"  {f.name:32s} {f.stat().st_size / 1024:8.1f} KB")

@@ -124,3 +124,14 @@ def test_predictor_blend_and_inputs(golden_dir):
         torch.testing.assert_close(r, g["responses"][blend], rtol=1e-6, atol=1e-6)
     with pytest.raises(ValueError):
         O.predict_trial(fake, stacked, n_out, 16, 2, "cosine")
+
+
+def test_correlation_metric(golden_dir):
+    """oracle.correlation_metric == the reference's CorrelationMetric (metrics.py:34-74) on the shared batches."""
+    from tests.shapes import corr_step_outputs
+    g = torch.load(golden_dir / "corr_metric.pt", weights_only=False)
+    r = O.correlation_metric(corr_step_outputs())
+    assert set(r["mice_corr"]) == set(g["mice_corr"]) == {0, 2}  # mouse 1 never had a sample
+    for m, v in g["mice_corr"].items():
+        assert abs(r["mice_corr"][m] - v) < 1e-6
+        assert float((torch.from_numpy(r["per_neuron"][m]) - g["per_neuron"][m]).abs().max()) < 2e-6

@@ -396,3 +396,110 @@ def test_full_size_properties(dev):
     gmax = max(float(g.abs().max()) for g in outs[0][2].values())
     assert all(bool(torch.isfinite(g).all()) for g in outs[0][2].values())
     assert float(outs[0][2]["core.blocks.5.conv_pwl.1.bn.bias"].abs().max()) < 1e-2 * gmax
+
+
+def test_correlation_metric_device(dev, golden_dir):
+    """streaming device accumulators == the reference's concatenate-and-corr (golden) == oracle."""
+    from sensorium_b200.metrics import CorrelationMetric, corr
+    from tests.shapes import corr_step_outputs
+    g = torch.load(golden_dir / "corr_metric.pt", weights_only=False)
+    steps = corr_step_outputs()
+    metric = CorrelationMetric()
+    for s in steps:
+        tg, w = s["target"]
+        metric.update({"prediction": [p.to(dev) for p in s["prediction"]], "target": ([t.to(dev) for t in tg], w.to(dev))})
+    res = metric.compute()
+    assert set(res) == {0, 2}
+    ref = O.correlation_metric(steps)
+    per = metric.compute_per_neuron()
+    for m in res:
+        assert abs(float(res[m]) - g["mice_corr"][m]) < 2e-6
+        assert abs(float(res[m]) - ref["mice_corr"][m]) < 2e-6
+        assert float((per[m][0].cpu().double() - g["per_neuron"][m]).abs().max()) < 5e-6
+    # update() after reset() starts from zero; 2-D (B, n) predictions take the T = 1 path of the reference
+    metric.reset()
+    p2 = torch.rand(6, 9, device=dev)
+    t2 = p2 * 2 + torch.rand(6, 9, device=dev)
+    w2 = torch.ones(6, 1, device=dev)
+    metric.update({"prediction": [p2], "target": ([t2], w2)})
+    want = corr(p2.cpu().numpy(), t2.cpu().numpy(), axis=0).mean()
+    assert abs(float(metric.compute()[0]) - float(want)) < 2e-6
+    state = type("S", (), {"phase": "val", "metrics": {}})()
+    metric.epoch_complete(state)
+    assert set(state.metrics) == {"val_corr_mouse_0", "val_corr"}
+
+
+@pytest.mark.parametrize("vdtype", [torch.uint8, torch.float32])
+@pytest.mark.parametrize("Hv,Wv,fill", [(36, 64, 0.0), (21, 30, 7.5)])
+def test_assemble_clips_bit_exact(dev, vdtype, Hv, Wv, fill):
+    """clips built on the device from the raw trial == StackInputsProcessor (inputs.py:22-36) followed
+    by the window gather of predict_trial (predictors.py:42-51), bit for bit."""
+    from sensorium_b200._lib import call
+    L, size, step = 53, 16, 2
+    behind = (size - 1) * step
+    g = torch.Generator().manual_seed(5)
+    video = torch.randint(0, 256, (Hv, Wv, L), generator=g).to(vdtype)
+    beh, pup = torch.rand(2, L, generator=g) * 9, torch.rand(2, L, generator=g) * 30
+    stacked = O.stack_inputs(video, beh, pup, size=(64, 64), fill=fill)            # (5, L, 64, 64)
+    last0, nw = behind + 3, 11
+    want = torch.stack([stacked[:, O.make_window_indexes(last0 + i, size, step, "last")] for i in range(nw)])
+    clips = torch.empty((nw, 5, size, 64, 64), dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    call("dwn_assemble_clips", video.to(dev), 2 if vdtype == torch.uint8 else 0, beh.to(dev), pup.to(dev), clips, L, Hv, Wv,
+         64, 64, fill, size, step, last0, nw, st)
+    assert torch.equal(clips.cpu(), want)
+    with pytest.raises(Exception):  # window range outside the trial is refused, not clamped
+        call("dwn_assemble_clips", video.to(dev), 0, beh.to(dev), pup.to(dev), clips, L, Hv, Wv, 64, 64, fill, size, step,
+             L - 2, nw, st)
+
+
+def test_distillation_train_step_vs_oracle(dev):
+    """C4 (argus_models.py:31-71): frozen teacher (wider expansion) fills the targets / weights of the mice a sample does
+    not belong to, then the student trains on all mice.  Loss, the mutated targets and the student gradients must match
+    the oracle (teacher forward in eval mode -> distill_fill -> student forward -> MicePoissonLoss)."""
+    from sensorium_b200 import DwiseNeuro
+    from sensorium_b200.argus_models import MouseModel
+    from sensorium_b200.utils import init_weights
+    kw_s = dict(TINY_KW, drop_path_rate=0.0, drop_rate=0.0, expansion_ratio=2)
+    kw_t = dict(TINY_KW, drop_path_rate=0.0, drop_rate=0.0, expansion_ratio=3)
+    params = {"nn_module": ("dwiseneuro", {"readout_outputs": TINY_OUTS, **kw_s}), "loss": ("mice_poisson", {}),
+              "optimizer": ("AdamW", {"lr": 1e-3, "weight_decay": 0.05}), "device": "cuda:0", "amp": False, "iter_size": 1}
+    torch.manual_seed(0)
+    m = MouseModel(params)
+    init_weights(m.nn_module)
+    m.nn_module.precision = "fp32"
+    torch.manual_seed(1)
+    teacher = DwiseNeuro(readout_outputs=TINY_OUTS, **kw_t).to(dev)
+    init_weights(teacher)
+    teacher.precision = "fp32"
+    teacher.eval()
+    m.distill_model, m.distill_ratio = teacher, 0.36
+    B = 5
+    x = O.synthetic_clip(B, 16, 32, seed=3)
+    tg, w = O.synthetic_targets(B, TINY_OUTS, 16, seed=4)
+    sd_s = {k: v.detach().clone() for k, v in m.nn_module.state_dict().items()}
+    sd_t = {k: v.detach().clone() for k, v in teacher.state_dict().items()}
+    names = [k for k, _ in m.nn_module.named_parameters()]
+    for k in names:
+        sd_s[k].requires_grad_(True)
+    # ---- oracle
+    cfg_s, cfg_t = O.make_cfg(TINY_OUTS, **kw_s), O.make_cfg(TINY_OUTS, **kw_t)
+    xd = x.to(dev)
+    tg_o, w_o = [t.clone().to(dev) for t in tg], w.clone().to(dev)
+    with torch.no_grad():
+        t_out = O.dwiseneuro_forward(xd, sd_t, cfg_t, None, False)
+    O.distill_fill(tg_o, w_o, t_out, 0.36)
+    ref_loss = O.mice_poisson_loss(O.dwiseneuro_forward(xd, sd_s, cfg_s, None, True), tg_o, w_o)
+    ref_loss.backward()
+    # ---- product: the public train step on a HOST batch
+    out = m.train_step((x, ([t.clone() for t in tg], w.clone())), None)
+    assert abs(out["loss"] - float(ref_loss)) / abs(float(ref_loss)) < FP32_TOL
+    got_t, got_w = out["target"]
+    assert rel(got_w, w_o) < 1e-6
+    for a, b in zip(got_t, tg_o):
+        assert rel(a, b) < FP32_TOL
+    gmax = max(float(sd_s[k].grad.abs().max()) for k in names)
+    for k, p in m.nn_module.named_parameters():
+        assert p.grad is not None, k  # with distillation every mouse is live for every sample
+        err = float((p.grad - sd_s[k].grad).abs().max())
+        assert err <= FP32_TOL * max(float(sd_s[k].grad.abs().max()), 3e-3 * gmax) + 1e-6 * gmax, (k, err)
