@@ -102,7 +102,7 @@ class MouseModel(_Base):
     def train_step(self, batch, state: State) -> dict:
         self.train()
         self.optimizer.zero_grad()
-        loss_value = 0
+        chunk_losses = []
         for i, chunk_batch in enumerate(deep_chunk(batch, self.iter_size)):
             host_w = chunk_batch[1][1]
             distill = self.distill_model is not None and self.distill_ratio
@@ -118,11 +118,16 @@ class MouseModel(_Base):
                 loss = self.loss(prediction, target)
                 loss = loss / self.iter_size
             self.grad_scaler.scale(loss).backward()
-            loss_value += loss.item()
+            chunk_losses.append(loss.detach())
         self.grad_scaler.step(self.optimizer)
         self.grad_scaler.update()
         if self.model_ema is not None:
             self.model_ema.update(self.nn_module)
+        # the reference reads loss.item() right after each backward (argus_models.py:56); reading the same values once
+        # the optimizer and EMA kernels are enqueued returns the same number without idling the GPU at the sync
+        loss_value = 0
+        for l in chunk_losses:
+            loss_value += l.item()
         prediction = deep_detach(prediction)
         target = deep_detach(target)
         prediction = self.prediction_transform(prediction)

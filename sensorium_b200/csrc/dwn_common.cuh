@@ -242,6 +242,48 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// Column sums of two quantities of a partial table for the BN finalize kernels.  Block = 1024 threads =
+// 8 channels x 128 row slices (grid = C/8 CTAs: enough CTAs and few enough rows per thread that the whole table is
+// fetched in one or two rounds of independent loads).  Fixed summation order: deterministic.
+// partial row p, quantity q, channel cp lives at partial[(p*NQ + q)*Cp + cp].  Returns the sums in threads 0..7
+// (channel blockIdx.x*8 + threadIdx.x); sm must hold 2*32*8 doubles.
+__device__ __forceinline__ void finalize_colsum2(const float* __restrict__ partial, int P, int NQ, int qa, int qb, int Cp,
+                                                 int cp, bool valid, double* sm, double& out_a, double& out_b) {
+  const int sl = threadIdx.x >> 3, cl = threadIdx.x & 7, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    const long rs = (long)NQ * Cp;
+    const float* pa = partial + (long)qa * Cp + cp;
+    const float* pb = partial + (long)qb * Cp + cp;
+    int p = sl;
+    for (; p + 384 < P; p += 512) {  // four independent partial rows in flight per quantity
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a4[u] += pa[(long)(p + 128 * u) * rs];
+        b4[u] += pb[(long)(p + 128 * u) * rs];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)  // tail: at most three rows are left
+      if (p + 128 * u < P) {
+        a4[u] += pa[(long)(p + 128 * u) * rs];
+        b4[u] += pb[(long)(p + 128 * u) * rs];
+      }
+  }
+  double a = ((double)a4[0] + (double)a4[1]) + ((double)a4[2] + (double)a4[3]);
+  double b = ((double)b4[0] + (double)b4[1]) + ((double)b4[2] + (double)b4[3]);
+#pragma unroll
+  for (int o = 8; o < 32; o <<= 1) {  // the 4 slices of a warp that share a channel
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane < 8) { sm[warp * 8 + cl] = a; sm[256 + warp * 8 + cl] = b; }
+  __syncthreads();
+  out_a = 0; out_b = 0;
+  if (threadIdx.x < 8)
+    for (int w = 0; w < 32; ++w) { out_a += sm[w * 8 + threadIdx.x]; out_b += sm[256 + w * 8 + threadIdx.x]; }
+}
+
 // BN coefficient table layout: coef[4][C] = {scale, shift, mean, rstd}
 //   y = scale*x + shift ;  xhat = (x-mean)*rstd
 // BN backward coefficient table: bcoef[2][C] = {c1 = sum(dy)/N, c2 = sum(dy*xhat)/N}

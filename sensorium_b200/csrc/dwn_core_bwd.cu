@@ -22,33 +22,11 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
                                                               double count, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta, float* __restrict__ bcoef,
                                                               int C) {
-  __shared__ float s0[32][33], s1[32][33];
-  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  float a = 0.f, b = 0.f;
-  if (c < C) {
-    float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
-    int p = sl;
-    for (; p + 96 < P; p += 128) {  // four independent partial rows in flight
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        a4[u] += partial[((long)(p + 32 * u) * NQ + q0) * C + c];
-        b4[u] += partial[((long)(p + 32 * u) * NQ + q0 + 1) * C + c];
-      }
-    }
-    for (; p < P; p += 32) {
-      a4[0] += partial[((long)p * NQ + q0) * C + c];
-      b4[0] += partial[((long)p * NQ + q0 + 1) * C + c];
-    }
-    a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
-    b = (b4[0] + b4[1]) + (b4[2] + b4[3]);
-  }
-  s0[sl][cl] = a;
-  s1[sl][cl] = b;
-  __syncthreads();
-  if (sl != 0 || c >= C) return;
-  double da = 0, db = 0;
-  for (int i = 0; i < 32; ++i) { da += (double)s0[i][cl]; db += (double)s1[i][cl]; }
+  __shared__ double s_red[512];
+  const int c = blockIdx.x * 8 + (threadIdx.x & 7);  // block = (8 channels, 128 row slices), see finalize_colsum2
+  double da, db;
+  finalize_colsum2(partial, P, NQ, q0, q0 + 1, C, c < C ? c : 0, c < C, s_red, da, db);
+  if (threadIdx.x >= 8 || c >= C) return;
   if (dbeta) dbeta[c] = (float)da;
   if (dgamma) dgamma[c] = (float)db;
   bcoef[c] = (float)(da / count);
@@ -57,7 +35,7 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
 
 extern "C" int dwn_bn_bwd_finalize(const float* partial, int P, int NQ, int q0, double count, float* dgamma,
                                    float* dbeta, float* bcoef, int C, void* stream) {
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(partial, P, NQ, q0, count, dgamma, dbeta,
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 1024, 0, (cudaStream_t)stream>>>(partial, P, NQ, q0, count, dgamma, dbeta,
                                                                            bcoef, C);
   DWN_LAUNCH_CHECK();
   return 0;
@@ -1299,9 +1277,14 @@ extern "C" int dwn_bn_bwd_apply(void* g, const void* x, const float* coef, const
 // out[i] = sum_z partial[z][i]   (split-K / per-CTA partial reductions); optional transposed channel layout
 __global__ void reduce_rows_kernel(const float* __restrict__ partial, int Z, long n, float* __restrict__ out) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int z = 0; z < Z; ++z) s += partial[(long)z * n + i];
-    out[i] = s;
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent rows in flight
+    int z = 0;
+    for (; z + 3 < Z; z += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s4[u] += partial[(long)(z + u) * n + i];
+    }
+    for (; z < Z; ++z) s4[0] += partial[(long)z * n + i];
+    out[i] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
   }
 }
 extern "C" int dwn_reduce_rows(const float* partial, int Z, long n, float* out, void* stream) {
@@ -1319,8 +1302,16 @@ __global__ void __launch_bounds__(1024) dw_wgrad_finalize_kernel(const float* __
   const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl, k = blockIdx.y;
   float a = 0.f;
-  if (c < C)
-    for (int p = sl; p < P; p += 32) a += partial[((long)p * NQ + q0 + k) * C + c];
+  if (c < C) {
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent partial rows in flight
+    int p = sl;
+    for (; p + 96 < P; p += 128) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a4[u] += partial[((long)(p + 32 * u) * NQ + q0 + k) * C + c];
+    }
+    for (; p < P; p += 32) a4[0] += partial[((long)p * NQ + q0 + k) * C + c];
+    a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+  }
   s0[sl][cl] = a;
   __syncthreads();
   if (sl != 0 || c >= C) return;

@@ -133,39 +133,16 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
                                                           long long* __restrict__ nbt, float momentum, float eps,
                                                           int training, float* __restrict__ coef, int C, int Cp,
                                                           int NQ) {
-  // block = (32 channels, 32 slices); partial has Cp channels, channel c reads column c % Cp
-  // (cyclic channel tiling of the shortcut, dwiseneuro.py:130-132)
-  __shared__ double s_sum[32][33], s_sq[32][33];
-  int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  int c = blockIdx.x * 32 + cl;
+  // block = (8 channels, 128 row slices), see finalize_colsum2; partial has Cp channels, channel c reads column
+  // c % Cp (cyclic channel tiling of the shortcut, dwiseneuro.py:130-132)
+  __shared__ double s_red[512];
+  const int c = blockIdx.x * 8 + (threadIdx.x & 7);
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt && training) *nbt += 1;
   double mean, var;
   if (training) {
-    double s = 0, q = 0;
-    if (c < C) {
-      const int cp = c % Cp;
-      float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
-      int p = sl;
-      for (; p + 96 < P; p += 128) {  // four independent partial rows in flight
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          s4[u] += partial[((long)(p + 32 * u) * NQ) * Cp + cp];
-          q4[u] += partial[((long)(p + 32 * u) * NQ + 1) * Cp + cp];
-        }
-      }
-      for (; p < P; p += 32) {
-        s4[0] += partial[((long)p * NQ) * Cp + cp];
-        q4[0] += partial[((long)p * NQ + 1) * Cp + cp];
-      }
-      s = ((double)s4[0] + (double)s4[1]) + ((double)s4[2] + (double)s4[3]);
-      q = ((double)q4[0] + (double)q4[1]) + ((double)q4[2] + (double)q4[3]);
-    }
-    s_sum[sl][cl] = s;
-    s_sq[sl][cl] = q;
-    __syncthreads();
-    if (sl != 0 || c >= C) return;
-    s = 0; q = 0;
-    for (int i = 0; i < 32; ++i) { s += s_sum[i][cl]; q += s_sq[i][cl]; }
+    double s, q;
+    finalize_colsum2(partial, P, NQ, 0, 1, Cp, c < C ? c % Cp : 0, c < C, s_red, s, q);
+    if (threadIdx.x >= 8 || c >= C) return;
     mean = s / count;
     var = q / count - mean * mean;
     if (var < 0) var = 0;
@@ -175,7 +152,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
       rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
     }
   } else {
-    if (sl != 0 || c >= C) return;
+    if (threadIdx.x >= 8 || c >= C) return;
     mean = rmean[c];
     var = rvar[c];
   }
@@ -190,7 +167,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
 extern "C" int dwn_bn_finalize(const float* partial, int P, double count, const float* gamma, const float* beta,
                                float* rmean, float* rvar, long long* nbt, float momentum, float eps, int training,
                                float* coef, int C, int Cp, int NQ, void* stream) {
-  bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(partial, P, count, gamma, beta, rmean, rvar, nbt,
+  bn_finalize_kernel<<<(C + 7) / 8, 1024, 0, (cudaStream_t)stream>>>(partial, P, count, gamma, beta, rmean, rvar, nbt,
                                                                       momentum, eps, training, coef, C, Cp > 0 ? Cp : C,
                                                                       NQ > 0 ? NQ : 2);
   DWN_LAUNCH_CHECK();
