@@ -117,6 +117,26 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
   return d;
 }
 
+// one warp stores its staged 32-row x 64-column sub-tile (row pitch 272 bytes) with coalesced 16-byte vectors
+template <int ESZ>
+__device__ __forceinline__ void store_subtile(const uint8_t* my_stage, uint8_t* dbase, long ldd, int row0, int n0, int c0,
+                                              int lane, int m_limit, int block_n, int n_limit) {
+  constexpr int NVEC = 64 * ESZ / 16;  // 16-byte vectors per row segment: 8 (bf16) or 16 (fp32)
+  constexpr int EPV = 16 / ESZ;        // elements per vector
+  constexpr int RSTEP = 32 / NVEC;     // rows covered by one warp-wide store: 4 or 2
+  const int j = lane % NVEC, r0 = lane / NVEC;
+  const int lcol = c0 + j * EPV, gcol = n0 + lcol;
+  if (lcol >= block_n || gcol >= n_limit) return;
+  const uint8_t* src = my_stage + r0 * 272 + j * 16;
+  uint8_t* dst = dbase + ((size_t)(row0 + r0) * ldd + gcol) * ESZ;
+  const size_t dstep = (size_t)RSTEP * ldd * ESZ;
+  const int rows = m_limit - row0 - r0;  // store while it * RSTEP < rows
+#pragma unroll
+  for (int it = 0; it < NVEC; ++it) {
+    if (it * RSTEP < rows) *reinterpret_cast<uint4*>(dst + it * dstep) = *reinterpret_cast<const uint4*>(src + it * RSTEP * 272);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05 GEMM kernel
 // ------------------------------------------------------------------------------------------------
@@ -127,6 +147,7 @@ constexpr int GT_STAGE_PITCH = 272;                    // staging row pitch (byt
 constexpr int GT_EPI_WARPS = 8;   // two warps per TMEM lane quarter, interleaved over 64-column sub-tiles
 constexpr int GT_STAGING_BYTES = GT_EPI_WARPS * 32 * GT_STAGE_PITCH;
 constexpr int GT_THREADS = 64 + 32 * GT_EPI_WARPS;   // warp0 TMA, warp1 MMA, warps2.. epilogue
+static_assert(GT_STAGE_PITCH == 272, "store_subtile() assumes the 272-byte staging pitch");
 
 struct GemmTcParams {
   int K, K2, block_n, b_bytes, stages;  // K2 > 0: D += A2 (MxK2) * B2^T (second operand pair, same majors)
@@ -254,7 +275,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int n0 = n_blk * p.block_n;
       if (e.epi == 0) {
         const int esz = e.d_bf16 ? 2 : 4;
-        const int nvec = 64 * esz / 16;  // 16-byte vectors per 64-column row segment
         uint8_t* dbase = (uint8_t*)e.D + (size_t)z * e.d_zstride * esz;
         for (int c0 = hsel * 64; c0 < p.block_n; c0 += 128) {
           if (n0 + c0 >= e.n_limit) break;
@@ -286,17 +306,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
           }
           __syncwarp();
-          const int epv = 16 / esz;  // elements per 16-byte vector
-          for (int i = lane; i < 32 * nvec; i += 32) {
-            const int r = i / nvec, j = i % nvec;
-            const int grow = row0 + r;
-            const int lcol = c0 + j * epv;
-            const int gcol = n0 + lcol;
-            if (grow < e.m_limit && lcol < p.block_n && gcol < e.n_limit) {
-              uint4 w = *reinterpret_cast<const uint4*>(my_stage + r * GT_STAGE_PITCH + j * 16);
-              *reinterpret_cast<uint4*>(dbase + ((size_t)grow * e.ldd + gcol) * esz) = w;
-            }
-          }
+          // coalesced 16-byte stores: a lane keeps its column vector j and walks down the rows, so the column
+          // predicate and the address are loop invariants plus a constant row step (no per-store div/mod)
+          if (e.d_bf16) store_subtile<2>(my_stage, dbase, e.ldd, row0, n0, c0, lane, e.m_limit, p.block_n, e.n_limit);
+          else store_subtile<4>(my_stage, dbase, e.ldd, row0, n0, c0, lane, e.m_limit, p.block_n, e.n_limit);
           __syncwarp();
         }
       } else {

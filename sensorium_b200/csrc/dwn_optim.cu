@@ -41,14 +41,51 @@ __global__ void __launch_bounds__(256) adamw_kernel(const DwnTensorEntry* __rest
   const float step_size = lr / s_c[0];
   const float bc2s = s_c[1];
   const float decay = 1.0f - lr * wd;
-  for (long i = off + threadIdx.x; i < end; i += blockDim.x) {
-    const float g = e.g[i];
-    float p = e.p[i] * decay;
-    float m = e.m[i];
+  auto update = [&](float g, float& p, float& m, float& v) {
+    p = p * decay;
     m = m + (g - m) * (1.0f - b1);
-    const float v = e.v[i] * b2 + (1.0f - b2) * g * g;
+    v = v * b2 + (1.0f - b2) * g * g;
     const float denom = sqrtf(v) / bc2s + eps;
     p = p - step_size * (m / denom);
+  };
+  // 16-byte vector body (chunks start at multiples of 16384 elements, so only the base pointers decide the alignment;
+  // gradients that are views into a coalesced data-parallel bucket may be misaligned and take the scalar path)
+  const uintptr_t bits = (uintptr_t)e.p | (uintptr_t)e.g | (uintptr_t)e.m | (uintptr_t)e.v | (uintptr_t)e.ema |
+                         ((uintptr_t)e.shadow << 1);
+  const long nvec = (bits & 15) == 0 ? (end - off) / 4 : 0;
+#pragma unroll 2
+  for (long q = threadIdx.x; q < nvec; q += blockDim.x) {
+    const long i = off + 4 * q;
+    const float4 g4 = *reinterpret_cast<const float4*>(e.g + i);
+    float4 p4 = *reinterpret_cast<const float4*>(e.p + i);
+    float4 m4 = *reinterpret_cast<const float4*>(e.m + i);
+    float4 v4 = *reinterpret_cast<const float4*>(e.v + i);
+    update(g4.x, p4.x, m4.x, v4.x);
+    update(g4.y, p4.y, m4.y, v4.y);
+    update(g4.z, p4.z, m4.z, v4.z);
+    update(g4.w, p4.w, m4.w, v4.w);
+    *reinterpret_cast<float4*>(e.p + i) = p4;
+    *reinterpret_cast<float4*>(e.m + i) = m4;
+    *reinterpret_cast<float4*>(e.v + i) = v4;
+    if (e.shadow) {
+      uint2 sh;
+      sh.x = pack_bf16x2(p4.x, p4.y);
+      sh.y = pack_bf16x2(p4.z, p4.w);
+      *reinterpret_cast<uint2*>(e.shadow + i) = sh;
+    }
+    if (e.ema) {
+      float4 a4 = *reinterpret_cast<const float4*>(e.ema + i);
+      a4.x = ema_decay * a4.x + (1.0f - ema_decay) * p4.x;
+      a4.y = ema_decay * a4.y + (1.0f - ema_decay) * p4.y;
+      a4.z = ema_decay * a4.z + (1.0f - ema_decay) * p4.z;
+      a4.w = ema_decay * a4.w + (1.0f - ema_decay) * p4.w;
+      *reinterpret_cast<float4*>(e.ema + i) = a4;
+    }
+  }
+  for (long i = off + 4 * nvec + threadIdx.x; i < end; i += blockDim.x) {
+    const float g = e.g[i];
+    float p = e.p[i], m = e.m[i], v = e.v[i];
+    update(g, p, m, v);
     e.p[i] = p;
     e.m[i] = m;
     e.v[i] = v;
@@ -82,7 +119,20 @@ __global__ void __launch_bounds__(256) ema_kernel(const DwnTensorEntry* __restri
     for (long i = off + threadIdx.x; i < end; i += blockDim.x)
       em[i] = (long long)(decay * (float)em[i] + (1.0f - decay) * (float)mo[i]);
   } else {
-    for (long i = off + threadIdx.x; i < end; i += blockDim.x) e.ema[i] = decay * e.ema[i] + (1.0f - decay) * e.p[i];
+    const long nvec = ((((uintptr_t)e.ema | (uintptr_t)e.p) & 15) == 0) ? (end - off) / 4 : 0;
+#pragma unroll 2
+    for (long q = threadIdx.x; q < nvec; q += blockDim.x) {
+      const long i = off + 4 * q;
+      float4 a4 = *reinterpret_cast<const float4*>(e.ema + i);
+      const float4 p4 = *reinterpret_cast<const float4*>(e.p + i);
+      a4.x = decay * a4.x + (1.0f - decay) * p4.x;
+      a4.y = decay * a4.y + (1.0f - decay) * p4.y;
+      a4.z = decay * a4.z + (1.0f - decay) * p4.z;
+      a4.w = decay * a4.w + (1.0f - decay) * p4.w;
+      *reinterpret_cast<float4*>(e.ema + i) = a4;
+    }
+    for (long i = off + 4 * nvec + threadIdx.x; i < end; i += blockDim.x)
+      e.ema[i] = decay * e.ema[i] + (1.0f - decay) * e.p[i];
   }
 }
 
