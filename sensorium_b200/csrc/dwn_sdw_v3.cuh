@@ -84,9 +84,10 @@ sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, c
   const int chunk = blockIdx.x % nchunks, worker = blockIdx.x / nchunks, nworkers = gridDim.x / nchunks;
   const int c0 = chunk * CC;
   constexpr int NVEC = NR * (256 / RPI);  // 16-byte vectors per raw tile (W*cvn == 256/RPI)
+  // three raw tiles in a ring: while tile k is activated and convolved, tiles k+1 and k+2 are in flight
+  // (two buffers kept only ~40 KB in flight per SM, below what the HBM latency needs)
   bf16* raw0 = reinterpret_cast<bf16*>(smem_v3);
-  bf16* raw1 = raw0 + (size_t)NVEC * 8;
-  float* act = reinterpret_cast<float*>(raw1 + (size_t)NVEC * 8);
+  float* act = reinterpret_cast<float*>(raw0 + (size_t)3 * NVEC * 8);
   float* sco = act + (size_t)NR * WP * CC;  // [2][CC] BN1+SiLU constants (kept out of the register file)
   // ---- loop-invariant coordinates of this thread inside one pass
   constexpr int vpr = 256 / RPI;                   // vectors per tile row
@@ -138,12 +139,14 @@ sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, c
   int t = worker, k = 0;
   if (t < ntiles) issue(t, raw0);
   cp_async_commit();
-  for (; t < ntiles; t += nworkers, ++k) {
-    const bf16* cur = (k & 1) ? raw1 : raw0;
-    bf16* nxt = (k & 1) ? raw0 : raw1;
-    if (t + nworkers < ntiles) issue(t + nworkers, nxt);
+  if (t + nworkers < ntiles) issue(t + nworkers, raw0 + (size_t)NVEC * 8);
+  cp_async_commit();
+  for (; t < ntiles; t += nworkers, k = (k == 2 ? 0 : k + 1)) {
+    const bf16* cur = raw0 + (size_t)k * NVEC * 8;
+    bf16* nxt = raw0 + (size_t)(k == 0 ? 2 : k - 1) * NVEC * 8;  // buffer (k+2)%3: its tile was consumed last iteration
+    if (t + 2 * nworkers < ntiles) issue(t + 2 * nworkers, nxt);
     cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<2>();
     __syncthreads();  // raw tile landed for everybody; everybody is done with the previous act tile
     const int p = t >> nbsh, ho0 = (t & nbm) * THO;
     const int hi0 = ho0 * S - 1;
