@@ -119,3 +119,25 @@ def test_argus_shim_checkpoint_roundtrip(tmp_path):
         assert torch.equal(a, b)
     parts = argus_shim.deep_chunk((torch.arange(8), ([torch.arange(8), torch.arange(8)], torch.arange(8))), 2)
     assert len(parts) == 2 and parts[1][1][0][1].tolist() == [4, 5, 6, 7]
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every ctypes signature string in sensorium_b200/_lib.py has the arity and the scalar/pointer kinds of the C
+    prototype in include/dwn_b200.h (a mismatch would silently corrupt the stack of a kernel launch)."""
+    import re
+    from pathlib import Path
+    header = (Path(__file__).resolve().parents[1] / "include" / "dwn_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = dict(re.findall(r"\bint\s+(dwn_\w+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    kinds = {"p": "pointer", "i": "int", "l": "long", "f": "float", "d": "double"}
+    for name, sig in _lib.SIGNATURES.items():
+        assert name in protos, name
+        params = [a.strip() for a in protos[name].split(",") if a.strip() and a.strip() != "void"]
+        assert len(params) == len(sig), (name, len(params), len(sig))
+        for ch, par in zip(sig, params):
+            if "*" in par:
+                want = "pointer"
+            else:
+                ty = par.rsplit(" ", 1)[0].replace("const", "").strip()
+                want = {"int": "int", "long": "long", "float": "float", "double": "double"}.get(ty)
+            assert want == kinds[ch], (name, par, ch)
