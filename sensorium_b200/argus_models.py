@@ -67,7 +67,7 @@ class MouseModel(_Base):
         Returns (input, target, ready) where ready() makes the compute stream wait for the side-stream copies."""
         x, target = chunk_batch
         dev = self.device
-        if dev.type != "cuda" or not torch.is_tensor(x):
+        if dev.type != "cuda" or not torch.is_tensor(x) or x.is_cuda:  # already resident (DevicePrefetcher) or no GPU
             inp, tgt = deep_to(chunk_batch, dev, non_blocking=True)
             return inp, tgt, (lambda: None)
         main = torch.cuda.current_stream(dev)
@@ -106,8 +106,13 @@ class MouseModel(_Base):
         for i, chunk_batch in enumerate(deep_chunk(batch, self.iter_size)):
             host_w = chunk_batch[1][1]
             distill = self.distill_model is not None and self.distill_ratio
-            if isinstance(self.loss, MicePoissonLoss) and not host_w.is_cuda:
-                self.loss.set_live_hint([True] * host_w.shape[1] if distill else (host_w != 0).any(0).tolist())
+            if isinstance(self.loss, MicePoissonLoss):
+                if distill:
+                    self.loss.set_live_hint([True] * host_w.shape[1])
+                elif not host_w.is_cuda:
+                    self.loss.set_live_hint((host_w != 0).any(0).tolist())
+                elif hasattr(host_w, "_dwn_live"):  # batch prefetched by sensorium_b200.prefetch.DevicePrefetcher
+                    self.loss.set_live_hint(host_w._dwn_live)
             input, target, ready = self._to_device_overlapped(chunk_batch)
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
                 if self.distill_model is not None and self.distill_ratio:

@@ -503,3 +503,40 @@ def test_distillation_train_step_vs_oracle(dev):
         assert p.grad is not None, k  # with distillation every mouse is live for every sample
         err = float((p.grad - sd_s[k].grad).abs().max())
         assert err <= FP32_TOL * max(float(sd_s[k].grad.abs().max()), 3e-3 * gmax) + 1e-6 * gmax, (k, err)
+
+
+def test_device_prefetcher_is_transparent(dev):
+    """Batches that arrive through DevicePrefetcher (copied one ahead on a side stream) train bit-identically to host
+    batches handed to train_step directly, including a batch in which a mouse has no sample."""
+    from sensorium_b200.argus_models import MouseModel
+    from sensorium_b200.prefetch import DevicePrefetcher
+    from sensorium_b200.utils import init_weights
+
+    def batches():
+        out = []
+        for i in range(3):
+            x = O.synthetic_clip(4, 16, 32, seed=10 + i)
+            tg, w = O.synthetic_targets(4, TINY_OUTS, 16, seed=20 + i)
+            if i == 1:
+                w[:, 1] = 0
+                w[:, 0] = 1
+            out.append((x.pin_memory(), ([t.pin_memory() for t in tg], w.pin_memory())))
+        return out
+
+    def run(prefetch):
+        params = {"nn_module": ("dwiseneuro", {"readout_outputs": TINY_OUTS, **TINY_KW}), "loss": ("mice_poisson", {}),
+                  "optimizer": ("AdamW", {"lr": 2e-3, "weight_decay": 0.05}), "device": "cuda:0", "amp": True,
+                  "iter_size": 1}
+        torch.manual_seed(0)
+        m = MouseModel(params)
+        init_weights(m.nn_module)
+        torch.manual_seed(3)
+        src = DevicePrefetcher(batches(), dev) if prefetch else batches()
+        losses = [m.train_step(b, None)["loss"] for b in src]
+        return m, losses
+
+    m1, l1 = run(False)
+    m2, l2 = run(True)
+    assert l1 == l2
+    for a, b in zip(m1.nn_module.state_dict().values(), m2.nn_module.state_dict().values()):
+        assert torch.equal(a, b)
