@@ -88,12 +88,12 @@ __global__ void block_bwd_reduce_kernel(const float* __restrict__ dO, const T* _
   for (int m = m0; m < Mo; m += mstep, ++kk) {
     const int b = dt.div(dh.div(dw.div(m)));
     float g[4], y[4], x[4];
+    const float d = dp ? dp[b] : 1.0f;  // before the wait: its latency overlaps the pipeline wait
     cp_async_wait<DEPTH - 1>();
     quad_from(*pipe.slot(kk, 0), g);
     pipe_read_quad<T>(pipe.slot(kk, 1), y);
     quad_from(*pipe.slot(kk, 2), x);
     issue(kk + DEPTH);
-    const float d = dp ? dp[b] : 1.0f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float d4 = d * g[j];

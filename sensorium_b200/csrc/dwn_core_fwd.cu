@@ -199,33 +199,47 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
   }
   float st[3][4] = {};
   const int plane = Tn * H * W, M = B * plane;
-  // (a per-thread cp.async prefetch of the CIN input scalars was tried here and was 2x slower: the 16 threads of a
-  // pixel share the same scalars, which plain loads broadcast but LDGSTS copies once per thread)
-#pragma unroll 2
-  for (int m = blockIdx.x * ln + lane; m < M; m += gridDim.x * ln) {
-    const int b = dplane.div(m), pos = m - b * plane;
-    const int wq = dw.mod(pos), hq = dh.mod(dw.div(pos)), tq = dh.div(dw.div(pos));
-    float xv[CIN];
+  // Four positions per trip: all 4*CIN input scalars are loaded before the first use, so a trip costs one load latency
+  // instead of four (the kernel is write-bound but was limited by these dependent loads).  A per-thread cp.async
+  // prefetch was tried and was 2x slower: the 16 threads of a position share the scalars, which plain loads
+  // broadcast but LDGSTS copies once per thread.
+  const int m0 = blockIdx.x * ln + lane, mstep = gridDim.x * ln;
+  for (int mb = m0; mb < M; mb += 4 * mstep) {
+    float xv[4][CIN];
 #pragma unroll
-    for (int k = 0; k < CIN; ++k) xv[k] = __ldg(&x[((long)b * CIN + k) * plane + pos]);
-    float pt[4], ph[4], pw[4], o[4];
-    ldq(pe_t + tq * C0 + c, pt);
-    ldq(pe_h + hq * C0 + c, ph);
-    ldq(pe_w + wq * C0 + c, pw);
+    for (int u = 0; u < 4; ++u) {
+      const int m = mb + u * mstep;
+      if (m < M) {
+        const int b = dplane.div(m), pos = m - b * plane;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = 0.f;
-#pragma unroll
-      for (int k = 0; k < CIN; ++k) a = fmaf(wr[j][k], xv[k], a);
-      o[j] = fmaf(a, sc[j], sh[j]) + ((pt[j] + ph[j]) + pw[j]);
+        for (int k = 0; k < CIN; ++k) xv[u][k] = __ldg(&x[((long)b * CIN + k) * plane + pos]);
+      }
     }
-    stq(out + (long)m * C0 + c, o);
-    if (out_bf) stq(out_bf + (long)m * C0 + c, o);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) st[2][j] += o[j];
-    if (partial && (hq % next_stride == 0) && (wq % next_stride == 0)) {
+    for (int u = 0; u < 4; ++u) {
+      const int m = mb + u * mstep;
+      if (m >= M) break;
+      const int b = dplane.div(m), pos = m - b * plane;
+      const int wq = dw.mod(pos), hq = dh.mod(dw.div(pos)), tq = dh.div(dw.div(pos));
+      float pt[4], ph[4], pw[4], o[4];
+      ldq(pe_t + tq * C0 + c, pt);
+      ldq(pe_h + hq * C0 + c, ph);
+      ldq(pe_w + wq * C0 + c, pw);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { st[0][j] += o[j]; st[1][j] = fmaf(o[j], o[j], st[1][j]); }
+      for (int j = 0; j < 4; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < CIN; ++k) a = fmaf(wr[j][k], xv[u][k], a);
+        o[j] = fmaf(a, sc[j], sh[j]) + ((pt[j] + ph[j]) + pw[j]);
+      }
+      stq(out + (long)m * C0 + c, o);
+      if (out_bf) stq(out_bf + (long)m * C0 + c, o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st[2][j] += o[j];
+      if (partial && (hq % next_stride == 0) && (wq % next_stride == 0)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { st[0][j] += o[j]; st[1][j] = fmaf(o[j], o[j], st[1][j]); }
+      }
     }
   }
   if (partial)  // [P][3][C0]: strided sum / sumsq (next shortcut BN) and the full column sum (Gram statistics)
@@ -835,21 +849,21 @@ __global__ void block_out_kernel(const T* __restrict__ y_raw, const float* __res
     const int hq = dh.mod(r1), bt = dh.div(r1);
     const int tq = dt.mod(bt), b = dt.div(bt);
     float y[4], x[4], o[4];
+    // the small cached loads (drop-path scale, position-encoding rows) are issued before the pipeline wait: the asm
+    // barrier of cp.async.wait_group keeps the compiler from hoisting them, and after it their latency is exposed
+    const float d = dp ? dp[b] : 1.0f;
+    float pt[4] = {0.f, 0.f, 0.f, 0.f}, ph[4] = {0.f, 0.f, 0.f, 0.f}, pw[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pe_t) {
+      ldq(pe_t + tq * Co + c, pt);
+      ldq(pe_h + hq * Co + c, ph);
+      ldq(pe_w + wq * Co + c, pw);
+    }
     cp_async_wait<DEPTH - 1>();
     pipe_read_quad<T>(pipe.slot(kk, 0), y);
     quad_from(*pipe.slot(kk, 1), x);
     issue(kk + DEPTH);
-    const float d = dp ? dp[b] : 1.0f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = d * fmaf(y[j], s4[j], h4[j]) + fmaf(x[j], ss[j], hs[j]);
-    if (pe_t) {
-      float pt[4], ph[4], pw[4];
-      ldq(pe_t + tq * Co + c, pt);
-      ldq(pe_h + hq * Co + c, ph);
-      ldq(pe_w + wq * Co + c, pw);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] += (pt[j] + ph[j]) + pw[j];
-    }
+    for (int j = 0; j < 4; ++j) o[j] = d * fmaf(y[j], s4[j], h4[j]) + fmaf(x[j], ss[j], hs[j]) + ((pt[j] + ph[j]) + pw[j]);
     stq(out + (long)m * Co + c, o);
     if (out_bf) stq(out_bf + (long)m * Co + c, o);
 #pragma unroll
