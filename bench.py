@@ -33,6 +33,19 @@ BATCH, FRAMES, SIZE = 32, 16, 64
 LR, WD, EMA_DECAY = 3e-4 * 32 / 4, 0.05, 0.999
 
 
+# Rank 0 must print exactly ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner
+# with printf when NCCL_DEBUG is VERSION or WARN), so file descriptor 1 is pointed at stderr for the whole run and the
+# JSON line goes to a private duplicate of the original stdout.
+_JSON_OUT = sys.stdout
+
+
+def _claim_stdout():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def synthetic_batch(batch: int, seed: int):
     """clip (B,5,16,64,64) + one labelled mouse per sample, dense zero targets elsewhere."""
     from oracle.dwiseneuro_oracle import synthetic_clip, synthetic_targets
@@ -118,7 +131,7 @@ def run_reference(args):
                          "sample": f"{args.steps} train steps of batch {sample_b} (oracle port, fp32, torch CPU)"},
         "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def main():
@@ -135,6 +148,7 @@ def main():
                          "(for `ncu --profile-from-start off`: the launch list of exactly one step)")
     ap.add_argument("--seed-base", type=int, default=1000, help="rank r draws its synthetic batch with seed base+r")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -150,8 +164,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: NCCL's version banner / debug lines go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     args.warmup = max(args.warmup, 3)
 
@@ -314,7 +326,7 @@ def main():
         line["cpu_baseline"] = {"value": val, "unit": "clips/s", "cores": threads, "kind": "port",
                                 "sample": "2 train steps of batch 8 after 1 warm-up (oracle port of the reference: "
                                           "fp32 fwd + MicePoissonLoss + bwd + torch AdamW on the host CPU)"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
