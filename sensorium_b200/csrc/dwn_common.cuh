@@ -30,7 +30,9 @@ template <> struct VecT<float> { static constexpr int V = 4; };
 template <> struct VecT<bf16> { static constexpr int V = 8; };
 
 __device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& lo, float& hi) {
-  lo = __uint_as_float(u << 16);
+  // PRMT + LOP3, both on the ALU pipe: `u << 16` is compiled to IMAD.SHL / IMAD.U32, which competes with the FFMA2s of
+  // the stencil kernels for the FMA pipe (13 % of sdw_bwd's dynamic instructions were IMADs)
+  lo = __uint_as_float(__byte_perm(u, 0u, 0x1044));
   hi = __uint_as_float(u & 0xffff0000u);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
