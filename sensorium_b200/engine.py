@@ -18,7 +18,6 @@ from typing import Dict, List, Optional
 
 import torch
 
-from . import _lib
 from ._lib import call, gemm
 
 F32, BF16 = 0, 1

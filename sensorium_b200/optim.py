@@ -4,7 +4,7 @@ skipped entirely (no decay, step not advanced).  One kernel launch updates all p
 the bf16 weight shadows used by the tcgen05 GEMMs."""
 from __future__ import annotations
 
-from typing import Iterable, Optional
+from typing import Iterable
 
 import torch
 

@@ -11,7 +11,6 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from . import constants
 from ._lib import call
 from .indexes import IndexesGenerator
 from .inputs import get_inputs_processor
