@@ -65,3 +65,34 @@ class ModelEma(nn.Module):
     def set(self, model):
         for e, m in zip(self.ema.state_dict().values(), model.state_dict().values()):
             e.copy_(m)
+
+
+def save_ema_model(model, file_path) -> None:
+    """Write the EMA weights in the argus checkpoint layout the reference's ``EmaCheckpoint.save_model`` produces
+    (ema.py:61-73): ``{'model_name', 'params', 'nn_state_dict'}`` with the state dict on the CPU, so that
+    ``argus.load_model`` / ``Predictor`` load it like any other checkpoint."""
+    nn_module = model.model_ema.ema
+    if isinstance(nn_module, (nn.DataParallel, nn.parallel.DistributedDataParallel)):
+        nn_module = nn_module.module
+    torch.save({"model_name": model.__class__.__name__, "params": model.params,
+                "nn_state_dict": {k: v.detach().to("cpu") for k, v in nn_module.state_dict().items()}}, file_path)
+
+
+try:  # pragma: no cover - pytorch-argus is absent in this image
+    from argus.callbacks import Checkpoint as _CheckpointBase  # type: ignore
+except ImportError:
+    class _CheckpointBase:
+        """Minimal stand-in for argus.callbacks.Checkpoint: only the hook the reference overrides."""
+
+        def save_model(self, state, file_path):
+            state.model.save(file_path)
+
+
+class EmaCheckpoint(_CheckpointBase):
+    """argus Checkpoint callback that stores the EMA weights instead of the raw ones (ema.py:61-73)."""
+
+    def save_model(self, state, file_path):
+        save_ema_model(state.model, file_path)
+        logger = getattr(state, "logger", None)
+        if logger is not None:
+            logger.info(f"Model saved to '{file_path}'")

@@ -141,3 +141,32 @@ def test_ctypes_signatures_match_the_header():
                 ty = par.rsplit(" ", 1)[0].replace("const", "").strip()
                 want = {"int": "int", "long": "long", "float": "float", "double": "double"}.get(ty)
             assert want == kinds[ch], (name, par, ch)
+
+
+def test_ema_checkpoint_layout(tmp_path):
+    """EmaCheckpoint.save_model writes the EMA weights in the argus layout of the reference (ema.py:61-73) and the file
+    loads back through load_model (what Predictor does, predictors.py:25)."""
+    from copy import deepcopy
+    from types import SimpleNamespace
+    from sensorium_b200 import argus_shim
+    from sensorium_b200.argus_models import MouseModel
+    from sensorium_b200.ema import EmaCheckpoint
+    params = {"nn_module": ("dwiseneuro", {"readout_outputs": (5, 4), "core_features": (8,), "spatial_strides": (1,),
+                                           "expansion_ratio": 2, "se_reduce_ratio": 4, "cortex_features": (8,)}),
+              "loss": ("mice_poisson", {}), "optimizer": ("AdamW", {"lr": 1e-3}), "device": "cpu", "amp": True,
+              "iter_size": 1}
+    m = MouseModel(params)
+    ema_module = deepcopy(m.nn_module)
+    with torch.no_grad():
+        for p in ema_module.parameters():
+            p.add_(1.0)  # the EMA copy differs from the raw weights
+    m.model_ema = SimpleNamespace(ema=ema_module)
+    path = tmp_path / "model-001-0.250000.pth"
+    EmaCheckpoint().save_model(SimpleNamespace(model=m), path)
+    state = torch.load(path, weights_only=False)
+    assert set(state) == {"model_name", "params", "nn_state_dict"} and state["model_name"] == "MouseModel"
+    assert all(v.device.type == "cpu" for v in state["nn_state_dict"].values())
+    loaded = argus_shim.load_model(path, device="cpu", optimizer=None, loss=None)
+    for (k, a), b in zip(ema_module.state_dict().items(), loaded.nn_module.state_dict().values()):
+        assert torch.equal(a, b), k
+    assert not torch.equal(loaded.nn_module.core.stem[0].weight, m.nn_module.core.stem[0].weight)
