@@ -183,6 +183,14 @@ int dwn_corr_update(const float* pred, const float* target, const float* weights
                     double* acc, double* cnt, void* stream);
 int dwn_corr_finalize(const double* acc, const double* cnt, int n, double eps, float* out, float* out_mean,
                       void* stream);
+/* CutMix (mixers.py:52-67) and batch collation (datasets.py:172-187) on the device.
+ * x1, x2, out: (B, planes, H, W) fp32; boxes: (B, 4) int32 {bbx1, bby1, bbx2, bby2} exactly as rand_bbox returns them
+ * (bbx runs over H, bby over W, like the reference's slicing); lam: (B) fp32. */
+int dwn_cutmix(const float* x1, const float* x2, const int* boxes, float* out, int B, long planes, int H, int W,
+               void* stream);
+int dwn_lerp_rows(const float* t1, const float* t2, const float* lam, float* out, int B, long row, void* stream);
+int dwn_scatter_mouse_targets(const float* compact, const int* ids, int m, float* out, int B, int n_m, int n_max, int T,
+                              void* stream);
 int dwn_window_blend(const float* pred, const float* blend, float* out, int n_out, int L, int size, int step, int win0,
                      int nwin, long pred_wstride, void* stream);
 

@@ -77,6 +77,9 @@ SIGNATURES = {
     "dwn_assemble_clips": "pippp" + "iiiii" + "f" + "iiii" + "p",
     "dwn_corr_update": "ppp" + "iiii" + "pp" + "p",
     "dwn_corr_finalize": "pp" + "i" + "d" + "pp" + "p",
+    "dwn_cutmix": "pppp" + "i" + "l" + "ii" + "p",
+    "dwn_lerp_rows": "pppp" + "i" + "l" + "p",
+    "dwn_scatter_mouse_targets": "pp" + "i" + "p" + "iiii" + "p",
     # conv_pw algebra (Gram statistics, BN1-backward folded into GEMMs)
     "dwn_partial_colsum": "piiiipp",
     "dwn_pw_stats": "pppdpppppffpiip",

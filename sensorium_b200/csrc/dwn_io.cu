@@ -138,3 +138,84 @@ extern "C" int dwn_corr_finalize(const double* acc, const double* cnt, int n, do
   DWN_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// f3: CutMix and batch collation on the device (mixers.py:52-67, datasets.py:124-129, 172-187).
+//   dwn_cutmix     : out[b] = x1[b] with the box rows [bbx1, bbx2) x columns [bby1, bby2) of the last two dims taken from
+//                    x2[b] (the reference indexes `inputs[..., bbx1:bbx2, bby1:bby2]`, i.e. "x" runs over H); a sample
+//                    whose box is empty (or that the host decided not to mix) is a plain copy of x1.
+//   dwn_lerp_rows  : out[b] = (1 - lam[b]) * t1[b] + lam[b] * t2[b]          (target mixing, one row per sample)
+//   dwn_scatter_mouse_targets : out_m[b][j][t] = ids[b] == m ? compact[b][j][t] : 0   (per-mouse target tensors from
+//                    the compact per-sample targets, so the host never uploads the ~90 % zeros of the collated batch)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void cutmix_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const int* __restrict__ boxes,
+                              float* __restrict__ out, long planes, int H, int W, long total4) {
+  const int W4 = W >> 2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    const int w0 = (int)(i % W4) * 4;
+    long r = i / W4;
+    const int h = (int)(r % H);
+    const long b = r / H / planes;
+    const int hx1 = boxes[b * 4], wy1 = boxes[b * 4 + 1], hx2 = boxes[b * 4 + 2], wy2 = boxes[b * 4 + 3];
+    float4 a = *reinterpret_cast<const float4*>(x1 + i * 4);
+    if (h >= hx1 && h < hx2 && w0 + 3 >= wy1 && w0 < wy2) {
+      const float4 c = *reinterpret_cast<const float4*>(x2 + i * 4);
+      if (w0 >= wy1 && w0 < wy2) a.x = c.x;
+      if (w0 + 1 >= wy1 && w0 + 1 < wy2) a.y = c.y;
+      if (w0 + 2 >= wy1 && w0 + 2 < wy2) a.z = c.z;
+      if (w0 + 3 >= wy1 && w0 + 3 < wy2) a.w = c.w;
+    }
+    *reinterpret_cast<float4*>(out + i * 4) = a;
+  }
+}
+
+// x1, x2, out: (B, planes, H, W) fp32 (planes = C*T); boxes: (B, 4) int32 {bbx1, bby1, bbx2, bby2} as rand_bbox returns
+extern "C" int dwn_cutmix(const float* x1, const float* x2, const int* boxes, float* out, int B, long planes, int H, int W,
+                          void* stream) {
+  DWN_REQUIRE(W % 4 == 0, "dwn_cutmix: W %% 4 != 0");
+  const long total4 = (long)B * planes * H * (W / 4);
+  if (total4 == 0) return 0;
+  int gx = (int)((total4 + 255) / 256);
+  if (gx > 148 * 16) gx = 148 * 16;
+  cutmix_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(x1, x2, boxes, out, planes, H, W, total4);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void lerp_rows_kernel(const float* __restrict__ t1, const float* __restrict__ t2, const float* __restrict__ lam,
+                                 float* __restrict__ out, long row, long total) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const float l = lam[i / row];
+    out[i] = (1.0f - l) * t1[i] + l * t2[i];
+  }
+}
+extern "C" int dwn_lerp_rows(const float* t1, const float* t2, const float* lam, float* out, int B, long row, void* stream) {
+  const long total = (long)B * row;
+  if (total == 0) return 0;
+  int gx = (int)((total + 255) / 256);
+  if (gx > 148 * 16) gx = 148 * 16;
+  lerp_rows_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(t1, t2, lam, out, row, total);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void scatter_mouse_targets_kernel(const float* __restrict__ compact, const int* __restrict__ ids, int m,
+                                             float* __restrict__ out, int n_m, int n_max, int T, long total) {
+  const long row = (long)n_m * T;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / row, r = i - b * row;
+    out[i] = ids[b] == m ? compact[b * (long)n_max * T + r] : 0.0f;
+  }
+}
+// compact: (B, n_max, T) fp32, rows beyond the sample's own neuron count are ignored; out: (B, n_m, T)
+extern "C" int dwn_scatter_mouse_targets(const float* compact, const int* ids, int m, float* out, int B, int n_m, int n_max,
+                                         int T, void* stream) {
+  DWN_REQUIRE(n_m <= n_max, "dwn_scatter_mouse_targets: n_m %d > n_max %d", n_m, n_max);
+  const long total = (long)B * n_m * T;
+  if (total == 0) return 0;
+  int gx = (int)((total + 255) / 256);
+  if (gx > 148 * 16) gx = 148 * 16;
+  scatter_mouse_targets_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(compact, ids, m, out, n_m, n_max, T, total);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}

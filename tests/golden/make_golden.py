@@ -92,11 +92,34 @@ def gen_corr_metric():
     print("corr_metric.pt:", {int(k): float(v) for k, v in res.items()})
 
 
+def gen_cutmix():
+    """mixers.py:10-67 run by the real reference CutMix (numpy RNG seeded) on six small sample pairs."""
+    RX = importlib.import_module("src.mixers")
+    g = torch.Generator().manual_seed(21)
+    mixer = RX.CutMix(alpha=1.0, prob=0.5)
+    np.random.seed(1234)
+    recs = []
+    for i in range(6):
+        s1 = (torch.rand(2, 3, 16, 16, generator=g), torch.rand(7, 3, generator=g))
+        s2 = (torch.rand(2, 3, 16, 16, generator=g), torch.rand(7, 3, generator=g))
+        used = mixer.use()
+        if used:
+            out = mixer(s1, s2)
+        else:
+            out = s1
+        recs.append({"s1": s1, "s2": s2, "used": bool(used), "out": (out[0].clone(), out[1].clone())})
+    torch.save({"seed": 1234, "alpha": 1.0, "prob": 0.5, "records": recs}, OUT / "cutmix.pt")
+    print("cutmix.pt: used =", [r["used"] for r in recs])
+
+
 def main():
     install_argus_stub()
     sys.path.insert(0, str(REF))
     if "--only-corr" in sys.argv:
         gen_corr_metric()
+        return
+    if "--only-cutmix" in sys.argv:
+        gen_cutmix()
         return
     R = importlib.import_module("src.models.dwiseneuro")
     RL = importlib.import_module("src.losses")
@@ -269,6 +292,7 @@ def main():
                 "stacked_checksum": float(stacked.double().sum()), "stacked_slice": stacked[:, 5, 10:54:7, ::9].clone(),
                 "responses": res, "n_out": n_out}, OUT / "predictor_blend.pt")
     gen_corr_metric()
+    gen_cutmix()
     print("golden fixtures written to", OUT)
     for f in sorted(OUT.glob("*")):
         print(f"  {f.name:32s} {f.stat().st_size / 1024:8.1f} KB")

@@ -135,3 +135,24 @@ def test_correlation_metric(golden_dir):
     for m, v in g["mice_corr"].items():
         assert abs(r["mice_corr"][m] - v) < 1e-6
         assert float((torch.from_numpy(r["per_neuron"][m]) - g["per_neuron"][m]).abs().max()) < 2e-6
+
+
+def test_cutmix_host_decisions_and_oracle(golden_dir):
+    """The host side of the device CutMix draws the reference's random numbers in the reference's order
+    (mixers.py:13-14, 36-49, 57-66): same seed -> same samples mixed, same boxes, and oracle.cutmix reproduces the
+    reference's mixed sample bit for bit."""
+    import numpy as np
+    from sensorium_b200.mixers import DeviceCutMix
+    g = torch.load(golden_dir / "cutmix.pt", weights_only=False)
+    recs = g["records"]
+    np.random.seed(g["seed"])
+    boxes, lams = DeviceCutMix(g["alpha"], g["prob"]).sample(len(recs), 16, 16)
+    for b, r in enumerate(recs):
+        used = bool(boxes[b].any()) or float(lams[b]) != 0.0
+        if not r["used"]:
+            assert not used and torch.equal(r["out"][0], r["s1"][0])
+            continue
+        x, t = O.cutmix(r["s1"][0], r["s1"][1], r["s2"][0], r["s2"][1], boxes[b])
+        assert torch.equal(x, r["out"][0]) and torch.equal(t, r["out"][1])
+        area = (boxes[b][2] - boxes[b][0]) * (boxes[b][3] - boxes[b][1]) / 256.0
+        assert abs(float(lams[b]) - area) < 1e-7

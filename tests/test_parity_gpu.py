@@ -540,3 +540,36 @@ def test_device_prefetcher_is_transparent(dev):
     assert l1 == l2
     for a, b in zip(m1.nn_module.state_dict().values(), m2.nn_module.state_dict().values()):
         assert torch.equal(a, b)
+
+
+def test_cutmix_and_collation_on_device(dev, golden_dir):
+    """box copy + target lerp on a device batch == the reference CutMix per sample (golden), and the
+    compact targets scattered into per-mouse tensors == construct_mice_sample + default collate (oracle)."""
+    from sensorium_b200.mixers import DeviceCutMix, collate_on_device
+    g = torch.load(golden_dir / "cutmix.pt", weights_only=False)
+    recs = g["records"]
+    np.random.seed(g["seed"])
+    mixer = DeviceCutMix(g["alpha"], g["prob"])
+    x1 = torch.stack([r["s1"][0] for r in recs]).to(dev)
+    x2 = torch.stack([r["s2"][0] for r in recs]).to(dev)
+    t1 = torch.stack([r["s1"][1] for r in recs]).to(dev)
+    t2 = torch.stack([r["s2"][1] for r in recs]).to(dev)
+    x, t = mixer(x1, x2, t1, t2)
+    assert sum(r["used"] for r in recs) >= 2
+    for b, r in enumerate(recs):
+        assert torch.equal(x[b].cpu(), r["out"][0]), b        # pure copies: bit-exact
+        assert rel(t[b].cpu(), r["out"][1]) < 1e-6, b
+    # collation: ragged neuron counts, a mouse without a sample
+    outs = (5, 9, 4)
+    ids = torch.tensor([2, 0, 0, 2, 2])
+    gen = torch.Generator().manual_seed(8)
+    samples = [(int(m), torch.rand(outs[int(m)], 6, generator=gen)) for m in ids]
+    compact = torch.zeros(len(ids), max(outs), 6)
+    for b, (m, tt) in enumerate(samples):
+        compact[b, :tt.shape[0]] = tt
+        compact[b, tt.shape[0]:] = 123.0  # padding rows must never leak into the batch
+    want_t, want_w = O.collate_mice_batch(samples, outs)
+    got_t, got_w = collate_on_device(compact.to(dev), ids.to(dev), outs)
+    assert torch.equal(got_w.cpu(), want_w)
+    for a, b_ in zip(got_t, want_t):
+        assert torch.equal(a.cpu(), b_)
