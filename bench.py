@@ -46,6 +46,10 @@ def _claim_stdout():
     os.dup2(2, 1)
 
 
+WORKLOAD = ("DwiseNeuro true_batch_001 (expansion 7) full train step: fwd + MicePoissonLoss + bwd + AdamW + EMA, "
+            "all 10 readouts, batch 32 per GPU, clip 5x16x64x64")
+
+
 def synthetic_batch(batch: int, seed: int):
     """clip (B,5,16,64,64) + one labelled mouse per sample, dense zero targets elsewhere."""
     from oracle.dwiseneuro_oracle import synthetic_clip, synthetic_targets
@@ -125,8 +129,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DwiseNeuro true_batch_001 train step (fwd+Poisson loss+bwd+AdamW), all 10 readouts",
-                   "sample": f"batch {sample_b} per step on host CPU"},
+        "config": {"workload": WORKLOAD,
+                   "sample": f"batch {sample_b} per step on the host CPU (oracle port of the reference; EMA update not included)"},
         "cpu_baseline": {"value": val, "unit": "clips/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} train steps of batch {sample_b} (oracle port, fp32, torch CPU)"},
         "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -309,8 +313,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "DwiseNeuro true_batch_001 (expansion 7) full train step: fwd + MicePoissonLoss + bwd + "
-                               "AdamW + EMA, all 10 readouts, batch 32 per GPU, clip 5x16x64x64",
+        "config": {"workload": WORKLOAD,
                    "global_batch": BATCH * world, "parallelism": f"dp{world}", "weights": "random-init (init_weights)",
                    "l2": "working set per step (>15 GB of activations) exceeds the 126 MB L2"},
         "e2e": {"value": BATCH * world * args.e2e_steps / (e2e_ms * 1e-3), "unit": "clips/s",
