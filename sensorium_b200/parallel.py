@@ -107,3 +107,33 @@ class DataParallelGrads:
         pm = self._pm_dev
         one = torch.ones((), dtype=torch.int32, device=dev)
         self.active = torch.where(pm >= 0, self._flags[pm.clamp(min=0)], one).to(torch.int32).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Inference (C5): embarrassingly parallel — trials are sharded across ranks, every rank holds all models.
+# ---------------------------------------------------------------------------------------------------------------------
+def shard_trials(num_trials: int, rank: Optional[int] = None, world: Optional[int] = None) -> List[int]:
+    """Trial indices handled by ``rank``: round-robin, so that long and short trials spread evenly.  Without arguments
+    the rank / world size of the default process group are used (1 process: every trial)."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    return list(range(rank, num_trials, world))
+
+
+def predict_trials_sharded(predict_fn, trials, group=None) -> Dict[int, "torch.Tensor"]:
+    """Run ``predict_fn(trial) -> Tensor`` on this rank's shard of ``trials`` and gather every result on every rank
+    (no collective on the hot path; one ``all_gather_object`` of host arrays at the end).  Returns {trial index: result}."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = {i: predict_fn(trials[i]) for i in shard_trials(len(trials), rank, world)}
+    mine = {i: (v.detach().cpu() if torch.is_tensor(v) else v) for i, v in mine.items()}
+    if world == 1:
+        return mine
+    parts: List = [None] * world
+    dist.all_gather_object(parts, mine, group=group)
+    out: Dict[int, "torch.Tensor"] = {}
+    for p in parts:
+        out.update(p)
+    return out

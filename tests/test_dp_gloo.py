@@ -112,3 +112,36 @@ def test_readout_exchange_with_rank_dependent_mice():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res)
+
+
+def _worker_trials(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sensorium_b200.parallel import predict_trials_sharded, shard_trials
+    trials = [torch.full((3,), float(i)) for i in range(7)]  # 7 trials do not divide 2 ranks
+    seen = []
+
+    def predict(t):
+        seen.append(int(t[0]))
+        return t * 2 + rank * 0  # result must not depend on which rank computed it
+
+    res = predict_trials_sharded(predict, trials)
+    ok = sorted(res) == list(range(7)) and all(torch.equal(res[i], trials[i] * 2) for i in range(7))
+    ok &= seen == shard_trials(7, rank, world) == list(range(rank, 7, world))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_inference_trials_are_sharded_and_gathered():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_trials, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res)
+    from sensorium_b200.parallel import shard_trials
+    assert shard_trials(5, 0, 1) == [0, 1, 2, 3, 4] and shard_trials(3, 5, 8) == []
