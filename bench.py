@@ -182,7 +182,7 @@ def main():
     init_weights(model.nn_module)
     if world > 1:
         from sensorium_b200.parallel import DataParallelGrads
-        model.optimizer.active_provider = DataParallelGrads.attach(model.nn_module)
+        DataParallelGrads.attach(model.nn_module, model.optimizer)
     model.model_ema = ModelEma(model.nn_module, decay=EMA_DECAY)
 
     x, tg, w = synthetic_batch(BATCH, args.seed_base + rank)

@@ -1,7 +1,7 @@
 // Algebraic shortcuts around the point-wise expansion conv_pw (E = X W^T, dwiseneuro.py:90-93), bf16 pipeline.
 // Both use that E is linear in the block input X, whose Gram matrix Gx = X^T X (ci x ci) and column sums sx are
 // tiny compared with E (M x 7ci):
-//   forward : BatchNorm statistics of E without reading E:  mean_c = w_c.sx/M,  E[e^2]_c = w_c^T Gx w_c / M
+//   forward : BatchNorm statistics of E without reading E:  mean_c = w_c.sx/M,  var_c = w_c^T (Gx/M - mu mu^T) w_c
 //   backward: BN1 backward is affine, dE_raw = a*G - d*E - b (G = dE_pre), so
 //        dX = G (diag(a) W) - X (W^T diag(d) W) - (b^T W)          -> one dual-K GEMM, no pass over E
 //        dW = diag(a) (G^T X) - b (x) sx - diag(d) W Gx            -> the split-K wgrad GEMM on G + a tiny finalize
@@ -45,28 +45,34 @@ __global__ void __launch_bounds__(256) pw_stats_kernel(const float* __restrict__
   float* wc = sw + wid * ci;
   for (int k = lane; k < ci; k += 32) wc[k] = __bfloat162float(w[(long)c * ci + k]);
   __syncwarp();
+  const double inv_m = 1.0 / count;
   double m1 = 0;
   for (int k = lane; k < ci; k += 32) m1 += (double)wc[k] * (double)sx[k];
   m1 = warp_sum_d(m1);
-  // q = w^T G w: every lane accumulates its column slice of each row; four rows in flight to hide L2 latency
+  // var = w^T C w with the CENTRED second moment C = Gx/M - mu mu^T formed in fp64 entry by entry (never the
+  // difference of two large quadratic forms): every lane accumulates its column slice of each row, four rows in
+  // flight to hide L2 latency
   double q = 0;
   for (int j0 = 0; j0 < ci; j0 += 4) {
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    double muj[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) muj[jj] = j0 + jj < ci ? (double)sx[j0 + jj] * inv_m : 0.0;
     for (int k = lane; k < ci; k += 32) {
-      const float wk = wc[k];
+      const double wk = (double)wc[k], muk = (double)sx[k] * inv_m;
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj)
-        if (j0 + jj < ci) v[jj] = fmaf(gram[(long)(j0 + jj) * ci + k], wk, v[jj]);
+        if (j0 + jj < ci) v[jj] = fma((double)gram[(long)(j0 + jj) * ci + k] * inv_m - muj[jj] * muk, wk, v[jj]);
     }
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
-      if (j0 + jj < ci) q += (double)wc[j0 + jj] * (double)v[jj];
+      if (j0 + jj < ci) q += (double)wc[j0 + jj] * v[jj];
   }
   q = warp_sum_d(q);
   if (lane != 0) return;
-  const double mean = m1 / count;
-  double var = q / count - mean * mean;
-  if (var < 0) var = 0;
+  const double mean = m1 * inv_m;
+  double var = q;
+  if (var < 0) var = 0;  // guard only: C is positive semi-definite up to the rounding of Gx
   const double rstd = 1.0 / sqrt(var + (double)eps);
   const double g = gamma[c], b = beta[c];
   coef[c] = (float)(g * rstd);

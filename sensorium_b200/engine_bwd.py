@@ -48,7 +48,7 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
 
     dp = getattr(mod, "_dp", None)
     if dp is not None:
-        dp.begin([g is not None for g in grad_outs], dev)
+        dp.begin([g is not None for g in grad_outs], dev, mice=[r.m for r in sv.readouts])
 
     # ---------------- readouts -------------------------------------------------------------------
     K = cfg["cortex_features"][-1]
@@ -90,7 +90,7 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
     else:
         dX.zero_()
     if dp is not None:
-        dp.reduce_readouts(grads)
+        dp.reduce_readouts(grads, mice=[r.m for r in sv.readouts])
 
     # ---------------- cortex ---------------------------------------------------------------------
     dOut = dX

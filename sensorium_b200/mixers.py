@@ -2,9 +2,11 @@
 
 The reference mixes samples inside the DataLoader workers on the CPU (mixers.py:52-67 called from
 datasets.py:124-129) and collates ten mostly-zero target tensors per sample (datasets.py:172-187), so 1.5x samples are
-loaded and ~160 MB of zeros are uploaded per batch of 32.  Here the *decisions* stay on the host with the reference's
-exact numpy RNG call order (``use()`` -> ``np.random.random()``, then ``np.random.beta``, then the two
-``np.random.randint`` of ``rand_bbox``), and the *work* — box copy, target lerp, scatter of the compact per-sample
+loaded and ~160 MB of zeros are uploaded per batch of 32.  Here the *decisions* stay on the host and draw the same
+numpy calls per sample as ``CutMix`` itself (``use()`` -> ``np.random.random()``, then ``np.random.beta``, then the two
+``np.random.randint`` of ``rand_bbox``).  This reproduces ``CutMix.__call__`` under a given numpy state; it does NOT
+reproduce the reference *dataset's* stream, which reseeds numpy inside ``get_sample_tensors(index + 1)`` between
+``use()`` and the beta draw (datasets.py:124-129, utils.py:12-15).  The *work* — box copy, target lerp, scatter of the compact per-sample
 targets into the per-mouse tensors — is three kernels on the device batch."""
 from __future__ import annotations
 

@@ -98,4 +98,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 sh = getattr(p, "_dwn_shadow", None)
                 if sh is not None:
                     set_shadow(p, sh[1])
+        provider = getattr(self, "active_provider", None)
+        if provider is not None and hasattr(provider, "consumed"):
+            provider.consumed()
         return loss

@@ -42,20 +42,40 @@ class DataParallelGrads:
         return None  # copies of the module (ModelEma) are not trained: no exchange state to carry
 
     @staticmethod
-    def attach(mod, group=None) -> "DataParallelGrads":
-        """Broadcast rank 0's parameters / buffers and enable the overlapped gradient exchange."""
+    def attach(mod, optimizer, group=None) -> "DataParallelGrads":
+        """Broadcast rank 0's parameters / buffers, enable the overlapped gradient exchange and wire the optimizer's
+        skip flags.  ``optimizer`` is mandatory: without the flags a mouse that is absent on EVERY rank would receive a
+        zero (non-None) gradient and AdamW would still decay its readout, unlike the reference where ``grad is None``
+        skips the tensor.  Pass ``optimizer=False`` only when the caller consumes ``.active`` itself."""
+        if optimizer is None:
+            raise ValueError("DataParallelGrads.attach needs the optimizer (its has-grad flags come from the exchange)")
         with torch.no_grad():
             for t in mod.state_dict().values():
                 dist.broadcast(t, src=0, group=group)
         mod._dp = DataParallelGrads(mod, group)
+        if optimizer is not False:
+            optimizer.active_provider = mod._dp
         return mod._dp
 
     # called by engine_bwd.run_backward ---------------------------------------------------------------
-    def begin(self, local_live: List[bool], dev) -> None:
+    def begin(self, local_live: List[bool], dev, mice: Optional[List[int]] = None) -> None:
+        """``local_live[j]``: the j-th readout output of this forward has a gradient; ``mice[j]`` is its mouse index
+        (forward with ``index=m`` returns one output).  The flags always cover all ``n_mice``."""
         self.bytes_reduced = 0
-        flags = torch.tensor([1 if v else 0 for v in local_live], dtype=torch.int32).to(dev, non_blocking=True)
+        if mice is None:
+            mice = list(range(len(local_live)))
+        row = [0] * self.n_mice
+        for j, v in enumerate(local_live):
+            if v:
+                row[mice[j]] = 1
+        flags = torch.tensor(row, dtype=torch.int32).to(dev, non_blocking=True)
         self.works.append(dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group, async_op=True))
         self._flags = flags
+
+    def consumed(self) -> None:
+        """Called by the optimizer after a step: the next backward starts a new accumulation window."""
+        self._flags_acc = None
+        self.active = None
 
     def reduce(self, grads: Dict[torch.Tensor, torch.Tensor], keys) -> None:
         keys = [k for k in keys if grads.get(k) is not None]
@@ -77,11 +97,12 @@ class DataParallelGrads:
                 grads[k] = flat[off:off + n].view(grads[k].shape)
                 off += n
 
-    def reduce_readouts(self, grads: Dict[torch.Tensor, torch.Tensor]) -> None:
+    def reduce_readouts(self, grads: Dict[torch.Tensor, torch.Tensor], mice: Optional[List[int]] = None) -> None:
         """Exchange the readout gradients.  Every rank must issue the SAME sequence of collectives, so the
         readouts go in mouse order on all ranks; a mouse without a local sample contributes a zero bucket
-        (its has-grad flag was MAX-reduced in ``begin``)."""
-        for r in self.mod.readouts:
+        (its has-grad flag was MAX-reduced in ``begin``).  ``mice``: the mice of this forward (all, or [index])."""
+        readouts = self.mod.readouts if mice is None else [self.mod.readouts[m] for m in mice]
+        for r in readouts:
             ps = list(r.parameters())
             for p in ps:
                 if grads.get(p) is None:
@@ -106,7 +127,10 @@ class DataParallelGrads:
             self._pm_dev = self.param_mouse.to(dev)
         pm = self._pm_dev
         one = torch.ones((), dtype=torch.int32, device=dev)
-        self.active = torch.where(pm >= 0, self._flags[pm.clamp(min=0)], one).to(torch.int32).contiguous()
+        # iter_size > 1: a mouse is live for the optimizer step if ANY micro-batch since the last step had it
+        acc = getattr(self, "_flags_acc", None)
+        self._flags_acc = self._flags if acc is None else torch.maximum(acc, self._flags)
+        self.active = torch.where(pm >= 0, self._flags_acc[pm.clamp(min=0)], one).to(torch.int32).contiguous()
 
 
 # ---------------------------------------------------------------------------------------------------------------------

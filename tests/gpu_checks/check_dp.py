@@ -56,7 +56,7 @@ def main():
             for m, p in zip(mean, params):
                 if p.grad is not None:
                     m += p.grad / world
-        dp = DataParallelGrads.attach(net)
+        dp = DataParallelGrads.attach(net, False)
         for it in range(3):
             x, tg, w = shard(rank, dev)
             for p in params:

@@ -23,7 +23,7 @@ def _worker(rank, world, port, q):
     torch.manual_seed(rank)  # different weights per rank before attach
     net = DwiseNeuro(readout_outputs=(5, 4, 3), core_features=(8,), spatial_strides=(1,), expansion_ratio=2,
                      se_reduce_ratio=4, cortex_features=(8,), groups=2)
-    dp = DataParallelGrads.attach(net)
+    dp = DataParallelGrads.attach(net, False)
     w0 = net.core.stem[0].weight.detach().clone()
     params = list(net.parameters())
     g = torch.Generator().manual_seed(100 + rank)
@@ -73,7 +73,7 @@ def _worker_readouts(rank, world, port, q):
     from sensorium_b200.parallel import DataParallelGrads
     net = DwiseNeuro(readout_outputs=(5, 4, 3), core_features=(8,), spatial_strides=(1,), expansion_ratio=2,
                      se_reduce_ratio=4, cortex_features=(8,), groups=2)
-    dp = DataParallelGrads.attach(net)
+    dp = DataParallelGrads.attach(net, False)
     # the set of mice with a local sample differs per rank (the usual case at N=8 with 10 mice in a batch of 32):
     # rank 0 sees mice {0, 2}, rank 1 sees {1, 2}; the readout shapes differ, so any rank-dependent collective order
     # would pair tensors of different sizes
@@ -145,3 +145,57 @@ def test_inference_trials_are_sharded_and_gathered():
     assert all(ok for _, ok in res)
     from sensorium_b200.parallel import shard_trials
     assert shard_trials(5, 0, 1) == [0, 1, 2, 3, 4] and shard_trials(3, 5, 8) == []
+
+
+def _worker_flags(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sensorium_b200 import DwiseNeuro
+    from sensorium_b200.parallel import DataParallelGrads
+    net = DwiseNeuro(readout_outputs=(5, 4, 3), core_features=(8,), spatial_strides=(1,), expansion_ratio=2,
+                     se_reduce_ratio=4, cortex_features=(8,), groups=2)
+
+    class Opt:  # stand-in for FusedAdamW: attach() must wire the provider, step() calls consumed()
+        active_provider = None
+
+    opt = Opt()
+    dp = DataParallelGrads.attach(net, opt)
+    ok = opt.active_provider is dp
+    params = list(net.parameters())
+    idx = {id(p): i for i, p in enumerate(params)}
+    w = [idx[id(net.readouts[m].layer[1].weight)] for m in range(3)]
+    cpu = torch.device("cpu")
+    # iter_size 2: micro-batch 1 has mouse 0 (rank 0 only), micro-batch 2 has mouse 2 only; mouse 1 never
+    dp.begin([rank == 0, False, False], cpu)
+    dp.finish(cpu)
+    dp.begin([False, False, True], cpu)
+    dp.finish(cpu)
+    act = dp.active.tolist()
+    ok &= [act[i] for i in w] == [1, 0, 1]
+    dp.consumed()                                   # optimizer stepped: a new accumulation window starts
+    ok &= dp.active is None
+    # forward(x, index=1): one output whose mouse is 1 -> the flags still cover all three mice
+    dp.begin([True], cpu, mice=[1])
+    dp.finish(cpu)
+    act = dp.active.tolist()
+    ok &= [act[i] for i in w] == [0, 1, 0] and act[idx[id(net.core.stem[0].weight)]] == 1
+    try:
+        DataParallelGrads.attach(net, None)
+        ok = False
+    except ValueError:
+        pass
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_has_grad_flags_accumulate_over_micro_batches_and_cover_all_mice():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_flags, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res)
