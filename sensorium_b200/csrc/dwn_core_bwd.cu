@@ -1276,15 +1276,16 @@ extern "C" int dwn_bn_bwd_apply(void* g, const void* x, const float* coef, const
 
 // out[i] = sum_z partial[z][i]   (split-K / per-CTA partial reductions); optional transposed channel layout
 __global__ void reduce_rows_kernel(const float* __restrict__ partial, int Z, long n, float* __restrict__ out) {
+  // fp64 accumulation: the split-K partials of the Gram matrix / weight gradients are long sums of like-signed terms
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    float s4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent rows in flight
+    double s4[4] = {0.0, 0.0, 0.0, 0.0};  // four independent rows in flight
     int z = 0;
     for (; z + 3 < Z; z += 4) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) s4[u] += partial[(long)(z + u) * n + i];
+      for (int u = 0; u < 4; ++u) s4[u] += (double)partial[(long)(z + u) * n + i];
     }
-    for (; z < Z; ++z) s4[0] += partial[(long)z * n + i];
-    out[i] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    for (; z < Z; ++z) s4[0] += (double)partial[(long)z * n + i];
+    out[i] = (float)((s4[0] + s4[1]) + (s4[2] + s4[3]));
   }
 }
 extern "C" int dwn_reduce_rows(const float* partial, int Z, long n, float* out, void* stream) {

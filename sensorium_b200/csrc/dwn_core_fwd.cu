@@ -234,8 +234,10 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
       }
       stq(out + (long)m * C0 + c, o);
       if (out_bf) stq(out_bf + (long)m * C0 + c, o);
+      // Gram statistics describe E = Xb W^T, so the column sum is taken over the bf16-ROUNDED operand when there is one
+      // (inputs with many repeated values round coherently: mean(Xb) - mean(X) does not average out)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) st[2][j] += o[j];
+      for (int j = 0; j < 4; ++j) st[2][j] += out_bf ? __bfloat162float(__float2bfloat16_rn(o[j])) : o[j];
       if (partial && (hq % next_stride == 0) && (wq % next_stride == 0)) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { st[0][j] += o[j]; st[1][j] = fmaf(o[j], o[j], st[1][j]); }
@@ -867,7 +869,7 @@ __global__ void block_out_kernel(const T* __restrict__ y_raw, const float* __res
     stq(out + (long)m * Co + c, o);
     if (out_bf) stq(out_bf + (long)m * Co + c, o);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) st[2][j] += o[j];
+    for (int j = 0; j < 4; ++j) st[2][j] += out_bf ? __bfloat162float(__float2bfloat16_rn(o[j])) : o[j];  // see stem_fwd_kernel
     if (partial && (hq % next_stride == 0) && (wq % next_stride == 0)) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) { st[0][j] += o[j]; st[1][j] = fmaf(o[j], o[j], st[1][j]); }

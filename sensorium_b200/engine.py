@@ -138,8 +138,12 @@ def _split_k(rows: int, tiles: int) -> int:
 
 def _gram(xb, M, ci, st, dev, out=None):
     """Gx = X^T X (ci x ci, fp32) of the bf16 block input via a split-K (MN,MN) tcgen05 GEMM."""
-    tiles = math.ceil(ci / 128) * math.ceil(ci / 256)
-    zs = _split_k(M, tiles)
+    # short accumulation chains: the tensor core adds every K=16 slice into the fp32 TMEM accumulator with truncation,
+    # a bias that grows with the chain length (3.9e-4 on rstd at 16 k rows per split, measured); 2048 rows per split
+    # keep the Gram-derived statistics within 1e-4 of the direct ones at M = 2.1 M (tests/test_parity_fullsize_gpu.py)
+    zs = 1
+    while M % (zs * 2) == 0 and M // (zs * 2) >= 2048:
+        zs *= 2
     rows = M // zs
     part = _empty((zs, ci, ci), torch.float32, dev)
     gemm(st, dtype=BF16, A=xb, B=xb, a_mn=1, b_mn=1, lda=ci, ldb=ci, a_zstride=rows * ci, b_zstride=rows * ci,
