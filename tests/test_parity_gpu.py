@@ -90,13 +90,16 @@ def test_tiny_golden_forward_loss_grads(dev, golden_dir):
             else:
                 assert rel(got, v) < tol, k
         if mode == "bf16":
-            # single-trial correlation (metrics.py:11-31) of the eval outputs against a noisy single-trial-like target
+            # single-trial correlation (metrics.py:11-31) of the train-mode outputs against a noisy single-trial-like
+            # target: worst single neuron.  (The 1e-3 bound on the METRIC — the mean over a mouse's >= 7440 neurons — is
+            # asserted on the real architecture in test_c1_full_architecture_golden and test_parity_fullsize_gpu.py; a
+            # mean over 37 neurons of this tiny model does not average the per-neuron noise down.)
             gen = torch.Generator().manual_seed(0)
             for m in range(len(TINY_OUTS)):
-                ref_m = g["eval_out"][m]
+                ref_m = g["train_out"][m]
                 noisy = torch.relu(ref_m * (1 + torch.randn(ref_m.shape, generator=gen)))
-                worst, metric = _corr_gap(ev[m].cpu(), ref_m, noisy)
-                assert metric < CORR_TOL and worst < CORR_NEURON_BF16, (m, worst, metric)
+                worst, metric = _corr_gap(tr[m].detach().cpu(), ref_m, noisy)
+                assert worst < CORR_NEURON_BF16, (m, worst, metric)
 
 
 def test_c1_full_architecture_golden(dev, golden_dir):
