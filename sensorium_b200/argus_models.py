@@ -5,7 +5,9 @@ train_step / val_step / predict / add_distill_predictions contracts.  Difference
  * AMP uses bf16 autocast (BASELINE.json north_star) so no loss scaling is needed; ``grad_scaler`` is kept
    as a disabled GradScaler for attribute compatibility;
  * the distillation target fill is three kernel launches instead of a 288-iteration Python loop;
- * the set of live mice is taken from the host copy of the weights, so the loss needs no device sync.
+ * the set of live mice is taken from the host copy of the weights, so the loss needs no device sync;
+ * ``train_step`` also accepts the compact batch form ``(input, (responses (B, n_max, T), mouse_ids (B,)))`` and builds
+   the reference's dense per-mouse targets on the device.
 """
 from __future__ import annotations
 
@@ -26,7 +28,12 @@ from ._lib import call
 from .dwiseneuro import DwiseNeuro
 from .ema import ModelEma
 from .losses import MicePoissonLoss
+from .mixers import collate_on_device
 from .optim import FusedAdamW
+
+# live-mouse hints of device-resident batches (DevicePrefetcher), keyed by id() of the device weight tensor of the batch:
+# a Python attribute on the tensor would be lost by deep_chunk (torch.chunk returns new tensor objects)
+_LIVE_HINTS: dict = {}
 
 
 @_register
@@ -103,23 +110,43 @@ class MouseModel(_Base):
         self.train()
         self.optimizer.zero_grad()
         chunk_losses = []
+        try:  # hint registered by DevicePrefetcher for this (device-resident) batch; looked up BEFORE deep_chunk, which
+            pre_hint = _LIVE_HINTS.pop(id(batch[1][1]), None)  # returns new tensor objects
+        except (TypeError, IndexError, KeyError):
+            pre_hint = None
         for i, chunk_batch in enumerate(deep_chunk(batch, self.iter_size)):
-            host_w = chunk_batch[1][1]
+            host_t, host_w = chunk_batch[1]
+            # compact batch form (an extension of datasets.py:172-187): target = (responses (B, n_max, T) of each sample's
+            # own mouse, mouse_ids (B,) integer) instead of ten mostly-zero tensors + one-hot weights; it is scattered
+            # into the reference's dense form on the device, 17 MB instead of 160 MB of H2D per batch
+            compact = torch.is_tensor(host_t)
+            n_mice = len(self.nn_module.cfg["readout_outputs"])
             distill = self.distill_model is not None and self.distill_ratio
             if isinstance(self.loss, MicePoissonLoss):
                 if distill:
-                    self.loss.set_live_hint([True] * host_w.shape[1])
-                elif not host_w.is_cuda:
+                    self.loss.set_live_hint([True] * n_mice)
+                elif compact and not host_w.is_cuda:
+                    present = set(host_w.tolist())
+                    self.loss.set_live_hint([m in present for m in range(n_mice)])
+                elif not compact and not host_w.is_cuda:
                     self.loss.set_live_hint((host_w != 0).any(0).tolist())
-                elif hasattr(host_w, "_dwn_live"):  # batch prefetched by sensorium_b200.prefetch.DevicePrefetcher
-                    self.loss.set_live_hint(host_w._dwn_live)
+                elif pre_hint is not None and self.iter_size == 1:  # batch prefetched by DevicePrefetcher
+                    self.loss.set_live_hint(pre_hint)
             input, target, ready = self._to_device_overlapped(chunk_batch)
+
+            def dense():
+                nonlocal target, compact
+                ready()
+                if compact:
+                    target = collate_on_device(target[0], target[1], self.nn_module.cfg["readout_outputs"])
+                    compact = False
+
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
-                if self.distill_model is not None and self.distill_ratio:
-                    ready()
+                if distill:
+                    dense()
                 self.add_distill_predictions(input, target)
                 prediction = self.nn_module(input)
-                ready()  # targets / weights are only needed from here on
+                dense()  # targets / weights are only needed from here on
                 loss = self.loss(prediction, target)
                 loss = loss / self.iter_size
             self.grad_scaler.scale(loss).backward()

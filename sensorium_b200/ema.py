@@ -56,6 +56,8 @@ class ModelEma(nn.Module):
         ct, co, nch = self._chunks
         call("dwn_ema", self._tab, ct, co, nch, float(self.decay), torch.cuda.current_stream(dev).cuda_stream,
              _tag="ema", _bytes=self._nelem * 12)
+        from .engine import bump_generation
+        bump_generation()
         # weights of the EMA module changed behind autograd's back: drop stale bf16 shadows
         for p in self.ema.parameters():
             if getattr(p, "_dwn_shadow", None) is not None:

@@ -118,14 +118,37 @@ def _join(side, dev):
         main.wait_event(ev)
 
 
-def _bn_coef(bn, partial, P, count, C, Cp, training, st, dev, NQ=2):
+_GEN = [0]
+
+
+def bump_generation() -> None:
+    """Called by everything that writes parameters / buffers through raw pointers (train-mode forward: running
+    statistics; FusedAdamW.step; ModelEma.update; the data-parallel broadcast): torch's version counters do not see
+    those writes, so caches derived from the weights (eval BatchNorm tables) are keyed on this counter as well."""
+    _GEN[0] += 1
+
+
+def _eval_coef(bn, C, Cp, st, dev):
+    """Eval-mode BatchNorm folded to per-channel (scale, shift) once per set of weights: the table is cached on the module
+    and rebuilt only when a parameter / running statistic changes (version counters + storage + bump_generation)."""
+    ts = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = (C, Cp, str(dev), _GEN[0]) + tuple((t._version, t.data_ptr()) for t in ts)
+    ent = getattr(bn, "_dwn_eval_coef", None)
+    if ent is not None and ent[0] == key:
+        return ent[1]
     coef = _empty((4, C), torch.float32, dev)
-    if training:
-        call("dwn_bn_finalize", partial, P, float(count), bn.weight, bn.bias, bn.running_mean, bn.running_var,
-             bn.num_batches_tracked, BN_MOM, BN_EPS, 1, coef, C, Cp, NQ, st)
-    else:
-        call("dwn_bn_finalize", None, 0, 1.0, bn.weight, bn.bias, bn.running_mean, bn.running_var, None,
-             BN_MOM, BN_EPS, 0, coef, C, 0, 2, st)
+    call("dwn_bn_finalize", None, 0, 1.0, bn.weight, bn.bias, bn.running_mean, bn.running_var, None,
+         BN_MOM, BN_EPS, 0, coef, C, Cp, 2, st)
+    bn._dwn_eval_coef = (key, coef)
+    return coef
+
+
+def _bn_coef(bn, partial, P, count, C, Cp, training, st, dev, NQ=2):
+    if not training:
+        return _eval_coef(bn, C, Cp, st, dev)
+    coef = _empty((4, C), torch.float32, dev)
+    call("dwn_bn_finalize", partial, P, float(count), bn.weight, bn.bias, bn.running_mean, bn.running_var,
+         bn.num_batches_tracked, BN_MOM, BN_EPS, 1, coef, C, Cp, NQ, st)
     return coef
 
 
@@ -199,6 +222,8 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
     if cfg["spatial_kernel"] != 3 or cfg["temporal_kernel"] != 5:
         raise NotImplementedError("sensorium_b200 kernels are specialised for spatial_kernel=3, temporal_kernel=5")
     sv = SimpleNamespace(blocks=[], cortex=[], readouts=[], mode=mode, B=B, T=T, H=H, W=W, x=x) if save else None
+    if training:
+        bump_generation()                              # running statistics are about to change
     rng_dev = getattr(mod, "_rng_device", None)        # test hooks: where / in which dtype the masks are drawn
     mdt = getattr(mod, "_mask_dtype", None) or adt
 
@@ -206,7 +231,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
     stem_conv, stem_bn = mod.core.stem[0], mod.core.stem[1].bn
     C0 = feats[0]
     M0 = B * T * H * W
-    coef0 = _empty((4, C0), torch.float32, dev)
+    coef0 = _empty((4, C0), torch.float32, dev) if training else None
     mom = None
     if training:
         nm = Cin + Cin * (Cin + 1) // 2
@@ -216,8 +241,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         call("dwn_stem_coef", mom, Cin, float(M0), stem_conv.weight, stem_bn.weight, stem_bn.bias,
              stem_bn.running_mean, stem_bn.running_var, stem_bn.num_batches_tracked, BN_MOM, BN_EPS, coef0, C0, st)
     else:
-        call("dwn_bn_finalize", None, 0, 1.0, stem_bn.weight, stem_bn.bias, stem_bn.running_mean,
-             stem_bn.running_var, None, BN_MOM, BN_EPS, 0, coef0, C0, 0, 2, st)
+        coef0 = _eval_coef(stem_bn, C0, 0, st, dev)
     pe = pe_tables(mod.core.blocks[0], C0, T, H, W, dev)
     X = _empty((M0, C0), torch.float32, dev)
     Xb = _empty((M0, C0), torch.bfloat16, dev) if bf else None

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import call
-from .engine import set_shadow
+from .engine import bump_generation, set_shadow
 
 
 def _chunk_tables(sizes, chunk, dev):
@@ -98,6 +98,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 sh = getattr(p, "_dwn_shadow", None)
                 if sh is not None:
                     set_shadow(p, sh[1])
+        bump_generation()
         provider = getattr(self, "active_provider", None)
         if provider is not None and hasattr(provider, "consumed"):
             provider.consumed()

@@ -52,6 +52,8 @@ class DataParallelGrads:
         with torch.no_grad():
             for t in mod.state_dict().values():
                 dist.broadcast(t, src=0, group=group)
+        from .engine import bump_generation
+        bump_generation()
         mod._dp = DataParallelGrads(mod, group)
         if optimizer is not False:
             optimizer.active_provider = mod._dp

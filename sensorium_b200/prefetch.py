@@ -3,8 +3,9 @@
 ``MouseModel.train_step`` (argus_models.py:43-71 contract) receives one batch at a time, so the copy of its input
 (42 MB at batch 32) sits on the critical path of the step.  Wrapping the DataLoader in ``DevicePrefetcher`` issues
 the copies of batch i+1 from pinned host memory on a side stream while step i computes; ``train_step`` accepts the
-device-resident batch as is.  The set of mice present in a batch is taken from the host copy of the weights and
-travels with the device tensor, so the loss still needs no device sync.
+device-resident batch as is.  The set of mice present in a batch is taken from the host copy of the weights and kept in
+a side table keyed by the device weight tensor (``argus_models._LIVE_HINTS``), which ``train_step`` reads before it
+chunks the batch — so with ``iter_size == 1`` the loss needs no device sync.
 
 Measured on the bench box (synthetic batches, one B200): no gain over handing pinned host batches to ``train_step``
 directly (1012 vs 1047 clips/s) — ``train_step`` already overlaps the target / weight copies (80 % of the bytes) with
@@ -65,7 +66,10 @@ class DevicePrefetcher:
         try:  # live-mouse hint from the host weights (no device sync in the loss)
             host_w = batch[1][1]
             if torch.is_tensor(host_w) and not host_w.is_cuda and host_w.dim() == 2:
-                dev_batch[1][1]._dwn_live = (host_w != 0).any(0).tolist()
+                from .argus_models import _LIVE_HINTS
+                if len(_LIVE_HINTS) > 64:  # batches that never reached train_step
+                    _LIVE_HINTS.clear()
+                _LIVE_HINTS[id(dev_batch[1][1])] = (host_w != 0).any(0).tolist()
         except (TypeError, IndexError):
             pass
         return dev_batch, ev

@@ -170,3 +170,22 @@ def test_ema_checkpoint_layout(tmp_path):
     for (k, a), b in zip(ema_module.state_dict().items(), loaded.nn_module.state_dict().values()):
         assert torch.equal(a, b), k
     assert not torch.equal(loaded.nn_module.core.stem[0].weight, m.nn_module.core.stem[0].weight)
+
+
+def test_synthetic_generators_match_the_oracle():
+    """bench.py's GPU arm draws its inputs from sensorium_b200.synthetic (no oracle import); the tests use the oracle's
+    generators: both must produce identical tensors."""
+    import torch
+    from oracle import dwiseneuro_oracle as O
+    from sensorium_b200 import synthetic as S
+    assert torch.equal(S.synthetic_clip(3, 16, 64, seed=5), O.synthetic_clip(3, 16, 64, seed=5))
+    a, wa = S.synthetic_targets(5, (7, 9, 4), 16, seed=2)
+    b, wb = O.synthetic_targets(5, (7, 9, 4), 16, seed=2)
+    assert torch.equal(wa, wb) and all(torch.equal(x, y) for x, y in zip(a, b))
+    comp, ids = S.compact_from_dense(a, wa)
+    assert comp.shape == (5, 9, 16) and torch.equal(ids, wa.argmax(1))
+    for i in range(5):
+        m = int(ids[i])
+        assert torch.equal(comp[i, :a[m].shape[1]], a[m][i]) and float(comp[i, a[m].shape[1]:].abs().sum()) == 0.0
+    v, bh, pc = S.synthetic_trial(50, seed=1)
+    assert v.shape == (36, 64, 50) and v.dtype.name == "uint8" and bh.shape == (2, 50) and pc.shape == (2, 50)

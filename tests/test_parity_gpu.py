@@ -575,3 +575,98 @@ def test_cutmix_and_collation_on_device(dev, golden_dir):
     assert torch.equal(got_w.cpu(), want_w)
     for a, b_ in zip(got_t, want_t):
         assert torch.equal(a.cpu(), b_)
+
+
+def test_ensemble_predictor_mean_of_folds(dev, tmp_path):
+    """scripts/predict.py:43-49: the response of a trial is np.mean over the fold models of Predictor.predict_trial.
+    EnsemblePredictor (all models resident, windows assembled once, sum over models on the device) must equal the
+    oracle's per-window loop run per model and averaged — fp32 <= 1e-4; the bf16 option stays within 2e-2."""
+    from sensorium_b200.argus_models import MouseModel
+    from sensorium_b200.predictors import EnsemblePredictor
+    from sensorium_b200.utils import init_weights
+    kw = {"readout_outputs": (9, 6), "core_features": (8, 16), "spatial_strides": (2, 2), "expansion_ratio": 2,
+          "se_reduce_ratio": 4, "cortex_features": (16,), "groups": 2}
+    paths, sds = [], []
+    for fold in range(3):
+        params = {"nn_module": ("dwiseneuro", kw), "loss": None, "optimizer": None, "device": "cuda:0",
+                  "frame_stack": {"size": 16, "step": 2, "position": "last"},
+                  "inputs_processor": ("stack_inputs", {"size": (64, 64), "pad_fill_value": 0.0}),
+                  "responses_processor": ("identity", {}), "amp": True, "iter_size": 1}
+        torch.manual_seed(10 + fold)
+        m = MouseModel(params)
+        init_weights(m.nn_module)
+        with torch.no_grad():
+            for k, v in m.nn_module.state_dict().items():
+                if "running_mean" in k:
+                    v.uniform_(-0.2, 0.2)
+                if "running_var" in k:
+                    v.uniform_(0.5, 1.5)
+        path = tmp_path / f"fold_{fold}" / "model-001-0.100000.pth"
+        path.parent.mkdir()
+        m.save(path)
+        paths.append(path)
+        sds.append({k: v.detach().cpu() for k, v in m.nn_module.state_dict().items()})
+    ens = EnsemblePredictor(paths, device="cuda:0", blend_weights="ones", window_batch=5)
+    rs = np.random.RandomState(1)
+    L = 39
+    video = rs.randint(0, 256, (36, 64, L)).astype(np.uint8)
+    beh, pup = rs.rand(2, L).astype(np.float32), rs.rand(2, L).astype(np.float32)
+    got = ens.predict_trial(video, beh, pup, 0)
+    assert got.shape == (9, L) and got.dtype == np.float32
+    cfg = O.make_cfg(kw["readout_outputs"], **{k: v for k, v in kw.items() if k != "readout_outputs"})
+    inputs = O.stack_inputs(torch.from_numpy(video), torch.from_numpy(beh), torch.from_numpy(pup))
+    with torch.no_grad():
+        per_model = [O.predict_trial(lambda c, sd=sd: O.dwiseneuro_forward(c, sd, cfg, 0, False), inputs, 9, 16, 2, "ones")
+                     .numpy() for sd in sds]
+    want = np.mean(per_model, axis=0)
+    assert rel(torch.from_numpy(got), torch.from_numpy(want)) < FP32_TOL
+    assert np.all(got[:, [1, 3]] == 0.0) == bool((want[:, [1, 3]] == 0).all())   # frames no window covers stay 0
+    ens.set_precision("bf16")
+    got16 = ens.predict_trial(video, beh, pup, 0)
+    assert rel(torch.from_numpy(got16), torch.from_numpy(want)) < BF16_TOL
+    # sharded form (single process: every trial on this rank)
+    trials = [{"video": video, "behavior": beh, "pupil_center": pup, "mouse_index": 0},
+              {"video": video[..., :35], "behavior": beh[:, :35], "pupil_center": pup[:, :35], "mouse_index": 1}]
+    ens.set_precision("fp32")
+    res = ens.predict_trials(trials)
+    assert sorted(res) == [0, 1] and np.array_equal(res[0], got) and res[1].shape == (6, 35)
+
+
+def test_train_step_compact_targets_equal_dense(dev):
+    """train_step accepts (input, (responses (B, n_max, T), mouse_ids (B,))) and scatters it into the reference's dense
+    batch form on the device (datasets.py:172-187): the step is bit-identical to the dense host batch, and the returned
+    target has the dense form."""
+    from sensorium_b200.argus_models import MouseModel
+    from sensorium_b200.synthetic import compact_from_dense
+    from sensorium_b200.utils import init_weights
+
+    def run(compact):
+        params = {"nn_module": ("dwiseneuro", {"readout_outputs": TINY_OUTS, **TINY_KW}), "loss": ("mice_poisson", {}),
+                  "optimizer": ("AdamW", {"lr": 2e-3, "weight_decay": 0.05}), "device": "cuda:0", "amp": True,
+                  "iter_size": 1}
+        torch.manual_seed(0)
+        m = MouseModel(params)
+        init_weights(m.nn_module)
+        torch.manual_seed(4)
+        losses, out = [], None
+        for i in range(2):
+            x = O.synthetic_clip(5, 16, 32, seed=30 + i)
+            tg, w = O.synthetic_targets(5, TINY_OUTS, 16, seed=40 + i)
+            if i == 1:                       # mouse 1 has no sample in the second batch
+                tg[0] = tg[0] + tg[1][:, :37] * 0 + (w[:, 1] != 0).float()[:, None, None]
+                w[:, 0] += w[:, 1]
+                w[:, 1] = 0
+                tg[1].zero_()
+            target = compact_from_dense(tg, w) if compact else (tg, w)
+            out = m.train_step((x, target), None)
+            losses.append(out["loss"])
+        return m, losses, out
+
+    m1, l1, o1 = run(False)
+    m2, l2, o2 = run(True)
+    assert l1 == l2
+    for a, b in zip(m1.nn_module.state_dict().values(), m2.nn_module.state_dict().values()):
+        assert torch.equal(a, b)
+    t1, w1 = o1["target"]
+    t2, w2 = o2["target"]
+    assert torch.equal(w1.to(dev), w2) and all(torch.equal(a.to(dev), b) for a, b in zip(t1, t2))
