@@ -5,6 +5,14 @@ random-init weights.  One JSON line on stdout (rank 0).
 
   python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
   python bench.py --impl reference ...                   # reference algorithm on the host CPU (oracle port)
+
+The GPU arm's line carries, next to the contract keys (value / e2e / roofline / cpu_baseline / clocks / gpu_launches):
+  eager_b200  the reference algorithm (oracle restatement, cuDNN / cuBLAS, bf16 autocast, torch fused AdamW) on the SAME GPU
+  c4          BASELINE configs[3]: distillation train step (expansion-6 student, frozen expansion-7 teacher), e2e
+  infer       BASELINE configs[4]: 7-model ensemble over 300-frame trials, windows/s in fp32 and bf16, trials sharded
+              over the N ranks
+  gemm        tensor-pipe TFLOP/s of the tcgen05 GEMM groups and their fraction of the measured bf16 peak
+All of them are measured AFTER the timed region of `value`.
 """
 from __future__ import annotations
 
@@ -31,6 +39,7 @@ MODEL_KW = dict(in_channels=5, core_features=(64, 64, 64, 64, 128, 128, 128, 256
                 drop_path_rate=0.1)
 BATCH, FRAMES, SIZE = 32, 16, 64
 LR, WD, EMA_DECAY = 3e-4 * 32 / 4, 0.05, 0.999
+TRIAL_FRAMES, N_FOLDS = 300, 7
 
 
 # Rank 0 must print exactly ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner
@@ -50,9 +59,17 @@ WORKLOAD = ("DwiseNeuro true_batch_001 (expansion 7) full train step: fwd + Mice
             "all 10 readouts, batch 32 per GPU, clip 5x16x64x64")
 
 
+def bench_config(world: int) -> dict:
+    """The SAME config object for both arms (the reference arm times a bounded sample of this workload, see its
+    cpu_baseline.sample)."""
+    return {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+            "weights": "random-init (init_weights)",
+            "l2": "working set per step (>15 GB of activations) exceeds the 126 MB L2"}
+
+
 def synthetic_batch(batch: int, seed: int):
     """clip (B,5,16,64,64) + one labelled mouse per sample, dense zero targets elsewhere."""
-    from oracle.dwiseneuro_oracle import synthetic_clip, synthetic_targets
+    from sensorium_b200.synthetic import synthetic_clip, synthetic_targets
     x = synthetic_clip(batch, FRAMES, SIZE, seed=seed)
     tg, w = synthetic_targets(batch, NUM_NEURONS, FRAMES, seed=seed + 1)
     return x, tg, w
@@ -87,23 +104,31 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def cpu_reference_step(batch: int, steps: int, warmup: int):
-    """Reference algorithm (oracle port: functional torch restatement) on the host cores: fp32 train step
-    fwd + loss + bwd + AdamW, expansion 7, all readouts.  Returns clips/s, threads."""
+# ---------------------------------------------------------------------------------------------------------------------
+# reference algorithm (oracle port: functional torch restatement of the reference modules)
+# ---------------------------------------------------------------------------------------------------------------------
+def _oracle_state(device):
     from oracle import dwiseneuro_oracle as O
     from sensorium_b200 import DwiseNeuro
     from sensorium_b200.utils import init_weights
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     torch.manual_seed(0)
     net = DwiseNeuro(readout_outputs=NUM_NEURONS, **MODEL_KW)
     init_weights(net)
-    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sd = {k: v.detach().clone().to(device) for k, v in net.state_dict().items()}
     names = [k for k, _ in net.named_parameters()]
     del net
     params = [sd[k].requires_grad_(True) for k in names]
+    return O, sd, params, O.make_cfg(NUM_NEURONS, **MODEL_KW)
+
+
+def cpu_reference_step(batch: int, steps: int, warmup: int):
+    """Reference algorithm on the host cores: fp32 train step fwd + loss + bwd + torch AdamW + EMA over every state
+    entry (ema.py:47-55), expansion 7, all readouts.  Returns clips/s, threads, s/step."""
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    O, sd, params, cfg = _oracle_state("cpu")
+    ema = {k: v.detach().clone() for k, v in sd.items()}
     opt = torch.optim.AdamW(params, lr=LR, weight_decay=WD)
-    cfg = O.make_cfg(NUM_NEURONS, **MODEL_KW)
     x, tg, w = synthetic_batch(batch, 0)
     t_total = 0.0
     for it in range(warmup + steps):
@@ -113,29 +138,164 @@ def cpu_reference_step(batch: int, steps: int, warmup: int):
         loss = O.mice_poisson_loss(out, tg, w)
         loss.backward()
         opt.step()
+        O.ema_update(ema, sd, EMA_DECAY)
         dt = time.perf_counter() - t0
         if it >= warmup:
             t_total += dt
     return batch * steps / t_total, threads, t_total / steps
 
 
+def eager_b200_step(dev, steps: int = 3, warmup: int = 2):
+    """The reference algorithm as torch eager executes it on the SAME B200 (cuDNN / cuBLAS kernels, bf16 autocast,
+    torch's fused AdamW, EMA with torch._foreach ops), batch 32, resident inputs — the bar every kernel here has to beat."""
+    O, sd, params, cfg = _oracle_state(dev)
+    src = [v for v in sd.values() if v.dtype.is_floating_point]
+    ema = [v.detach().clone() for v in src]
+    opt = torch.optim.AdamW(params, lr=LR, weight_decay=WD, fused=True)
+    x, tg, w = synthetic_batch(BATCH, 0)
+    x, tg, w = x.to(dev), [t.to(dev) for t in tg], w.to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = O.dwiseneuro_forward(x, sd, cfg, None, True)
+            loss = O.mice_poisson_loss(out, tg, w)
+        loss.backward()
+        opt.step()
+        with torch.no_grad():
+            torch._foreach_lerp_(ema, [s.detach() for s in src], 1.0 - EMA_DECAY)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del opt, sd, params, ema, src
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms, "value": BATCH / (ms * 1e-3), "unit": "clips/s", "steps": steps,
+            "what": "oracle restatement of the reference under torch.autocast(bf16), cuDNN/cuBLAS kernels, fused AdamW, "
+                    "foreach EMA, batch 32, inputs resident (1 GPU)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     sample_b = 4
     val, threads, sec = cpu_reference_step(sample_b, args.steps, args.warmup)
+    sample = (f"each step = one fp32 train step (fwd + MicePoissonLoss + bwd + torch AdamW + EMA) of a batch-{sample_b} "
+              f"sample of the batch-32 workload on {threads} host threads (oracle port of the reference, torch CPU); "
+              f"{args.steps} steps after {args.warmup} warm-up")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "sample": f"batch {sample_b} per step on the host CPU (oracle port of the reference; EMA update not included)"},
-        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} train steps of batch {sample_b} (oracle port, fp32, torch CPU)"},
+        "config": bench_config(world),
+        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def _timed(fn, n, barrier, dev, world):
+    """n calls of fn between barriers; device time (CUDA events) and wall clock, max over ranks."""
+    import torch.distributed as dist
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(n):
+        fn()
+    g1.record()
+    barrier()
+    ms = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def bench_c4(dev, rank, world, barrier, steps=8):
+    """BASELINE configs[3] (configs/distillation_001.py): expansion-6 student trained on its own labels plus the frozen
+    expansion-7 teacher's predictions for the other nine mice (distill_ratio 0.36), drop-path / dropout on, EMA;
+    through MouseModel.train_step with a pinned HOST batch."""
+    from sensorium_b200 import DwiseNeuro
+    from sensorium_b200.argus_models import MouseModel
+    from sensorium_b200.ema import ModelEma
+    from sensorium_b200.synthetic import compact_from_dense
+    from sensorium_b200.utils import init_weights
+    kw_s = dict(MODEL_KW, expansion_ratio=6)
+    params = {"nn_module": ("dwiseneuro", {"readout_outputs": NUM_NEURONS, **kw_s}),
+              "loss": ("mice_poisson", {}), "optimizer": ("FusedAdamW", {"lr": LR, "weight_decay": WD}),
+              "device": str(dev), "amp": True, "iter_size": 1}
+    torch.manual_seed(1)
+    m = MouseModel(params)
+    init_weights(m.nn_module)
+    teacher = DwiseNeuro(readout_outputs=NUM_NEURONS, **MODEL_KW).to(dev)
+    init_weights(teacher)
+    teacher.eval()
+    if world > 1:
+        from sensorium_b200.parallel import DataParallelGrads
+        DataParallelGrads.attach(m.nn_module, m.optimizer)
+    m.model_ema = ModelEma(m.nn_module, decay=EMA_DECAY)
+    m.distill_model, m.distill_ratio = teacher, 0.36
+    x, tg, w = synthetic_batch(BATCH, 2000 + rank)
+    comp, ids = compact_from_dense(tg, w)
+    host = (x.pin_memory(), (comp.pin_memory(), ids.pin_memory()))
+    for _ in range(3):
+        m.train_step(host, None)
+    ms = _timed(lambda: m.train_step(host, None), steps, barrier, dev, world)
+    del m, teacher
+    torch.cuda.empty_cache()
+    return {"value": BATCH * world * steps / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms / steps, "steps": steps,
+            "path": "MouseModel.train_step(pinned host batch, compact targets) with distill_model (teacher forward + "
+                    "target fill + student fwd/bwd + AdamW + EMA) -> loss.item()"}
+
+
+def bench_infer(dev, rank, world, barrier):
+    """BASELINE configs[4] (scripts/predict.py:43-49,65-72 over src/predictors.py:36-55): 7 fold models resident per GPU,
+    300-frame trials (270 windows each), trials round-robin over the ranks, host arrays in -> host responses out."""
+    from sensorium_b200.argus_models import MouseModel
+    from sensorium_b200.predictors import EnsemblePredictor, Predictor
+    from sensorium_b200.synthetic import synthetic_trial
+    from sensorium_b200.utils import init_weights
+    params = {"nn_module": ("dwiseneuro", {"readout_outputs": NUM_NEURONS, **MODEL_KW}), "loss": None, "optimizer": None,
+              "device": str(dev), "frame_stack": {"size": 16, "step": 2, "position": "last"},
+              "inputs_processor": ("stack_inputs", {"size": (64, 64), "pad_fill_value": 0.0}),
+              "responses_processor": ("identity", {}), "amp": True, "iter_size": 1}
+    preds = []
+    for fold in range(N_FOLDS):
+        torch.manual_seed(fold)
+        m = MouseModel(params)
+        init_weights(m.nn_module)       # on the device
+        preds.append(Predictor.from_model(m, window_batch=64))
+    ens = EnsemblePredictor(preds, window_batch=64)
+    out = {"models": N_FOLDS, "trial_frames": TRIAL_FRAMES, "windows_per_trial": TRIAL_FRAMES - 30, "unit": "windows/s",
+           "path": "EnsemblePredictor.predict_trial per trial (raw uint8 trial on the host -> responses on the host), "
+                   "trials round-robin over ranks"}
+    for mode, per_rank in (("bf16", 2), ("fp32", 1)):
+        ens.set_precision(mode)
+        trials = []
+        for i in range(per_rank * world):
+            v, b, p = synthetic_trial(TRIAL_FRAMES, seed=100 + i)
+            trials.append({"video": v, "behavior": b, "pupil_center": p, "mouse_index": i % 5})
+        mine = trials[rank::world]
+        ens.predict_trial(**{k: (a[..., :64] if k != "mouse_index" else a) for k, a in mine[0].items()})  # warm-up
+        ms = _timed(lambda: [ens.predict_trial(**t) for t in mine], 1, barrier, dev, world)
+        out[mode] = {"value": (TRIAL_FRAMES - 30) * N_FOLDS * len(trials) / (ms * 1e-3), "ms": ms, "trials": len(trials)}
+    del ens, preds
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -145,6 +305,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the eager_b200 / c4 / infer legs")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--profile-out", default="")
     ap.add_argument("--cuda-profiler-step", action="store_true",
@@ -157,9 +318,10 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    from sensorium_b200 import _lib
+    from sensorium_b200 import _lib, engine
     from sensorium_b200.argus_models import MouseModel
     from sensorium_b200.ema import ModelEma
+    from sensorium_b200.synthetic import compact_from_dense
     from sensorium_b200.utils import init_weights
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -180,13 +342,16 @@ def main():
     }
     model = MouseModel(params)
     init_weights(model.nn_module)
+    dp = None
     if world > 1:
         from sensorium_b200.parallel import DataParallelGrads
-        DataParallelGrads.attach(model.nn_module, model.optimizer)
+        dp = DataParallelGrads.attach(model.nn_module, model.optimizer)
     model.model_ema = ModelEma(model.nn_module, decay=EMA_DECAY)
 
     x, tg, w = synthetic_batch(BATCH, args.seed_base + rank)
-    host_batch = (x.pin_memory(), ([t.pin_memory() for t in tg], w.pin_memory()))
+    comp, ids = compact_from_dense(tg, w)
+    host_dense = (x.pin_memory(), ([t.pin_memory() for t in tg], w.pin_memory()))
+    host_compact = (host_dense[0], (comp.pin_memory(), ids.pin_memory()))
     dev_x = x.to(dev)
     dev_tg = [t.to(dev) for t in tg]
     dev_w = w.to(dev)
@@ -228,46 +393,56 @@ def main():
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    bytes_reduced = dp.bytes_reduced if dp is not None else 0
     if args.cuda_profiler_step:
         torch.cuda.profiler.start()
         device_step()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-    # per-kernel CUDA-event accounting: the same step, right after the timed region, with one event pair around
-    # every launch (kept out of the timed region so that the ~1.5k event records do not perturb `value`)
+
+    # ---- end-to-end: public API (MouseModel.train_step) with pinned HOST buffers, H2D + loss.item() inside
+    def e2e(host):
+        for _ in range(3):
+            model.train_step(host, None)
+        return _timed(lambda: model.train_step(host, None), args.e2e_steps, barrier, dev, world)
+
+    e2e_ms = e2e(host_compact)
+    e2e_dense_ms = e2e(host_dense)
+    sampler.stop_flag = True
+
+    # ---- per-kernel accounting: the same step with every launch on ONE stream (engine.SERIALIZE) and one CUDA-event
+    # pair around every launch, so no two measured intervals overlap; run after the timed region so that the ~1.5k event
+    # records do not perturb `value`
     prof_steps = max(2, min(4, args.steps))
+    engine.SERIALIZE = True
+    device_step()
     _lib.PROF = []
     for _ in range(prof_steps):
         device_step()
     barrier()
     prof, _lib.PROF = _lib.PROF, None
+    engine.SERIALIZE = False
 
-    # ---- end-to-end: public API (MouseModel.train_step) with pinned HOST buffers, H2D + loss.item() inside
-    # (sensorium_b200.prefetch.DevicePrefetcher was measured here as well: 1012 clips/s against 1047 for the plain call
-    # below, whose target copies already overlap the forward pass inside train_step)
-    for _ in range(3):
-        model.train_step(host_batch, None)
-    barrier()
-    t0 = time.perf_counter()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for _ in range(args.e2e_steps):
-        model.train_step(host_batch, None)
-    g1.record()
-    barrier()
-    e2e_ms = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    sampler.stop_flag = True
+    extras = {}
+    if not args.no_extras:
+        del dev_tg
+        model.optimizer.zero_grad()
+        torch.cuda.empty_cache()
+        extras["c4"] = bench_c4(dev, rank, world, barrier)
+        extras["infer"] = bench_infer(dev, rank, world, barrier)
+        if rank == 0:
+            try:
+                extras["eager_b200"] = eager_b200_step(dev)
+            except Exception as e:  # noqa: BLE001
+                extras["eager_b200"] = {"unavailable": repr(e)[:200]}
+        barrier()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- per-kernel accounting from the CUDA events recorded inside the timed region
+    # ---- per-kernel table from the serialized profile steps
     agg = defaultdict(lambda: [0.0, 0, 0, 0])
     for name, tag, nbytes, flops, a, b in prof:
         k = tag or name
@@ -282,6 +457,7 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    tc_peak = float(peaks.get("bf16_tflops_sustained", 1366.0))
     total_kernel_ms = sum(v[0] for v in agg.values())
     table = sorted(((k, v[0] / prof_steps, v[1] // prof_steps, v[2] / max(v[0], 1e-9) * 1e-6, v[3] / max(v[0], 1e-9) * 1e-9)
                     for k, v in agg.items()), key=lambda r: -r[1])
@@ -291,7 +467,9 @@ def main():
                 "frac": top[3] / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "share_of_step": top_entry[0] / max(total_kernel_ms, 1e-9),
                 "launches_per_step": top[2], "ms_per_step": top[1],
-                "how": f"CUDA events around every launch of this kernel over {prof_steps} steps run right after the timed region"}
+                "how": f"CUDA events around every launch of this kernel over {prof_steps} steps run right after the timed "
+                       "region with all launches serialized on one stream (no overlapping intervals); share_of_step is "
+                       "relative to the sum of all serialized kernel times"}
     roofline["algorithmic_bytes_per_launch"] = top_entry[2] / max(top_entry[1], 1)
     try:  # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/)
         tr = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text())
@@ -305,30 +483,47 @@ def main():
             f.write("kernel,ms_per_step,launches_per_step,GB/s,TFLOP/s,share\n")
             for k, msps, n, gbs, tf in table:
                 f.write(f"{k},{msps:.4f},{n},{gbs:.1f},{tf:.2f},{msps * prof_steps / total_kernel_ms:.4f}\n")
+    gemm = {}
+    for k, msps, n, gbs, tf in table:
+        if k.startswith(("pw_", "pwl_", "readout_fwd", "readout_wgrad", "readout_dgrad")):
+            gemm[k] = {"tflops": round(tf, 1), "frac_of_bf16_peak": round(tf / tc_peak, 3), "hbm_gbs": round(gbs, 1),
+                       "frac_of_hbm_peak": round(gbs / hbm_peak, 3), "ms_per_step": round(msps, 3)}
+    gemm["_peak"] = {"bf16_tflops_sustained": tc_peak, "bound": "the point-wise GEMMs (K <= 256) sit below the ridge "
+                     "(56-224 FLOP/B vs ~210): HBM-bound, tensor-pipe fraction reported for completeness"}
 
     clips = BATCH * world * args.steps
     value = clips / (ms * 1e-3)
-    h2d = x.numel() * 4 + sum(t.numel() for t in tg) * 4 + w.numel() * 4
+    h2d = x.numel() * 4 + comp.numel() * 4 + ids.numel() * 8
+    h2d_dense = x.numel() * 4 + sum(t.numel() for t in tg) * 4 + w.numel() * 4
     line = {
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "global_batch": BATCH * world, "parallelism": f"dp{world}", "weights": "random-init (init_weights)",
-                   "l2": "working set per step (>15 GB of activations) exceeds the 126 MB L2"},
+        "config": bench_config(world),
         "e2e": {"value": BATCH * world * args.e2e_steps / (e2e_ms * 1e-3), "unit": "clips/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": args.e2e_steps,
-                "path": "MouseModel.train_step(pinned host batch) -> loss.item()"},
+                "path": "MouseModel.train_step(pinned host batch: clips + compact per-sample targets + mouse ids) -> "
+                        "loss.item()"},
+        "e2e_dense": {"value": BATCH * world * args.e2e_steps / (e2e_dense_ms * 1e-3), "unit": "clips/s",
+                      "h2d_bytes_per_step": h2d_dense, "d2h_bytes_per_step": 4,
+                      "path": "same call with the reference's dense batch form (ten mostly-zero target tensors)"},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": roofline,
-        "kernel_table_ms_per_step": {k: round(msps, 3) for k, msps, *_ in table[:12]},
+        "kernel_table_ms_per_step": {k: round(msps, 3) for k, msps, *_ in table[:14]},
+        "kernel_table_source": "serialized CUDA-event intervals (engine.SERIALIZE), sum = "
+                               f"{total_kernel_ms / prof_steps:.2f} ms per step",
+        "gemm": gemm,
     }
+    if world > 1:
+        line["comm"] = {"bytes_reduced_per_step": bytes_reduced, "collective": "ncclAllReduce(AVG) per bucket, overlapped "
+                        "with backward"}
+    line.update(extras)
     if not args.no_cpu_baseline and world == 1:
         val, threads, sec = cpu_reference_step(8, 2, 1)
         line["cpu_baseline"] = {"value": val, "unit": "clips/s", "cores": threads, "kind": "port",
                                 "sample": "2 train steps of batch 8 after 1 warm-up (oracle port of the reference: "
-                                          "fp32 fwd + MicePoissonLoss + bwd + torch AdamW on the host CPU)"}
+                                          "fp32 fwd + MicePoissonLoss + bwd + torch AdamW + EMA on the host CPU)"}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

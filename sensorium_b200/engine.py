@@ -82,6 +82,9 @@ def set_shadow(p: torch.Tensor, sh: torch.Tensor) -> None:
 
 
 _side = {}
+# bench.py's per-kernel accounting sets this: every launch goes to the current stream, so CUDA-event pairs around single
+# launches never overlap each other (side-stream work would otherwise be counted twice)
+SERIALIZE = False
 
 
 class _nullctx:
@@ -94,7 +97,7 @@ class _nullctx:
 
 def _side_streams(dev, njobs, n=3):
     """Side streams for independent per-mouse launches (readout GEMMs)."""
-    if njobs < 2:
+    if njobs < 2 or SERIALIZE:
         return []
     key = (dev.index, n)
     if key not in _side:
@@ -279,9 +282,9 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
             sx = _empty((ci,), torch.float32, dev)
             coef1 = _empty((4, mid), torch.float32, dev)
             bn1 = blk.conv_pw[1].bn
-            stats_side = [_stats_stream(dev)]
+            stats_side = [] if SERIALIZE else [_stats_stream(dev)]
             _fork(stats_side, dev)
-            with torch.cuda.stream(stats_side[0]):
+            with torch.cuda.stream(stats_side[0]) if stats_side else _nullctx():
                 sst = _stream(dev)
                 _gram(Xb, Mi, ci, sst, dev, out=gram)
                 call("dwn_partial_colsum", sc_part, _P, 3, 2, ci, sx, sst)
@@ -289,7 +292,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
                      bn1.running_var, bn1.num_batches_tracked, BN_MOM, BN_EPS, coef1, mid, ci, sst)
         gemm(st, dtype=dcode, A=Xb if bf else X, B=wsh, lda=ci, ldb=ci, M=Mi, N=mid, K=ci, Z=1,
              D=E, d_dtype=dcode, ldd=mid, _tag="pw_fwd", _bytes=(Mi * ci + mid * ci + Mi * mid) * es)
-        if stats_side:
+        if gram is not None:
             _join(stats_side, dev)
         else:
             coef1 = _bn_coef(blk.conv_pw[1].bn, _colstats(E, Mi, mid, mid, dcode, st, dev) if training else None, _P,

@@ -35,8 +35,9 @@ def get_blend_weights(name: str, size: int):
 
 class Predictor:
     def __init__(self, model_path: Path | str, device: str = "cuda:0", blend_weights="ones", window_batch: int = 32,
-                 precision: str = "auto"):
-        self.model: MouseModel = _load_model(model_path, device=device, optimizer=None, loss=None)
+                 precision: str = "auto", _model=None):
+        self.model: MouseModel = _model if _model is not None else _load_model(model_path, device=device,
+                                                                                optimizer=None, loss=None)
         self.model.eval()
         self.model.nn_module.precision = precision
         self.inputs_processor = get_inputs_processor(*self.model.params["inputs_processor"])
@@ -47,6 +48,12 @@ class Predictor:
         self.indexes_generator = IndexesGenerator(self.frame_stack_size, self.frame_stack_step)
         self.blend_weights = get_blend_weights(blend_weights, self.frame_stack_size)
         self.window_batch = int(window_batch)
+
+    @classmethod
+    def from_model(cls, model: "MouseModel", blend_weights="ones", window_batch: int = 32, precision: str = "auto"):
+        """Predictor over an already constructed MouseModel (no checkpoint file)."""
+        return cls(None, device=str(model.device), blend_weights=blend_weights, window_batch=window_batch,
+                   precision=precision, _model=model)
 
     @torch.no_grad()
     def predict_trial_device(self, inputs: torch.Tensor, mouse_index: int) -> torch.Tensor:
@@ -133,7 +140,8 @@ class EnsemblePredictor:
         model_paths = list(model_paths)
         if not model_paths:
             raise ValueError("EnsemblePredictor needs at least one model path")
-        self.predictors = [Predictor(p, device=device, blend_weights=blend_weights, window_batch=window_batch,
+        self.predictors = [p if isinstance(p, Predictor) else
+                           Predictor(p, device=device, blend_weights=blend_weights, window_batch=window_batch,
                                      precision=precision) for p in model_paths]
         p0 = self.predictors[0]
         for p in self.predictors[1:]:  # the reference builds every fold from the same config
