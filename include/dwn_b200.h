@@ -51,8 +51,14 @@ typedef struct {
   long lda2, ldb2;
   int K2;
   unsigned dbg_lbo_a, dbg_sbo_a, dbg_lbo_b, dbg_sbo_b; /* debug override of MN-major descriptor strides */
+  int split;                 /* 3: A and B each hold three bf16 planes (hi, mid, lo of an fp32 operand, dwn_split3) with
+                                the layout described above, a_pstride / b_pstride elements apart; the six significant
+                                plane products are accumulated in fp32 -> fp32-accurate product on the tensor cores */
+  long a_pstride, b_pstride;
 } dwn_gemm_desc;
 int dwn_gemm(const dwn_gemm_desc* d, void* stream);
+/* fp32 -> three bf16 planes: dst[p][i], p = 0..2, x = dst[0] + dst[1] + dst[2] up to 2^-25 |x| (n % 4 == 0) */
+int dwn_split3(const float* src, void* dst, long n, void* stream);
 
 /* ---- stem (dwiseneuro.py:306-309) + positional encoding (:147-192) --------------------------------- */
 int dwn_input_moments(const float* x, int B, int cin, long plane, double* partial, int P, double* mom, void* stream);
@@ -76,7 +82,7 @@ int dwn_tdw_fwd(const void* in, const float* coef, const float* wgt, void* out, 
 
 /* ---- squeeze-excite (dwiseneuro.py:25-43) ---------------------------------------------------------------- */
 int dwn_se_pool(const void* in, const float* coef, void* act, float* partial, int J, int B, int Nsp, int C, int dtype,
-                void* stream);
+                void* stream);   /* dtype 2: fp32 in, act = three bf16 planes [3][ceil8(B*Nsp*C)] (dwn_split3 layout) */
 int dwn_se_mlp(const float* partial, int J, int Nsp, const float* w1, const float* b1, const float* w2, const float* b2,
                float* mean_out, float* hpre_out, float* gate_out, int B, int C, int RD, void* stream);
 int dwn_fold_gate(const float* w, const float* gate, void* out, int B, int N, int K, int dtype, void* stream);
@@ -143,7 +149,10 @@ int dwn_cortex_in_bwd(const float* dXc, const float* dOut, const float* xin, con
 /* ==== conv_pw algebra (dwiseneuro.py:90-93): BatchNorm statistics of E = X W^T from the Gram matrix of X, and the
  * BatchNorm backward folded into the dgrad / wgrad GEMMs (no pass over E) ================================== */
 int dwn_partial_colsum(const float* partial, int P, int NQ, int q, int C, float* out, void* stream);
-int dwn_pw_stats(const float* gram, const float* sx, const void* w_bf16, double count, const float* gamma,
+/* split-K partials part[Z][ci][ci] -> gram (raw, fp64-accumulated) and cgram = gram/count - mu mu^T (centred in fp64) */
+int dwn_gram_finalize(const float* part, int Z, int ci, const float* sx, double count, float* gram, float* cgram,
+                      void* stream);
+int dwn_pw_stats(const float* cgram, const float* sx, const void* w_bf16, double count, const float* gamma,
                  const float* beta, float* rmean, float* rvar, long long* nbt, float momentum, float eps, float* coef,
                  int mid, int ci, void* stream);
 int dwn_pw_bwd_prep(const float* coef, const float* bcoef, const void* w_bf16, void* wprime, void* negq, float* r,

@@ -23,6 +23,7 @@ class GemmDesc(C.Structure):
         ("n_out_total", C.c_int), ("row_offset_per_z", C.c_int), ("block_n", C.c_int),
         ("A2", C.c_void_p), ("B2", C.c_void_p), ("lda2", C.c_long), ("ldb2", C.c_long), ("K2", C.c_int),
         ("dbg_lbo_a", C.c_uint), ("dbg_sbo_a", C.c_uint), ("dbg_lbo_b", C.c_uint), ("dbg_sbo_b", C.c_uint),
+        ("split", C.c_int), ("a_pstride", C.c_long), ("b_pstride", C.c_long),
     ]
 
 
@@ -45,6 +46,7 @@ SIGNATURES = {
     "dwn_cortex_out": "ppppppp" + "iiiiii" + "p",
     "dwn_readout_prep": "pppp" + "iiii" + "p",
     "dwn_cast_bf16": "pplp",
+    "dwn_split3": "pplp",
     # backward
     "dwn_bn_bwd_finalize": "piiidpppip",
     "dwn_block_bwd_reduce": "ppppppp" + "iiiiiiiii" + "p",
@@ -82,6 +84,7 @@ SIGNATURES = {
     "dwn_scatter_mouse_targets": "pp" + "i" + "p" + "iiii" + "p",
     # conv_pw algebra (Gram statistics, BN1-backward folded into GEMMs)
     "dwn_partial_colsum": "piiiipp",
+    "dwn_gram_finalize": "piipdppp",
     "dwn_pw_stats": "pppdpppppffpiip",
     "dwn_pw_bwd_prep": "ppppppp" + "ii" + "p",
     "dwn_pw_wgrad_finalize": "ppppppp" + "ii" + "p",

@@ -319,24 +319,40 @@ sdw_fwd_kernel(const T* __restrict__ in, const float* __restrict__ coef, const f
     const int p = t / nb, ho0 = (t % nb) * THO;
     const int hi0 = ho0 * S - 1;
     __syncthreads();  // previous compute done before overwriting the tile
-#pragma unroll 2
-    for (int i = tid; i < nvec; i += nthr) {
-      int r, wq;
-      if (wsh >= 0) { r = i >> (wsh + cvsh); wq = (i >> cvsh) & (W - 1); }
-      else { r = i / (W * cvn); wq = (i / cvn) % W; }
-      const int hi = hi0 + r;
-      float v[V];
-      if (hi >= 0 && hi < H) {
-        ldv(in + (((long)p * H + hi) * W + wq) * C + c0 + lcv * V, v);
+    // batches of UB vectors per thread: all global loads of a batch are issued before the first use, so a tile costs
+    // nvec / (nthr * UB) exposed load latencies instead of nvec / (2 * nthr) (the fp32 launches ran at 1.5 TB/s)
+    constexpr int UB = 32 / V;
+    for (int i0 = tid; i0 < nvec; i0 += nthr * UB) {
+      float v[UB][V];
+      int dsto[UB];
 #pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = BnSilu<T>::act(v[j], lp0[j], lp1[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = 0.f;
+      for (int u = 0; u < UB; ++u) {
+        const int i = i0 + u * nthr;
+        dsto[u] = -1;
+        if (i < nvec) {
+          int r, wq;
+          if (wsh >= 0) { r = i >> (wsh + cvsh); wq = (i >> cvsh) & (W - 1); }
+          else { r = i / (W * cvn); wq = (i / cvn) % W; }
+          const int hi = hi0 + r;
+          dsto[u] = (r * WP + wq + 1) * CC + lcv * V;
+          if (hi >= 0 && hi < H) {
+            ldv(in + (((long)p * H + hi) * W + wq) * C + c0 + lcv * V, v[u]);
+          } else {
+            dsto[u] = -2 - dsto[u];  // outside the image: store zeros (padding applies after the activation)
+          }
+        }
       }
-      float* dst = tile + ((r * WP + wq + 1) * CC + lcv * V);
 #pragma unroll
-      for (int j = 0; j < V; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int u = 0; u < UB; ++u) {
+        if (dsto[u] == -1) continue;
+        const bool inside = dsto[u] >= 0;
+        float* dst = tile + (inside ? dsto[u] : -2 - dsto[u]);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[u][j] = inside ? BnSilu<T>::act(v[u][j], lp0[j], lp1[j]) : 0.f;
+#pragma unroll
+        for (int j = 0; j < V; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(v[u][j], v[u][j + 1], v[u][j + 2], v[u][j + 3]);
+      }
     }
     __syncthreads();
     float R[3][3][4];
@@ -601,7 +617,9 @@ extern "C" int dwn_tdw_fwd(const void* in, const float* coef, const float* wgt, 
 // =================================================================================================
 template <typename T>
 __global__ void se_pool_kernel(const T* __restrict__ in, const float* __restrict__ coef, T* __restrict__ act,
-                               float* __restrict__ partial, int Nsp, int C, int cvc) {
+                               float* __restrict__ partial, int Nsp, int C, int cvc, long pstride) {
+  // pstride > 0 (fp32 only): `act` receives the three bf16 planes of a (hi, mid, lo; dwn_split3 layout, planes pstride
+  // elements apart) instead of fp32 values — the A operand of the fp32-accurate tensor-core projection GEMM
   constexpr int V = VecT<T>::V;
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
@@ -622,7 +640,22 @@ __global__ void se_pool_kernel(const T* __restrict__ in, const float* __restrict
     ldv(in + base + (long)r * C, v);
 #pragma unroll
     for (int j = 0; j < V; ++j) v[j] = BnSilu<T>::act(v[j], q0[j], q1[j]);
-    stv(act + base + (long)r * C, v);
+    if (sizeof(T) == 4 && pstride > 0) {
+      bf16* pl = reinterpret_cast<bf16*>(act) + base + (long)r * C;
+      float h[4], m[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+        const float r1 = v[j] - h[j];
+        m[j] = __bfloat162float(__float2bfloat16_rn(r1));
+        l[j] = r1 - m[j];
+      }
+      *reinterpret_cast<uint2*>(pl) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+      *reinterpret_cast<uint2*>(pl + pstride) = make_uint2(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]));
+      *reinterpret_cast<uint2*>(pl + 2 * pstride) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+    } else {
+      stv(act + base + (long)r * C, v);
+    }
 #pragma unroll
     for (int j = 0; j < V; ++j) st[0][j] += v[j];
   }
@@ -704,17 +737,18 @@ extern "C" int dwn_se_pool(const void* in, const float* coef, void* act, float* 
     DWN_LAUNCH_CHECK();
     return 0;
   }
-  if (dtype == DWN_DT_F32) {
+  if (dtype == DWN_DT_F32 || dtype == 2) {  // 2: fp32 input, output = three bf16 planes (see se_pool_kernel)
     int cvc = dwn_largest_divisor_le(C / 4, 64), ln = 256 / cvc;
     dim3 grid(J, (C / 4) / cvc, B), block(cvc * ln);
+    const long n = (long)B * Nsp * C;
     se_pool_kernel<float><<<grid, block, block.x * 4 * sizeof(float), st>>>((const float*)in, coef, (float*)act, partial,
-                                                                           Nsp, C, cvc);
+                                                                           Nsp, C, cvc, dtype == 2 ? (n + 7) / 8 * 8 : 0);
   } else {
     DWN_REQUIRE(C % 8 == 0, "dwn_se_pool: C %% 8 != 0");
     int cvc = dwn_largest_divisor_le(C / 8, 64), ln = 256 / cvc;
     dim3 grid(J, (C / 8) / cvc, B), block(cvc * ln);
     se_pool_kernel<bf16><<<grid, block, block.x * 8 * sizeof(float), st>>>((const bf16*)in, coef, (bf16*)act, partial,
-                                                                          Nsp, C, cvc);
+                                                                          Nsp, C, cvc, 0);
   }
   DWN_LAUNCH_CHECK();
   return 0;
@@ -1059,6 +1093,38 @@ extern "C" int dwn_cast_bf16(const float* in, void* out, long n, void* stream) {
   if (gx > 4096) gx = 4096;
   if (gx < 1) gx = 1;
   cast_kernel<bf16><<<gx, 256, 0, (cudaStream_t)stream>>>(in, (bf16*)out, n);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// fp32 -> three bf16 planes (hi, mid, lo): x = hi + mid + lo up to 2^-25 |x|.  Operands of the fp32-accurate tensor-core
+// GEMM (dwn_gemm split = 3).  The residuals x - hi and x - hi - mid are exact in fp32.
+__global__ void __launch_bounds__(256) split3_kernel(const float4* __restrict__ in, uint2* __restrict__ p0,
+                                                     uint2* __restrict__ p1, uint2* __restrict__ p2, long n4) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = __ldcs(in + i);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    float h[4], m[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __bfloat162float(__float2bfloat16_rn(x[j]));
+      const float r1 = x[j] - h[j];
+      m[j] = __bfloat162float(__float2bfloat16_rn(r1));
+      l[j] = r1 - m[j];
+    }
+    p0[i] = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+    p1[i] = make_uint2(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]));
+    p2[i] = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+  }
+}
+extern "C" int dwn_split3(const float* src, void* dst, long n, void* stream) {
+  DWN_REQUIRE(n % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "dwn_split3: n %% 4 != 0 or misaligned");
+  const long n4 = n / 4;
+  long gx = (n4 + 255) / 256;
+  if (gx > 148 * 16) gx = 148 * 16;
+  if (gx < 1) gx = 1;
+  uint2* d = (uint2*)dst;
+  split3_kernel<<<(int)gx, 256, 0, (cudaStream_t)stream>>>((const float4*)src, d, d + n4, d + 2 * n4, n4);
   DWN_LAUNCH_CHECK();
   return 0;
 }

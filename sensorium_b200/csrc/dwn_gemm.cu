@@ -149,8 +149,19 @@ constexpr int GT_STAGING_BYTES = GT_EPI_WARPS * 32 * GT_STAGE_PITCH;
 constexpr int GT_THREADS = 64 + 32 * GT_EPI_WARPS;   // warp0 TMA, warp1 MMA, warps2.. epilogue
 static_assert(GT_STAGE_PITCH == 272, "store_subtile() assumes the 272-byte staging pitch");
 
+constexpr int GT_MAX_SEG = 6;
+// Operand maps of one launch.  The K loop runs over up to GT_MAX_SEG "segments" (a_map, b_map, K): one for a plain GEMM,
+// two for the dual-K form (D = A B^T + A2 B2^T), six for the fp32-accurate 3-way bf16 split (planes hi/mid/lo of both
+// operands, products lo*hi, mid*mid, hi*lo, mid*hi, hi*mid, hi*hi accumulated into the same fp32 TMEM tile).
+struct alignas(64) GemmMaps {
+  CUtensorMap a[3];
+  CUtensorMap b[3];
+};
+
 struct GemmTcParams {
-  int K, K2, block_n, b_bytes, stages;  // K2 > 0: D += A2 (MxK2) * B2^T (second operand pair, same majors)
+  int block_n, b_bytes, stages;
+  int nseg, seg_k[GT_MAX_SEG];
+  signed char seg_a[GT_MAX_SEG], seg_b[GT_MAX_SEG];
   int num_m_blocks, num_n_blocks, Z;
   int a_zmode, b_zmode, b_batch_rows;
   uint32_t lbo_a, lbo_b;  // debug override of MN-major LBO/SBO (0 = default)
@@ -160,8 +171,7 @@ struct GemmTcParams {
 
 template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(GT_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const GemmTcParams p) {
+gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = GT_A_BYTES + p.b_bytes;
@@ -185,8 +195,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int nk1 = (p.K + GT_BK - 1) / GT_BK;
-  const int num_k_blocks = nk1 + (p.K2 + GT_BK - 1) / GT_BK;
+  int num_k_blocks = 0;
+  for (int sg = 0; sg < p.nseg; ++sg) num_k_blocks += (p.seg_k[sg] + GT_BK - 1) / GT_BK;
   const int total_tiles = p.num_m_blocks * p.num_n_blocks * p.Z;
 
   if (warp == 0 && lane == 0) {
@@ -199,28 +209,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int z = tile / (p.num_n_blocks * p.num_m_blocks);
       const int za = p.a_zmode == 1 ? z : 0;
       const int zb = p.b_zmode == 1 ? z : (p.b_zmode == 2 ? (m_blk * GT_BM) / p.b_batch_rows : 0);
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + (size_t)stage * stage_bytes;
-        uint8_t* sb = sa + GT_A_BYTES;
-        mbar_expect_tx(&full_bar[stage], (uint32_t)(GT_A_BYTES + p.block_n * GT_BK * 2));
-        const bool second = kb >= nk1;
-        const CUtensorMap* ma = second ? &mapA2 : &mapA;
-        const CUtensorMap* mb = second ? &mapB2 : &mapB;
-        const int k0 = (second ? kb - nk1 : kb) * GT_BK;
-        if (A_MN) {
-          tma_load_3d(sa, ma, &full_bar[stage], m_blk * GT_BM, k0, za);
-          tma_load_3d(sa + 8192, ma, &full_bar[stage], m_blk * GT_BM + 64, k0, za);
-        } else {
-          tma_load_3d(sa, ma, &full_bar[stage], k0, m_blk * GT_BM, za);
+      for (int sg = 0; sg < p.nseg; ++sg) {
+        const CUtensorMap* ma = &maps.a[p.seg_a[sg]];
+        const CUtensorMap* mb = &maps.b[p.seg_b[sg]];
+        const int nk = (p.seg_k[sg] + GT_BK - 1) / GT_BK;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + GT_A_BYTES;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)(GT_A_BYTES + p.block_n * GT_BK * 2));
+          const int k0 = kb * GT_BK;
+          if (A_MN) {
+            tma_load_3d(sa, ma, &full_bar[stage], m_blk * GT_BM, k0, za);
+            tma_load_3d(sa + 8192, ma, &full_bar[stage], m_blk * GT_BM + 64, k0, za);
+          } else {
+            tma_load_3d(sa, ma, &full_bar[stage], k0, m_blk * GT_BM, za);
+          }
+          if (B_MN) {
+            for (int j = 0; j < p.block_n / 64; ++j)
+              tma_load_3d(sb + j * 8192, mb, &full_bar[stage], n_blk * p.block_n + j * 64, k0, zb);
+          } else {
+            tma_load_3d(sb, mb, &full_bar[stage], k0, n_blk * p.block_n, zb);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        if (B_MN) {
-          for (int j = 0; j < p.block_n / 64; ++j)
-            tma_load_3d(sb + j * 8192, mb, &full_bar[stage], n_blk * p.block_n + j * 64, k0, zb);
-        } else {
-          tma_load_3d(sb, mb, &full_bar[stage], k0, n_blk * p.block_n, zb);
-        }
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -444,8 +456,6 @@ static int gemm_tc(const dwn_gemm_desc* d, cudaStream_t st) {
   DWN_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0 && d->Z > 0, "dwn_gemm: empty problem");
   GemmTcParams p;
   memset(&p, 0, sizeof(p));
-  p.K = d->K;
-  p.K2 = d->A2 ? d->K2 : 0;
   p.block_n = d->block_n > 0 ? d->block_n : pick_block_n(d->N, d->b_mn, d->d_dtype == DWN_DT_BF16, d->epi);
   DWN_REQUIRE(p.block_n % 16 == 0 && p.block_n <= 256 && (!d->b_mn || p.block_n % 64 == 0), "dwn_gemm: bad block_n %d",
               p.block_n);
@@ -469,17 +479,35 @@ static int gemm_tc(const dwn_gemm_desc* d, cudaStream_t st) {
   DWN_REQUIRE(p.stages >= 2, "dwn_gemm: smem budget");
   const size_t smem = 1024 + (size_t)p.stages * (GT_A_BYTES + p.b_bytes) + GT_STAGING_BYTES + 256;
 
-  CUtensorMap mapA, mapB;
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
   const int za = d->a_zmode == 1 ? d->Z : 1;
   int zb = d->b_zmode == 1 ? d->Z : 1;
   if (d->b_zmode == 2) zb = (d->M + p.b_batch_rows - 1) / p.b_batch_rows;
-  if (make_operand_map(&mapA, d->A, d->a_mn, d->M, d->K, d->lda, d->a_zstride, za, GT_BM)) return -1;
-  if (make_operand_map(&mapB, d->B, d->b_mn, d->N, d->K, d->ldb, d->b_zstride, zb, p.block_n)) return -1;
-  CUtensorMap mapA2 = mapA, mapB2 = mapB;
-  if (p.K2 > 0) {
-    DWN_REQUIRE(d->B2 != nullptr, "dwn_gemm: A2 given without B2");
-    if (make_operand_map(&mapA2, d->A2, d->a_mn, d->M, d->K2, d->lda2, d->a_zstride, za, GT_BM)) return -1;
-    if (make_operand_map(&mapB2, d->B2, d->b_mn, d->N, d->K2, d->ldb2, d->b_zstride, zb, p.block_n)) return -1;
+  if (make_operand_map(&maps.a[0], d->A, d->a_mn, d->M, d->K, d->lda, d->a_zstride, za, GT_BM)) return -1;
+  if (make_operand_map(&maps.b[0], d->B, d->b_mn, d->N, d->K, d->ldb, d->b_zstride, zb, p.block_n)) return -1;
+  p.nseg = 1;
+  p.seg_k[0] = d->K;
+  if (d->split == 3) {
+    // fp32-accurate product from three bf16 planes per operand (x = hi + mid + lo, 8 mantissa bits each): the six
+    // products whose magnitude is >= 2^-16 of hi*hi, smallest first
+    DWN_REQUIRE(d->A2 == nullptr, "dwn_gemm: split and dual-K are exclusive");
+    DWN_REQUIRE(d->a_pstride % 8 == 0 && d->b_pstride % 8 == 0, "dwn_gemm: plane strides must be multiples of 8");
+    for (int pl = 1; pl < 3; ++pl) {
+      if (make_operand_map(&maps.a[pl], (const bf16*)d->A + (size_t)pl * d->a_pstride, d->a_mn, d->M, d->K, d->lda,
+                           d->a_zstride, za, GT_BM)) return -1;
+      if (make_operand_map(&maps.b[pl], (const bf16*)d->B + (size_t)pl * d->b_pstride, d->b_mn, d->N, d->K, d->ldb,
+                           d->b_zstride, zb, p.block_n)) return -1;
+    }
+    static const signed char sa[6] = {2, 1, 0, 1, 0, 0}, sb[6] = {0, 1, 2, 0, 1, 0};
+    p.nseg = 6;
+    for (int i = 0; i < 6; ++i) { p.seg_a[i] = sa[i]; p.seg_b[i] = sb[i]; p.seg_k[i] = d->K; }
+  } else if (d->A2) {
+    DWN_REQUIRE(d->B2 != nullptr && d->K2 > 0, "dwn_gemm: A2 given without B2 / K2");
+    if (make_operand_map(&maps.a[1], d->A2, d->a_mn, d->M, d->K2, d->lda2, d->a_zstride, za, GT_BM)) return -1;
+    if (make_operand_map(&maps.b[1], d->B2, d->b_mn, d->N, d->K2, d->ldb2, d->b_zstride, zb, p.block_n)) return -1;
+    p.nseg = 2;
+    p.seg_a[1] = 1; p.seg_b[1] = 1; p.seg_k[1] = d->K2;
   }
 
   const int total = p.num_m_blocks * p.num_n_blocks * p.Z;
@@ -489,7 +517,7 @@ static int gemm_tc(const dwn_gemm_desc* d, cudaStream_t st) {
   {                                                                                               \
     auto k = gemm_tc_kernel<AM, BM>;                                                              \
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
-    k<<<grid, GT_THREADS, smem, st>>>(mapA, mapB, mapA2, mapB2, p);                                             \
+    k<<<grid, GT_THREADS, smem, st>>>(maps, p);                                                   \
   }
   if (d->a_mn) { if (d->b_mn) LAUNCH(1, 1) else LAUNCH(1, 0) } else { if (d->b_mn) LAUNCH(0, 1) else LAUNCH(0, 0) }
 #undef LAUNCH
@@ -516,7 +544,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmSimtParams p) 
   __shared__ __align__(16) float Bs[16][68];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64, z = blockIdx.z;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64, z = blockIdx.z;  // M on grid.x: no 65535 limit
   const int za = p.a_zmode == 1 ? z : 0;
   const int zb = p.b_zmode == 1 ? z : (p.b_zmode == 2 ? m0 / p.b_batch_rows : 0);
   const float* A = p.A + (long)za * p.a_zs;
@@ -601,7 +629,8 @@ static int gemm_simt(const dwn_gemm_desc* d, cudaStream_t st) {
   if (d->b_zmode == 2) DWN_REQUIRE(p.b_batch_rows % 64 == 0, "dwn_gemm(simt): b_batch_rows %% 64 != 0");
   fill_epi(p.e, d);
   DWN_REQUIRE(d->d_dtype == DWN_DT_F32 || d->epi == 1, "dwn_gemm(simt): D must be fp32");
-  dim3 grid((d->N + 63) / 64, (d->M + 63) / 64, d->Z);
+  dim3 grid((d->M + 63) / 64, (d->N + 63) / 64, d->Z);
+  DWN_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "dwn_gemm(simt): N or Z too large");
   gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
   DWN_LAUNCH_CHECK();
   return 0;

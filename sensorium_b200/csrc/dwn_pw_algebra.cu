@@ -30,8 +30,49 @@ extern "C" int dwn_partial_colsum(const float* partial, int P, int NQ, int q, in
   return 0;
 }
 
+// Gram matrix from its split-K partials: gram[j][k] = sum_z part[z][j][k] (fp64 accumulation) and the CENTRED second
+// moment cgram[j][k] = gram[j][k]/M - mu_j mu_k formed in fp64 entry by entry (mu = sx/M), stored in fp32: the
+// cancellation of E[x x^T] - mu mu^T happens here, in double, so the quadratic forms of pw_stats_kernel are benign.
+// block = 32 entries x 32 z-slices
+__global__ void __launch_bounds__(1024) gram_finalize_kernel(const float* __restrict__ part, int Z, int ci,
+                                                            const float* __restrict__ sx, double count,
+                                                            float* __restrict__ gram, float* __restrict__ cgram) {
+  __shared__ double sred[32][33];
+  const int el = threadIdx.x & 31, zl = threadIdx.x >> 5;
+  const long n = (long)ci * ci;
+  const long i = (long)blockIdx.x * 32 + el;
+  double a = 0.0;
+  if (i < n) {
+    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+    int z = zl;
+    for (; z + 96 < Z; z += 128) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a4[u] += (double)part[(long)(z + 32 * u) * n + i];
+    }
+    for (; z < Z; z += 32) a4[0] += (double)part[(long)z * n + i];
+    a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+  }
+  sred[zl][el] = a;
+  __syncthreads();
+  if (zl != 0 || i >= n) return;
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < 32; ++q) s += sred[q][el];
+  const int j = (int)(i / ci), k = (int)(i % ci);
+  const double inv_m = 1.0 / count;
+  gram[i] = (float)s;
+  cgram[i] = (float)(s * inv_m - ((double)sx[j] * inv_m) * ((double)sx[k] * inv_m));
+}
+extern "C" int dwn_gram_finalize(const float* part, int Z, int ci, const float* sx, double count, float* gram,
+                                 float* cgram, void* stream) {
+  const long n = (long)ci * ci;
+  gram_finalize_kernel<<<(int)((n + 31) / 32), 1024, 0, (cudaStream_t)stream>>>(part, Z, ci, sx, count, gram, cgram);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
 // one warp per output channel c of conv_pw
-__global__ void __launch_bounds__(256) pw_stats_kernel(const float* __restrict__ gram, const float* __restrict__ sx,
+__global__ void __launch_bounds__(256) pw_stats_kernel(const float* __restrict__ cgram, const float* __restrict__ sx,
                                                       const bf16* __restrict__ w, double count,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       float* __restrict__ rmean, float* __restrict__ rvar,
@@ -49,30 +90,26 @@ __global__ void __launch_bounds__(256) pw_stats_kernel(const float* __restrict__
   double m1 = 0;
   for (int k = lane; k < ci; k += 32) m1 += (double)wc[k] * (double)sx[k];
   m1 = warp_sum_d(m1);
-  // var = w^T C w with the CENTRED second moment C = Gx/M - mu mu^T formed in fp64 entry by entry (never the
-  // difference of two large quadratic forms): every lane accumulates its column slice of each row, four rows in
-  // flight to hide L2 latency
+  // var = w^T C w on the centred second moment C (gram_finalize_kernel): every lane accumulates its column slice of each
+  // row, four rows in flight to hide L2 latency; rows are combined in fp64
   double q = 0;
   for (int j0 = 0; j0 < ci; j0 += 4) {
-    double v[4] = {0.0, 0.0, 0.0, 0.0};
-    double muj[4];
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) muj[jj] = j0 + jj < ci ? (double)sx[j0 + jj] * inv_m : 0.0;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
     for (int k = lane; k < ci; k += 32) {
-      const double wk = (double)wc[k], muk = (double)sx[k] * inv_m;
+      const float wk = wc[k];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj)
-        if (j0 + jj < ci) v[jj] = fma((double)gram[(long)(j0 + jj) * ci + k] * inv_m - muj[jj] * muk, wk, v[jj]);
+        if (j0 + jj < ci) v[jj] = fmaf(cgram[(long)(j0 + jj) * ci + k], wk, v[jj]);
     }
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
-      if (j0 + jj < ci) q += (double)wc[j0 + jj] * v[jj];
+      if (j0 + jj < ci) q += (double)wc[j0 + jj] * (double)v[jj];
   }
   q = warp_sum_d(q);
   if (lane != 0) return;
   const double mean = m1 * inv_m;
   double var = q;
-  if (var < 0) var = 0;  // guard only: C is positive semi-definite up to the rounding of Gx
+  if (var < 0) var = 0;  // guard only: C is positive semi-definite up to rounding
   const double rstd = 1.0 / sqrt(var + (double)eps);
   const double g = gamma[c], b = beta[c];
   coef[c] = (float)(g * rstd);
@@ -85,11 +122,11 @@ __global__ void __launch_bounds__(256) pw_stats_kernel(const float* __restrict__
     rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
   }
 }
-extern "C" int dwn_pw_stats(const float* gram, const float* sx, const void* w_bf16, double count, const float* gamma,
+extern "C" int dwn_pw_stats(const float* cgram, const float* sx, const void* w_bf16, double count, const float* gamma,
                             const float* beta, float* rmean, float* rvar, long long* nbt, float momentum, float eps,
                             float* coef, int mid, int ci, void* stream) {
   pw_stats_kernel<<<(mid + 7) / 8, 256, 8 * ci * sizeof(float), (cudaStream_t)stream>>>(
-      gram, sx, (const bf16*)w_bf16, count, gamma, beta, rmean, rvar, nbt, momentum, eps, coef, mid, ci);
+      cgram, sx, (const bf16*)w_bf16, count, gamma, beta, rmean, rvar, nbt, momentum, eps, coef, mid, ci);
   DWN_LAUNCH_CHECK();
   return 0;
 }

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import math
 import weakref
+from functools import partial as _partial
 from types import SimpleNamespace
 from typing import Dict, List, Optional
 
@@ -79,6 +80,52 @@ def _shadow(p: torch.Tensor) -> torch.Tensor:
 def set_shadow(p: torch.Tensor, sh: torch.Tensor) -> None:
     """Used by the fused optimizer, which writes the bf16 shadow itself."""
     p._dwn_shadow = (p._version, sh, p.data_ptr())
+
+
+# fp32 mode, eval (val_step / predict, argus_models.py:73-99): run the GEMMs on the tensor cores with fp32 accuracy — every
+# fp32 operand is split into three bf16 planes (dwn_split3) and the six significant plane products are accumulated in the
+# fp32 TMEM tile (dwn_gemm split = 3).  Training in fp32 mode keeps the FFMA GEMM.
+FP32_TENSOR_CORES = True
+
+
+def _planes(t: torch.Tensor, st) -> torch.Tensor:
+    n = t.numel()
+    pl = torch.empty((3, (n + 7) // 8 * 8), dtype=torch.bfloat16, device=t.device)
+    call("dwn_split3", t, pl, n, st)
+    if pl.shape[1] != n:
+        raise RuntimeError("split operand size must be a multiple of 8")
+    return pl
+
+
+def _param_planes(p: torch.Tensor, st) -> torch.Tensor:
+    """Split planes of a weight, cached like the bf16 shadows (version + storage + raw-write generation)."""
+    key = (p._version, p.data_ptr(), _GEN[0], str(p.device))
+    ent = getattr(p, "_dwn_planes", None)
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    pl = _planes(p.detach(), st)
+    p._dwn_planes = (key, pl)
+    return pl
+
+
+def gemm_f32(st, training: bool, a_param=None, b_param=None, a_planes=None, **kw):
+    """fp32-mode GEMM: tensor cores with split operands in eval mode when the shapes allow TMA (multiples of 8),
+    FFMA otherwise.  ``a_param`` / ``b_param``: the parameter an operand IS (its split planes are cached);
+    ``a_planes``: A already is a plane triple written by its producer."""
+    A, B = kw["A"], kw["B"]
+    if a_planes is not None:
+        pb = _planes(B, st)
+        return gemm(st, **dict(kw, A=a_planes, B=pb, dtype=BF16, split=3, a_pstride=a_planes.shape[1],
+                               b_pstride=pb.shape[1]))
+    ok = (FP32_TENSOR_CORES and not training and kw.get("A2") is None and kw["K"] % 8 == 0 and kw["lda"] % 8 == 0
+          and kw["ldb"] % 8 == 0 and kw.get("a_zstride", 0) % 8 == 0 and kw.get("b_zstride", 0) % 8 == 0
+          and A.numel() % 8 == 0 and B.numel() % 8 == 0 and A.is_contiguous() and B.is_contiguous())
+    if not ok:
+        return gemm(st, **kw)
+    pa = _param_planes(a_param, st) if a_param is not None else _planes(A, st)
+    pb = _param_planes(b_param, st) if b_param is not None else _planes(B, st)
+    kw = dict(kw, A=pa, B=pb, dtype=BF16, split=3, a_pstride=pa.shape[1], b_pstride=pb.shape[1])
+    return gemm(st, **kw)
 
 
 _side = {}
@@ -162,11 +209,12 @@ def _split_k(rows: int, tiles: int) -> int:
     return z
 
 
-def _gram(xb, M, ci, st, dev, out=None):
-    """Gx = X^T X (ci x ci, fp32) of the bf16 block input via a split-K (MN,MN) tcgen05 GEMM."""
+def _gram(xb, M, ci, sx, st, dev, out=None):
+    """Gx = X^T X (ci x ci, fp32) of the bf16 block input via a split-K (MN,MN) tcgen05 GEMM; returns (Gx, centred
+    second moment Gx/M - mu mu^T) with mu = sx / M."""
     # short accumulation chains: the tensor core adds every K=16 slice into the fp32 TMEM accumulator with truncation,
-    # a bias that grows with the chain length (3.9e-4 on rstd at 16 k rows per split, measured); 2048 rows per split
-    # keep the Gram-derived statistics within 1e-4 of the direct ones at M = 2.1 M (tests/test_parity_fullsize_gpu.py)
+    # a bias that grows with the chain length; 2048 rows per split keep the Gram-derived statistics within 1e-4 of the
+    # direct ones at M = 2.1 M (tests/test_parity_fullsize_gpu.py::test_gram_batchnorm_statistics_full_rows)
     zs = 1
     while M % (zs * 2) == 0 and M // (zs * 2) >= 2048:
         zs *= 2
@@ -176,8 +224,9 @@ def _gram(xb, M, ci, st, dev, out=None):
          a_zmode=1, b_zmode=1, M=ci, N=ci, K=rows, Z=zs, D=part, d_dtype=F32, ldd=ci, d_zstride=ci * ci, _tag="gram",
          _bytes=M * ci * 2)
     g = _empty((ci, ci), torch.float32, dev) if out is None else out
-    call("dwn_reduce_rows", part, zs, ci * ci, g, st)
-    return g
+    cg = _empty((ci, ci), torch.float32, dev)
+    call("dwn_gram_finalize", part, zs, ci, sx, float(M), g, cg, st)
+    return g, cg
 
 
 _stats_side: Dict[int, "torch.cuda.Stream"] = {}
@@ -286,12 +335,13 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
             _fork(stats_side, dev)
             with torch.cuda.stream(stats_side[0]) if stats_side else _nullctx():
                 sst = _stream(dev)
-                _gram(Xb, Mi, ci, sst, dev, out=gram)
                 call("dwn_partial_colsum", sc_part, _P, 3, 2, ci, sx, sst)
-                call("dwn_pw_stats", gram, sx, wsh, float(Mi), bn1.weight, bn1.bias, bn1.running_mean,
+                _, cgram = _gram(Xb, Mi, ci, sx, sst, dev, out=gram)
+                call("dwn_pw_stats", cgram, sx, wsh, float(Mi), bn1.weight, bn1.bias, bn1.running_mean,
                      bn1.running_var, bn1.num_batches_tracked, BN_MOM, BN_EPS, coef1, mid, ci, sst)
-        gemm(st, dtype=dcode, A=Xb if bf else X, B=wsh, lda=ci, ldb=ci, M=Mi, N=mid, K=ci, Z=1,
-             D=E, d_dtype=dcode, ldd=mid, _tag="pw_fwd", _bytes=(Mi * ci + mid * ci + Mi * mid) * es)
+        (gemm if bf else _partial(gemm_f32, training=training, b_param=wpw))(
+            st, dtype=dcode, A=Xb if bf else X, B=wsh, lda=ci, ldb=ci, M=Mi, N=mid, K=ci, Z=1,
+            D=E, d_dtype=dcode, ldd=mid, _tag="pw_fwd", _bytes=(Mi * ci + mid * ci + Mi * mid) * es)
         if gram is not None:
             _join(stats_side, dev)
         else:
@@ -310,11 +360,18 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
              _tag="tdw_fwd", _bytes=2 * Mo * mid * es)
         coef3 = _bn_coef(blk.temp_covn_dw[1].bn, part, _P, Mo, mid, 0, training, st, dev)
         # 4. squeeze-excite: a = SiLU(BN3(Tm)), gate folded into per-sample projection weights
-        A = _empty((Mo, mid), adt, dev)
         rd = blk.se.conv_reduce.weight.shape[0]
         pool_part = _empty((B, _J_SE, mid), torch.float32, dev)
-        call("dwn_se_pool", Tm, coef3, A, pool_part, _J_SE, B, Nsp, mid, dcode, st, _tag="se_pool",
-             _bytes=2 * Mo * mid * es)
+        # fp32 eval: the squeeze kernel writes the three bf16 planes of a directly (operand of the split GEMM)
+        a_planes = (not bf) and (not training) and FP32_TENSOR_CORES and mid % 8 == 0 and (Mo * mid) % 8 == 0
+        if a_planes:
+            A = _empty((3, Mo * mid), torch.bfloat16, dev)
+            call("dwn_se_pool", Tm, coef3, A, pool_part, _J_SE, B, Nsp, mid, 2, st, _tag="se_pool",
+                 _bytes=Mo * mid * 10)
+        else:
+            A = _empty((Mo, mid), adt, dev)
+            call("dwn_se_pool", Tm, coef3, A, pool_part, _J_SE, B, Nsp, mid, dcode, st, _tag="se_pool",
+                 _bytes=2 * Mo * mid * es)
         mean = _empty((B, mid), torch.float32, dev)
         hpre = _empty((B, rd), torch.float32, dev)
         gate = _empty((B, mid), torch.float32, dev)
@@ -324,9 +381,10 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         call("dwn_fold_gate", blk.conv_pwl[0].weight, gate, Wb, B, co, mid, dcode, st)
         # 5. point-wise linear projection, batched over samples (B operand = gated weights of the sample)
         Y = _empty((Mo, co), adt, dev)
-        gemm(st, dtype=dcode, A=A, B=Wb, lda=mid, ldb=mid, a_zstride=Nsp * mid, b_zstride=co * mid, a_zmode=1,
-             b_zmode=1, M=Nsp, N=co, K=mid, Z=B, D=Y, d_dtype=dcode, ldd=co, d_zstride=Nsp * co, _tag="pwl_fwd",
-             _bytes=(Mo * mid + B * co * mid + Mo * co) * es)
+        (gemm if bf else _partial(gemm_f32, training=training, a_planes=A if a_planes else None))(
+            st, dtype=dcode, A=A, B=Wb, lda=mid, ldb=mid, a_zstride=Nsp * mid, b_zstride=co * mid, a_zmode=1,
+            b_zmode=1, M=Nsp, N=co, K=mid, Z=B, D=Y, d_dtype=dcode, ldd=co, d_zstride=Nsp * co, _tag="pwl_fwd",
+            _bytes=(Mo * mid + B * co * mid + Mo * co) * es)
         coef4 = _bn_coef(blk.conv_pwl[1].bn, _colstats(Y, Mo, co, co, dcode, st, dev) if training else None, _P, Mo, co,
                          0, training, st, dev)
         coef_sc = _bn_coef(blk.bn_sc.bn, sc_part, _P, Mo, co, ci, training, st, dev, NQ=3)
@@ -363,9 +421,10 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         I, O = layer.in_features, layer.out_features
         wc = layer.conv.weight
         Yc = _empty((Mbt, O), adt, dev)
-        gemm(st, dtype=dcode, A=cxb if bf else cx, B=_shadow(wc) if bf else wc, lda=I, ldb=I // G, a_zstride=I // G,
-             b_zstride=(O // G) * (I // G), a_zmode=1, b_zmode=1, M=Mbt, N=O // G, K=I // G, Z=G, D=Yc, d_dtype=dcode,
-             ldd=O, d_zstride=O // G)
+        (gemm if bf else _partial(gemm_f32, training=training, b_param=wc))(
+            st, dtype=dcode, A=cxb if bf else cx, B=_shadow(wc) if bf else wc, lda=I, ldb=I // G, a_zstride=I // G,
+            b_zstride=(O // G) * (I // G), a_zmode=1, b_zmode=1, M=Mbt, N=O // G, K=I // G, Z=G, D=Yc, d_dtype=dcode,
+            ldd=O, d_zstride=O // G)
         coef = _bn_coef(layer.bn.bn, _colstats(Yc, Mbt, O, O, dcode, st, dev) if training else None, _P, Mbt, O, 0,
                         training, st, dev)
         coef_sc = _bn_coef(layer.bn_sc.bn, _colstats(cx, Mbt, I, I, F32, st, dev) if training else None, _P, Mbt, O, I,
@@ -415,10 +474,11 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
             sst = _stream(dev)
             if prep:
                 call("dwn_readout_prep", cx, mask, xm, xt, Mbt, K, T, dcode, sst)
-            gemm(sst, dtype=dcode, A=wq, B=xm, lda=Kg, ldb=K, a_zstride=half * Kg, b_zstride=Kg, a_zmode=1, b_zmode=1,
-                 M=half, N=Mbt, K=Kg, Z=G, epi=1, D=pred, bias=conv.bias, beta=cfg["softplus_beta"], Tn=T,
-                 n_out_total=n_out, row_offset_per_z=half, n_limit=Mbt, _tag="readout_fwd",
-                 _bytes=G * half * Kg * es + Mbt * K * es + B * n_out * T * 4)
+            (gemm if bf else _partial(gemm_f32, training=training, a_param=conv.weight))(
+                sst, dtype=dcode, A=wq, B=xm, lda=Kg, ldb=K, a_zstride=half * Kg, b_zstride=Kg, a_zmode=1, b_zmode=1,
+                M=half, N=Mbt, K=Kg, Z=G, epi=1, D=pred, bias=conv.bias, beta=cfg["softplus_beta"], Tn=T,
+                n_out_total=n_out, row_offset_per_z=half, n_limit=Mbt, _tag="readout_fwd",
+                _bytes=G * half * Kg * es + Mbt * K * es + B * n_out * T * 4)
         preds.append(pred)
         if save:
             sv.readouts.append(SimpleNamespace(m=m, mask=mask, xm=xm, xt=xt, pred=pred, n_out=n_out, half=half))
