@@ -50,6 +50,13 @@ class MouseModel(_Base):
         self.model_ema: ModelEma | None = None
         self.distill_model: torch.nn.Module | None = None
         self.distill_ratio: float = 0.0
+        # params["cuda_graph"] = True: the whole train step (distillation fill, forward, loss, backward, AdamW, EMA) is
+        # captured once per (shapes, set of mice present) and replayed — ~500 kernel launches become one graph launch
+        self.cuda_graph = bool(params.get("cuda_graph", False))
+        self._graphs: dict = {}
+        self._graph_seen: dict = {}
+        self._graph_pool = None
+        self.max_graphs = 12
 
     # argus_models.py:31-41
     @torch.no_grad()
@@ -105,9 +112,122 @@ class MouseModel(_Base):
 
         return inp, tgt, ready
 
+    # ---------------------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the train step
+    # ---------------------------------------------------------------------------------------------------------
+    def _graph_key(self, batch):
+        """Key of the captured step this batch can replay, or None when the step must run eagerly."""
+        if not (self.cuda_graph and self.iter_size == 1 and self.device.type == "cuda"
+                and isinstance(self.loss, MicePoissonLoss) and isinstance(self.optimizer, FusedAdamW)
+                and getattr(self.nn_module, "_dp", None) is None
+                and getattr(self.nn_module, "_rng_device", None) is None):
+            return None
+        try:
+            x, (t, w) = batch
+        except (TypeError, ValueError):
+            return None
+        if not torch.is_tensor(x) or not torch.is_tensor(w):
+            return None
+        compact = torch.is_tensor(t)
+        n_mice = len(self.nn_module.cfg["readout_outputs"])
+        distill = bool(self.distill_model is not None and self.distill_ratio)
+        if distill:
+            live = (True,) * n_mice
+        elif w.is_cuda:
+            hint = _LIVE_HINTS.get(id(w))          # device-resident batch (DevicePrefetcher registers the hint)
+            if hint is None:
+                return None                        # the set of mice present must be known on the host
+            live = tuple(bool(v) for v in hint)
+        elif compact:
+            present = set(w.tolist())
+            live = tuple(m in present for m in range(n_mice))
+        else:
+            live = tuple((w != 0).any(0).tolist())
+        tshape = tuple(t.shape) if compact else tuple(tuple(v.shape) for v in t)
+        return (tuple(x.shape), tuple(w.shape), str(w.dtype), compact, tshape, live, distill, self.amp,
+                self.model_ema is not None)
+
+    def _capture_step(self, key, batch):
+        from . import _lib
+        x, (t, w) = batch
+        dev = self.device
+        compact, live = key[3], key[5]
+        ent = State()
+        ent.x = torch.empty(x.shape, dtype=x.dtype, device=dev)
+        ent.t = torch.empty(t.shape, dtype=t.dtype, device=dev) if compact else [
+            torch.empty(v.shape, dtype=v.dtype, device=dev) for v in t]
+        ent.w = torch.empty(w.shape, dtype=w.dtype, device=dev)
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        self.optimizer.zero_grad(set_to_none=True)
+        params = [p for p in self.nn_module.parameters()]
+        launches0 = _lib.LAUNCHES
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, pool=self._graph_pool, capture_error_mode="relaxed"):
+            target = (ent.t, ent.w)
+            self.loss.set_live_hint(list(live))
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+                if compact:
+                    target = collate_on_device(ent.t, ent.w, self.nn_module.cfg["readout_outputs"])
+                self.add_distill_predictions(ent.x, target)
+                prediction = self.nn_module(ent.x)
+                loss = self.loss(prediction, target)
+            self.grad_scaler.scale(loss).backward()
+            self.optimizer.step()
+            if self.model_ema is not None:
+                self.model_ema.update(self.nn_module)
+        ent.graph = graph
+        ent.launches = _lib.LAUNCHES - launches0
+        ent.loss = loss.detach()
+        ent.prediction = deep_detach(prediction)
+        ent.target = deep_detach(target)
+        ent.grads = [p.grad for p in params]     # keeps the graph's gradient buffers alive; restored after a replay
+        ent.params = params
+        return ent
+
+    def _replay_step(self, ent, batch, sync: bool = True) -> dict:
+        from . import _lib
+        from .engine import bump_generation
+        x, (t, w) = batch
+        ent.x.copy_(x, non_blocking=True)
+        if torch.is_tensor(t):
+            ent.t.copy_(t, non_blocking=True)
+        else:
+            for d, s_ in zip(ent.t, t):
+                d.copy_(s_, non_blocking=True)
+        ent.w.copy_(w, non_blocking=True)
+        self.optimizer.sync_graph_lr()
+        ent.graph.replay()
+        _lib.LAUNCHES += ent.launches
+        bump_generation()                        # weights / running statistics / EMA changed behind torch's back
+        if self._graph_last is not ent:
+            for p, g in zip(ent.params, ent.grads):
+                p.grad = g
+            self._graph_last = ent
+        prediction = self.prediction_transform(ent.prediction)
+        return {"prediction": prediction, "target": ent.target, "loss": ent.loss.item() if sync else ent.loss}
+
+    _graph_last = None
+
+    def train_step_async(self, batch, state: State = None) -> dict:
+        """train_step without the device->host read of the loss: ``loss`` is returned as a 0-dim device tensor, so the
+        host can enqueue the next step while this one runs (an extension; the reference's train_step always syncs)."""
+        return self.train_step(batch, state, _sync=False)
+
     # argus_models.py:43-71
-    def train_step(self, batch, state: State) -> dict:
+    def train_step(self, batch, state: State, _sync: bool = True) -> dict:
         self.train()
+        key = self._graph_key(batch)
+        if key is not None:
+            ent = self._graphs.get(key)
+            if ent is None:
+                seen = self._graph_seen.get(key, 0)
+                self._graph_seen[key] = seen + 1
+                if seen >= 1 and len(self._graphs) < self.max_graphs:   # first occurrence runs eagerly (warm-up)
+                    ent = self._graphs[key] = self._capture_step(key, batch)
+            if ent is not None:
+                return self._replay_step(ent, batch, _sync)
+            self._graph_last = None
         self.optimizer.zero_grad()
         chunk_losses = []
         try:  # hint registered by DevicePrefetcher for this (device-resident) batch; looked up BEFORE deep_chunk, which
@@ -157,9 +277,12 @@ class MouseModel(_Base):
             self.model_ema.update(self.nn_module)
         # the reference reads loss.item() right after each backward (argus_models.py:56); reading the same values once
         # the optimizer and EMA kernels are enqueued returns the same number without idling the GPU at the sync
-        loss_value = 0
-        for l in chunk_losses:
-            loss_value += l.item()
+        if _sync:
+            loss_value = 0
+            for l in chunk_losses:
+                loss_value += l.item()
+        else:
+            loss_value = torch.stack(chunk_losses).sum()
         prediction = deep_detach(prediction)
         target = deep_detach(target)
         prediction = self.prediction_transform(prediction)

@@ -25,7 +25,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(const DwnTensorEntry* __rest
                                                     const int* __restrict__ chunk_tensor,
                                                     const long* __restrict__ chunk_off, const int* __restrict__ steps,
                                                     const int* __restrict__ active, float lr, float wd, float b1, float b2,
-                                                    float eps, float ema_decay) {
+                                                    float eps, float ema_decay, const float* __restrict__ lr_dev) {
+  // lr_dev != nullptr: the learning rate is read from device memory (a captured CUDA graph must see the scheduler's
+  // current value, a kernel argument would be frozen at capture time)
+  if (lr_dev) lr = *lr_dev;
   const int t = chunk_tensor[blockIdx.x];
   if (active && !active[t]) return;
   const DwnTensorEntry e = tab[t];
@@ -96,12 +99,12 @@ __global__ void __launch_bounds__(256) adamw_kernel(const DwnTensorEntry* __rest
 
 extern "C" int dwn_adamw(const void* tab, const int* chunk_tensor, const long* chunk_off, int nchunks, int* steps,
                          const int* active, int nt, float lr, float wd, float b1, float b2, float eps, float ema_decay,
-                         void* stream) {
+                         const float* lr_dev, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   adamw_step_kernel<<<(nt + 127) / 128, 128, 0, st>>>(steps, active, nt);
   DWN_LAUNCH_CHECK();
   adamw_kernel<<<nchunks, 256, 0, st>>>((const DwnTensorEntry*)tab, chunk_tensor, chunk_off, steps, active, lr, wd, b1, b2,
-                                        eps, ema_decay);
+                                        eps, ema_decay, lr_dev);
   DWN_LAUNCH_CHECK();
   return 0;
 }

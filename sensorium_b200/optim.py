@@ -13,6 +13,15 @@ from ._lib import call
 from .engine import bump_generation, set_shadow
 
 
+def _h2d(host: torch.Tensor, dev, keep: dict) -> torch.Tensor:
+    """Host table -> device.  Under CUDA-graph capture the copy becomes a memcpy node that re-reads the HOST buffer at
+    every replay, so the buffer is pinned and kept alive (``keep["pinned"]``); pageable copies are illegal in capture."""
+    if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
+        host = host.pin_memory()
+        keep.setdefault("pinned", []).append(host)
+    return host.to(dev, non_blocking=True)
+
+
 def _chunk_tables(sizes, chunk, dev):
     ct, co = [], []
     for t, n in enumerate(sizes):
@@ -27,57 +36,85 @@ class FusedAdamW(torch.optim.Optimizer):
                  weight_decay: float = 1e-2):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
-        self._tab = None
-        self._key = None
+        # launch caches (flat moment buffers, pointer tables, chunk tables) live on the optimizer, keyed by group index —
+        # NOT in param_groups, so state_dict() carries only torch's own {exp_avg, exp_avg_sq, step} per parameter
+        self._cache = {}
         self._active_cache = {}
 
-    def _build(self, group, params):
+    def _flatten(self, gi, params):
+        """Flat exp_avg / exp_avg_sq / step buffers; ``state[p]`` entries are views into them.  State that is already
+        present (load_state_dict) is copied in, so a loaded optimizer continues exactly where the saved one stopped."""
         dev = params[0].device
         sizes = [p.numel() for p in params]
         total = sum(sizes)
-        if "m" not in group:
-            group["m"] = torch.zeros(total, dtype=torch.float32, device=dev)
-            group["v"] = torch.zeros(total, dtype=torch.float32, device=dev)
-            group["steps"] = torch.zeros(len(params), dtype=torch.int32, device=dev)
-            off = 0
-            for i, p in enumerate(params):
-                st = self.state[p]
-                st["exp_avg"] = group["m"][off:off + sizes[i]].view_as(p)
-                st["exp_avg_sq"] = group["v"][off:off + sizes[i]].view_as(p)
-                st["step"] = group["steps"][i]
-                off += sizes[i]
-            group["chunks"] = _chunk_tables(sizes, _lib.lib().dwn_opt_chunk(), dev)
+        c = {"m": torch.zeros(total, dtype=torch.float32, device=dev),
+             "v": torch.zeros(total, dtype=torch.float32, device=dev),
+             "steps": torch.zeros(len(params), dtype=torch.int32, device=dev),
+             "chunks": _chunk_tables(sizes, _lib.lib().dwn_opt_chunk(), dev), "key": None, "tab": None}
+        off = 0
+        for i, p in enumerate(params):
+            st = self.state[p]
+            mv, vv, sv = c["m"][off:off + sizes[i]].view_as(p), c["v"][off:off + sizes[i]].view_as(p), c["steps"][i]
+            if "exp_avg" in st:
+                mv.copy_(st["exp_avg"])
+                vv.copy_(st["exp_avg_sq"])
+                sv.copy_(torch.as_tensor(st["step"]).to(torch.int32))
+            st["exp_avg"], st["exp_avg_sq"], st["step"] = mv, vv, sv
+            off += sizes[i]
+        self._cache[gi] = c
+        return c
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._cache.clear()          # the loaded state tensors no longer alias the flat buffers: re-flatten on next step
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._cache = {}
+        self._active_cache = {}
+
+    def _table(self, c, params, dev):
         rows = []
         for p in params:
             st = self.state[p]
             sh = getattr(p, "_dwn_shadow", None)
-            shp = 0
-            if sh is not None:
-                shp = sh[1].data_ptr()
             g = p.grad
             rows.append([p.data_ptr(), g.data_ptr() if g is not None else 0, st["exp_avg"].data_ptr(),
-                         st["exp_avg_sq"].data_ptr(), shp, 0, p.numel(), 0])
-        return torch.tensor(rows, dtype=torch.int64).to(dev, non_blocking=True)
+                         st["exp_avg_sq"].data_ptr(), sh[1].data_ptr() if sh is not None else 0, 0, p.numel(), 0])
+        return _h2d(torch.tensor(rows, dtype=torch.int64), dev, c)
+
+    def sync_graph_lr(self) -> None:
+        """Push the current learning rates to the device scalars that captured optimizer steps read."""
+        for gi, group in enumerate(self.param_groups):
+            c = self._cache.get(gi)
+            if c is not None and "lr_dev" in c and c.get("lr_val") != group["lr"]:
+                c["lr_dev"].fill_(float(group["lr"]))
+                c["lr_val"] = group["lr"]
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             params = [p for p in group["params"] if p.requires_grad]
             if not params:
                 continue
             dev = params[0].device
             if not params[0].is_cuda:
                 raise RuntimeError("FusedAdamW runs on CUDA only: no CPU fallback")
-            key = tuple((p.data_ptr(), p.grad.data_ptr() if p.grad is not None else 0,
-                         id(getattr(p, "_dwn_shadow", None) and p._dwn_shadow[1])) for p in params)
-            if group.get("_key") != key:
+            c = self._cache.get(gi)
+            if c is None or c["steps"].numel() != len(params):
+                c = self._flatten(gi, params)
+
+            def key_of():
+                return tuple((p.data_ptr(), p.grad.data_ptr() if p.grad is not None else 0,
+                              id(getattr(p, "_dwn_shadow", None) and p._dwn_shadow[1])) for p in params)
+
+            if c["key"] != key_of():
                 for p in params:
                     if p.grad is not None and (p.grad.dtype != torch.float32 or not p.grad.is_contiguous()):
                         p.grad = p.grad.float().contiguous()
-                group["_tab"] = self._build(group, params)
-                group["_key"] = tuple((p.data_ptr(), p.grad.data_ptr() if p.grad is not None else 0,
-                                       id(getattr(p, "_dwn_shadow", None) and p._dwn_shadow[1])) for p in params)
+                c["tab"] = self._table(c, params, dev)
+                c["key"] = key_of()
             act = tuple(p.grad is not None for p in params)
             active = None
             provider = getattr(self, "active_provider", None)
@@ -86,13 +123,20 @@ class FusedAdamW(torch.optim.Optimizer):
             elif not all(act):
                 active = self._active_cache.get(act)
                 if active is None:
-                    active = torch.tensor(act, dtype=torch.int32).to(dev)
+                    active = _h2d(torch.tensor(act, dtype=torch.int32), dev, c)
                     if len(self._active_cache) < 256:
                         self._active_cache[act] = active
-            ct, co, nch = group["chunks"]
+            ct, co, nch = c["chunks"]
             b1, b2 = group["betas"]
-            call("dwn_adamw", group["_tab"], ct, co, nch, group["steps"], active, len(params), float(group["lr"]),
-                 float(group["weight_decay"]), float(b1), float(b2), float(group["eps"]), 0.0,
+            lr_dev = None
+            if torch.cuda.is_current_stream_capturing():
+                # a captured step reads the learning rate from device memory; GraphedTrainStep refreshes it
+                # (sync_graph_lr) before every replay, so LR schedulers keep working
+                if "lr_dev" not in c:
+                    c["lr_dev"] = torch.empty((1,), dtype=torch.float32, device=dev)
+                lr_dev = c["lr_dev"]
+            call("dwn_adamw", c["tab"], ct, co, nch, c["steps"], active, len(params), float(group["lr"]),
+                 float(group["weight_decay"]), float(b1), float(b2), float(group["eps"]), 0.0, lr_dev,
                  torch.cuda.current_stream(dev).cuda_stream, _tag="adamw", _bytes=sum(p.numel() for p in params) * 30)
             for p in params:
                 sh = getattr(p, "_dwn_shadow", None)

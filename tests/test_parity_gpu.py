@@ -670,3 +670,71 @@ def test_train_step_compact_targets_equal_dense(dev):
     t1, w1 = o1["target"]
     t2, w2 = o2["target"]
     assert torch.equal(w1.to(dev), w2) and all(torch.equal(a.to(dev), b) for a, b in zip(t1, t2))
+
+
+def test_cuda_graph_train_step_is_bit_identical_to_eager(dev):
+    """params["cuda_graph"] = True: the train step is captured per (shapes, set of mice present) after one eager
+    warm-up occurrence and replayed.  With the RNG-driven layers off (drop-path / dropout consume a different Philox
+    offset under capture) every loss, weight, running statistic, optimizer moment and EMA entry must be bit-identical
+    to the eager run — across batches with different mice present (several graphs), a learning-rate change between steps
+    (the captured AdamW reads lr from device memory) and compact / dense batch forms."""
+    from sensorium_b200.argus_models import MouseModel
+    from sensorium_b200.ema import ModelEma
+    from sensorium_b200.synthetic import compact_from_dense
+    from sensorium_b200.utils import init_weights
+    kw = dict(TINY_KW, drop_path_rate=0.0, drop_rate=0.0)
+
+    def batches():
+        out = []
+        for i in range(8):
+            x = O.synthetic_clip(4, 16, 32, seed=60 + i % 3)
+            tg, w = O.synthetic_targets(4, TINY_OUTS, 16, seed=70 + i % 3)
+            if i % 2 == 1:                   # odd steps: mouse 2 absent -> a second graph
+                keep = (w[:, 2] == 0).float()
+                w = w * keep[:, None]
+                w[:, 0] = torch.clamp(w[:, 0] + (1 - keep), max=1.0)
+                tg[2].zero_()
+            out.append((x, compact_from_dense(tg, w) if i >= 4 and bool((w.sum(1) == 1).all()) else (tg, w)))
+        return out
+
+    def run(graph):
+        params = {"nn_module": ("dwiseneuro", {"readout_outputs": TINY_OUTS, **kw}), "loss": ("mice_poisson", {}),
+                  "optimizer": ("AdamW", {"lr": 2e-3, "weight_decay": 0.05}), "device": "cuda:0", "amp": True,
+                  "iter_size": 1, "cuda_graph": graph}
+        torch.manual_seed(0)
+        m = MouseModel(params)
+        init_weights(m.nn_module)
+        m.model_ema = ModelEma(m.nn_module, decay=0.9)
+        losses = []
+        for i, b in enumerate(batches()):
+            if i == 5:
+                m.set_lr(5e-4)
+            losses.append(m.train_step(b, None)["loss"])
+        return m, losses
+
+    m1, l1 = run(False)
+    m2, l2 = run(True)
+    assert len(m2._graphs) >= 2 and not m1._graphs
+    assert l1 == l2, (l1, l2)
+    for (k, a), b in zip(m1.nn_module.state_dict().items(), m2.nn_module.state_dict().values()):
+        assert torch.equal(a, b), k
+    for (k, a), b in zip(m1.model_ema.ema.state_dict().items(), m2.model_ema.ema.state_dict().values()):
+        assert torch.equal(a, b), k
+    for p1, p2 in zip(m1.nn_module.parameters(), m2.nn_module.parameters()):
+        s1, s2 = m1.optimizer.state[p1], m2.optimizer.state[p2]
+        assert torch.equal(s1["exp_avg"], s2["exp_avg"]) and torch.equal(s1["exp_avg_sq"], s2["exp_avg_sq"])
+        assert int(s1["step"]) == int(s2["step"])
+    # gradients of the last step are visible on the parameters, absent mice keep grad=None
+    assert all((p1.grad is None) == (p2.grad is None) for p1, p2 in zip(m1.nn_module.parameters(), m2.nn_module.parameters()))
+    g1 = m1.nn_module.core.stem[0].weight.grad
+    assert torch.equal(g1, m2.nn_module.core.stem[0].weight.grad)
+    # with the stochastic layers ON the captured step still trains (fresh masks per replay: the losses move and differ)
+    params = {"nn_module": ("dwiseneuro", {"readout_outputs": TINY_OUTS, **TINY_KW}), "loss": ("mice_poisson", {}),
+              "optimizer": ("AdamW", {"lr": 2e-3, "weight_decay": 0.05}), "device": "cuda:0", "amp": True,
+              "iter_size": 1, "cuda_graph": True}
+    torch.manual_seed(0)
+    m3 = MouseModel(params)
+    init_weights(m3.nn_module)
+    b0 = batches()[0]
+    ls = [m3.train_step(b0, None)["loss"] for _ in range(6)]
+    assert len(m3._graphs) == 1 and all(math.isfinite(v) for v in ls) and len(set(ls)) == 6 and ls[-1] < ls[0]
