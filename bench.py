@@ -225,7 +225,7 @@ def _timed(fn, n, barrier, dev, world):
     return ms
 
 
-def bench_c4(dev, rank, world, barrier, steps=8):
+def bench_c4(dev, rank, world, barrier, steps=8, graph=True):
     """BASELINE configs[3] (configs/distillation_001.py): expansion-6 student trained on its own labels plus the frozen
     expansion-7 teacher's predictions for the other nine mice (distill_ratio 0.36), drop-path / dropout on, EMA;
     through MouseModel.train_step with a pinned HOST batch."""
@@ -237,7 +237,7 @@ def bench_c4(dev, rank, world, barrier, steps=8):
     kw_s = dict(MODEL_KW, expansion_ratio=6)
     params = {"nn_module": ("dwiseneuro", {"readout_outputs": NUM_NEURONS, **kw_s}),
               "loss": ("mice_poisson", {}), "optimizer": ("FusedAdamW", {"lr": LR, "weight_decay": WD}),
-              "device": str(dev), "amp": True, "iter_size": 1}
+              "device": str(dev), "amp": True, "iter_size": 1, "cuda_graph": graph}
     torch.manual_seed(1)
     m = MouseModel(params)
     init_weights(m.nn_module)
@@ -306,6 +306,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the eager_b200 / c4 / infer legs")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="launch every kernel from Python (no graph replay)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--profile-out", default="")
     ap.add_argument("--cuda-profiler-step", action="store_true",
@@ -338,7 +339,7 @@ def main():
         "nn_module": ("dwiseneuro", {"readout_outputs": NUM_NEURONS, **MODEL_KW}),
         "loss": ("mice_poisson", {"log_input": False, "full": False, "eps": 1e-8}),
         "optimizer": ("FusedAdamW", {"lr": LR, "weight_decay": WD}),
-        "device": str(dev), "amp": True, "iter_size": 1,
+        "device": str(dev), "amp": True, "iter_size": 1, "cuda_graph": not args.no_cuda_graph,
     }
     model = MouseModel(params)
     init_weights(model.nn_module)
@@ -353,21 +354,15 @@ def main():
     host_dense = (x.pin_memory(), ([t.pin_memory() for t in tg], w.pin_memory()))
     host_compact = (host_dense[0], (comp.pin_memory(), ids.pin_memory()))
     dev_x = x.to(dev)
-    dev_tg = [t.to(dev) for t in tg]
-    dev_w = w.to(dev)
+    dev_comp, dev_ids = comp.to(dev), ids.to(dev)
     live = (w != 0).any(0).tolist()
+    from sensorium_b200.argus_models import _LIVE_HINTS
 
     def device_step():
-        model.train()
-        model.optimizer.zero_grad()
-        model.loss.set_live_hint(live)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            pred = model.nn_module(dev_x)
-            loss = model.loss(pred, (dev_tg, dev_w))
-        loss.backward()
-        model.optimizer.step()
-        model.model_ema.update(model.nn_module)
-        return loss
+        # the product's train step on a batch that is already resident in HBM, without the host read of the loss
+        # (MouseModel.train_step_async); the live-mouse hint travels like DevicePrefetcher's
+        _LIVE_HINTS[id(dev_ids)] = live
+        return model.train_step_async((dev_x, (dev_comp, dev_ids)), None)["loss"]
 
     def barrier():
         if world > 1:
@@ -415,6 +410,7 @@ def main():
     # records do not perturb `value`
     prof_steps = max(2, min(4, args.steps))
     engine.SERIALIZE = True
+    model.cuda_graph = False           # the accounting needs one event pair per launch: eager launches
     device_step()
     _lib.PROF = []
     for _ in range(prof_steps):
@@ -422,13 +418,14 @@ def main():
     barrier()
     prof, _lib.PROF = _lib.PROF, None
     engine.SERIALIZE = False
+    model.cuda_graph = not args.no_cuda_graph
 
     extras = {}
     if not args.no_extras:
-        del dev_tg
+        model._graphs.clear()
         model.optimizer.zero_grad()
         torch.cuda.empty_cache()
-        extras["c4"] = bench_c4(dev, rank, world, barrier)
+        extras["c4"] = bench_c4(dev, rank, world, barrier, graph=not args.no_cuda_graph)
         extras["infer"] = bench_infer(dev, rank, world, barrier)
         if rank == 0:
             try:
@@ -508,6 +505,9 @@ def main():
                       "h2d_bytes_per_step": h2d_dense, "d2h_bytes_per_step": 4,
                       "path": "same call with the reference's dense batch form (ten mostly-zero target tensors)"},
         "gpu_launches": launches,
+        "launch_mode": ("CUDA graph replay of the whole train step (captured per shape / set of mice present); "
+                        "gpu_launches counts the kernels inside the replayed graphs" if not args.no_cuda_graph else
+                        "one launch per kernel from Python (ctypes)"),
         "clocks": sampler.summary(),
         "roofline": roofline,
         "kernel_table_ms_per_step": {k: round(msps, 3) for k, msps, *_ in table[:14]},

@@ -62,6 +62,8 @@ class MouseModel(_Base):
     @torch.no_grad()
     def add_distill_predictions(self, input, target):
         if self.distill_model is not None and self.distill_ratio:
+            # the teacher is frozen by contract (eval, no_grad, never stepped): its folded BatchNorm tables stay valid
+            self.distill_model._dwn_frozen = True
             teacher = self.distill_model(input)
             target_tensors, mice_weights = target
             dev = mice_weights.device
@@ -115,7 +117,7 @@ class MouseModel(_Base):
     # ---------------------------------------------------------------------------------------------------------
     # CUDA-graph replay of the train step
     # ---------------------------------------------------------------------------------------------------------
-    def _graph_key(self, batch):
+    def _graph_key(self, batch, pre_hint=None):
         """Key of the captured step this batch can replay, or None when the step must run eagerly."""
         if not (self.cuda_graph and self.iter_size == 1 and self.device.type == "cuda"
                 and isinstance(self.loss, MicePoissonLoss) and isinstance(self.optimizer, FusedAdamW)
@@ -134,10 +136,9 @@ class MouseModel(_Base):
         if distill:
             live = (True,) * n_mice
         elif w.is_cuda:
-            hint = _LIVE_HINTS.get(id(w))          # device-resident batch (DevicePrefetcher registers the hint)
-            if hint is None:
+            if pre_hint is None:                   # device-resident batch: DevicePrefetcher registers the hint
                 return None                        # the set of mice present must be known on the host
-            live = tuple(bool(v) for v in hint)
+            live = tuple(bool(v) for v in pre_hint)
         elif compact:
             present = set(w.tolist())
             live = tuple(m in present for m in range(n_mice))
@@ -217,7 +218,11 @@ class MouseModel(_Base):
     # argus_models.py:43-71
     def train_step(self, batch, state: State, _sync: bool = True) -> dict:
         self.train()
-        key = self._graph_key(batch)
+        try:  # hint registered by DevicePrefetcher for this (device-resident) batch; looked up BEFORE deep_chunk, which
+            pre_hint = _LIVE_HINTS.pop(id(batch[1][1]), None)  # returns new tensor objects
+        except (TypeError, IndexError, KeyError):
+            pre_hint = None
+        key = self._graph_key(batch, pre_hint)
         if key is not None:
             ent = self._graphs.get(key)
             if ent is None:
@@ -230,10 +235,6 @@ class MouseModel(_Base):
             self._graph_last = None
         self.optimizer.zero_grad()
         chunk_losses = []
-        try:  # hint registered by DevicePrefetcher for this (device-resident) batch; looked up BEFORE deep_chunk, which
-            pre_hint = _LIVE_HINTS.pop(id(batch[1][1]), None)  # returns new tensor objects
-        except (TypeError, IndexError, KeyError):
-            pre_hint = None
         for i, chunk_batch in enumerate(deep_chunk(batch, self.iter_size)):
             host_t, host_w = chunk_batch[1]
             # compact batch form (an extension of datasets.py:172-187): target = (responses (B, n_max, T) of each sample's

@@ -178,11 +178,15 @@ def bump_generation() -> None:
     _GEN[0] += 1
 
 
+_FROZEN = [False]  # set by run_forward for modules flagged ``_dwn_frozen`` (teacher / predictor models: nothing writes
+#                    their weights through raw pointers, so raw-write generations do not invalidate their tables)
+
+
 def _eval_coef(bn, C, Cp, st, dev):
     """Eval-mode BatchNorm folded to per-channel (scale, shift) once per set of weights: the table is cached on the module
     and rebuilt only when a parameter / running statistic changes (version counters + storage + bump_generation)."""
     ts = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
-    key = (C, Cp, str(dev), _GEN[0]) + tuple((t._version, t.data_ptr()) for t in ts)
+    key = (C, Cp, str(dev), -1 if _FROZEN[0] else _GEN[0]) + tuple((t._version, t.data_ptr()) for t in ts)
     ent = getattr(bn, "_dwn_eval_coef", None)
     if ent is not None and ent[0] == key:
         return ent[1]
@@ -276,6 +280,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
     sv = SimpleNamespace(blocks=[], cortex=[], readouts=[], mode=mode, B=B, T=T, H=H, W=W, x=x) if save else None
     if training:
         bump_generation()                              # running statistics are about to change
+    _FROZEN[0] = bool(getattr(mod, "_dwn_frozen", False)) and not training
     rng_dev = getattr(mod, "_rng_device", None)        # test hooks: where / in which dtype the masks are drawn
     mdt = getattr(mod, "_mask_dtype", None) or adt
 

@@ -50,7 +50,11 @@ class FusedAdamW(torch.optim.Optimizer):
         c = {"m": torch.zeros(total, dtype=torch.float32, device=dev),
              "v": torch.zeros(total, dtype=torch.float32, device=dev),
              "steps": torch.zeros(len(params), dtype=torch.int32, device=dev),
-             "chunks": _chunk_tables(sizes, _lib.lib().dwn_opt_chunk(), dev), "key": None, "tab": None}
+             "chunks": _chunk_tables(sizes, _lib.lib().dwn_opt_chunk(), dev), "key": None, "tab": None,
+             # device copy of the learning rate for captured steps.  Allocated HERE, outside any capture: a tensor
+             # allocated inside a capture shares its address with earlier temporaries of the same graph, which would
+             # overwrite a value written before the replay
+             "lr_dev": torch.zeros((1,), dtype=torch.float32, device=dev)}
         off = 0
         for i, p in enumerate(params):
             st = self.state[p]
@@ -87,7 +91,7 @@ class FusedAdamW(torch.optim.Optimizer):
         """Push the current learning rates to the device scalars that captured optimizer steps read."""
         for gi, group in enumerate(self.param_groups):
             c = self._cache.get(gi)
-            if c is not None and "lr_dev" in c and c.get("lr_val") != group["lr"]:
+            if c is not None and c.get("lr_val") != group["lr"]:
                 c["lr_dev"].fill_(float(group["lr"]))
                 c["lr_val"] = group["lr"]
 
@@ -124,7 +128,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 active = self._active_cache.get(act)
                 if active is None:
                     active = _h2d(torch.tensor(act, dtype=torch.int32), dev, c)
-                    if len(self._active_cache) < 256:
+                    # a table created inside a capture lives in that graph's pool and is only valid inside its replay
+                    if len(self._active_cache) < 256 and not torch.cuda.is_current_stream_capturing():
                         self._active_cache[act] = active
             ct, co, nch = c["chunks"]
             b1, b2 = group["betas"]
@@ -132,8 +137,6 @@ class FusedAdamW(torch.optim.Optimizer):
             if torch.cuda.is_current_stream_capturing():
                 # a captured step reads the learning rate from device memory; GraphedTrainStep refreshes it
                 # (sync_graph_lr) before every replay, so LR schedulers keep working
-                if "lr_dev" not in c:
-                    c["lr_dev"] = torch.empty((1,), dtype=torch.float32, device=dev)
                 lr_dev = c["lr_dev"]
             call("dwn_adamw", c["tab"], ct, co, nch, c["steps"], active, len(params), float(group["lr"]),
                  float(group["weight_decay"]), float(b1), float(b2), float(group["eps"]), 0.0, lr_dev,

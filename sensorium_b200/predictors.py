@@ -39,6 +39,7 @@ class Predictor:
         self.model: MouseModel = _model if _model is not None else _load_model(model_path, device=device,
                                                                                 optimizer=None, loss=None)
         self.model.eval()
+        self.model.nn_module._dwn_frozen = True     # inference-only weights: folded BatchNorm tables are never stale
         self.model.nn_module.precision = precision
         self.inputs_processor = get_inputs_processor(*self.model.params["inputs_processor"])
         self.frame_stack_size = self.model.params["frame_stack"]["size"]
