@@ -738,3 +738,33 @@ def test_cuda_graph_train_step_is_bit_identical_to_eager(dev):
     b0 = batches()[0]
     ls = [m3.train_step(b0, None)["loss"] for _ in range(6)]
     assert len(m3._graphs) == 1 and all(math.isfinite(v) for v in ls) and len(set(ls)) == 6 and ls[-1] < ls[0]
+
+
+def test_train_fold_writes_a_reference_style_checkpoint(dev, tmp_path):
+    """folds.train_fold (scripts/train.py:43-170 without the data pipeline): warm-up + cosine stages, validation with the
+    device CorrelationMetric, one EMA checkpoint `model-{epoch:03d}-{val_corr:.6f}.pth` (max_saves=1) that Predictor /
+    get_best_model_path pick up."""
+    from sensorium_b200.folds import get_best_model_path, train_fold
+    from sensorium_b200.predictors import Predictor
+    kw = dict(TINY_KW, drop_path_rate=0.0, drop_rate=0.0)
+    cfg = {"batch_size": 4, "min_base_lr": 3e-6, "ema_decay": 0.9, "init_weights": True, "num_epochs": [1, 2],
+           "stages": ["warmup", "train"],
+           "argus_params": {"nn_module": ("dwiseneuro", {"readout_outputs": TINY_OUTS, **kw}),
+                            "loss": ("mice_poisson", {}), "optimizer": ("AdamW", {"lr": 2e-3, "weight_decay": 0.05}),
+                            "device": "cuda:0", "amp": True, "iter_size": 1, "cuda_graph": True,
+                            "frame_stack": {"size": 16, "step": 2, "position": "last"},
+                            "inputs_processor": ("stack_inputs", {"size": (32, 32), "pad_fill_value": 0.0}),
+                            "responses_processor": ("identity", {})}}
+    train = [(O.synthetic_clip(4, 16, 32, seed=i), O.synthetic_targets(4, TINY_OUTS, 16, seed=100 + i)) for i in range(3)]
+    val = [(O.synthetic_clip(4, 16, 32, seed=50), O.synthetic_targets(4, TINY_OUTS, 16, seed=150))]
+    logs = []
+    torch.manual_seed(0)
+    best = train_fold(cfg, tmp_path / "fold_0", train, val, log=logs.append)
+    files = sorted((tmp_path / "fold_0").glob("*.pth"))
+    assert len(files) == 1 and files[0] == best == get_best_model_path(tmp_path / "fold_0")
+    assert best.name.startswith("model-00") and len(logs) == 3 and "val_corr" in logs[-1]
+    ckpt = torch.load(best, map_location="cpu", weights_only=False)
+    assert set(ckpt) == {"model_name", "params", "nn_state_dict"} and ckpt["model_name"] == "MouseModel"
+    pr = Predictor(best, device="cuda:0")
+    out = pr.model.predict(O.synthetic_clip(1, 16, 32, seed=3), 0)
+    assert out.shape == (1, TINY_OUTS[0], 16) and bool(torch.isfinite(out).all())
