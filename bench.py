@@ -237,7 +237,7 @@ def bench_c4(dev, rank, world, barrier, steps=8, graph=True):
     kw_s = dict(MODEL_KW, expansion_ratio=6)
     params = {"nn_module": ("dwiseneuro", {"readout_outputs": NUM_NEURONS, **kw_s}),
               "loss": ("mice_poisson", {}), "optimizer": ("FusedAdamW", {"lr": LR, "weight_decay": WD}),
-              "device": str(dev), "amp": True, "iter_size": 1, "cuda_graph": graph}
+              "device": str(dev), "amp": True, "iter_size": 1, "cuda_graph": graph, "cuda_graph_dp": graph}
     torch.manual_seed(1)
     m = MouseModel(params)
     init_weights(m.nn_module)
@@ -307,6 +307,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the eager_b200 / c4 / infer legs")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch every kernel from Python (no graph replay)")
+    ap.add_argument("--no-cuda-graph-dp", action="store_true", help="N > 1: do not capture the data-parallel step")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0, help="N > 1: cap on the CTAs NCCL may use (0 = NCCL default)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--profile-out", default="")
     ap.add_argument("--cuda-profiler-step", action="store_true",
@@ -331,7 +333,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        opts = None
+        if args.nccl_max_ctas > 0:
+            # the gradient exchange has ~20 ms of backward to hide behind and needs < 50 GB/s: a few CTAs are enough and
+            # leave the SMs / HBM to the bandwidth-bound backward kernels
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = args.nccl_max_ctas
+            opts.config.min_ctas = min(args.nccl_max_ctas, max(1, opts.config.min_ctas if opts.config.min_ctas > 0 else 1))
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     args.warmup = max(args.warmup, 3)
 
     torch.manual_seed(0)
@@ -340,6 +349,7 @@ def main():
         "loss": ("mice_poisson", {"log_input": False, "full": False, "eps": 1e-8}),
         "optimizer": ("FusedAdamW", {"lr": LR, "weight_decay": WD}),
         "device": str(dev), "amp": True, "iter_size": 1, "cuda_graph": not args.no_cuda_graph,
+        "cuda_graph_dp": not args.no_cuda_graph_dp,
     }
     model = MouseModel(params)
     init_weights(model.nn_module)
@@ -517,7 +527,8 @@ def main():
     }
     if world > 1:
         line["comm"] = {"bytes_reduced_per_step": bytes_reduced, "collective": "ncclAllReduce(AVG) per bucket, overlapped "
-                        "with backward"}
+                        "with backward", "nccl_max_ctas": args.nccl_max_ctas or "default",
+                        "captured_in_cuda_graph": bool(model._graphs) and not args.no_cuda_graph_dp}
     line.update(extras)
     if not args.no_cpu_baseline and world == 1:
         val, threads, sec = cpu_reference_step(8, 2, 1)

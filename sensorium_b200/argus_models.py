@@ -53,6 +53,10 @@ class MouseModel(_Base):
         # params["cuda_graph"] = True: the whole train step (distillation fill, forward, loss, backward, AdamW, EMA) is
         # captured once per (shapes, set of mice present) and replayed — ~500 kernel launches become one graph launch
         self.cuda_graph = bool(params.get("cuda_graph", False))
+        # data-parallel steps are captured too (the NCCL all-reduces become graph nodes); every rank must then see the same
+        # sequence of graph keys, which holds with distillation (all mice live) or when the batch form is the same on all
+        # ranks and the loader hands every rank batches with the same set of mice
+        self.cuda_graph_dp = bool(params.get("cuda_graph_dp", False))
         self._graphs: dict = {}
         self._graph_seen: dict = {}
         self._graph_pool = None
@@ -121,7 +125,7 @@ class MouseModel(_Base):
         """Key of the captured step this batch can replay, or None when the step must run eagerly."""
         if not (self.cuda_graph and self.iter_size == 1 and self.device.type == "cuda"
                 and isinstance(self.loss, MicePoissonLoss) and isinstance(self.optimizer, FusedAdamW)
-                and getattr(self.nn_module, "_dp", None) is None
+                and (getattr(self.nn_module, "_dp", None) is None or self.cuda_graph_dp)
                 and getattr(self.nn_module, "_rng_device", None) is None):
             return None
         try:

@@ -36,6 +36,7 @@ class DataParallelGrads:
         self.active: Optional[torch.Tensor] = None
         self._avg = dist.get_backend(group) == "nccl"  # gloo (CPU tests) has no ReduceOp.AVG
         self._pm_dev = None
+        self._pinned: List = []
         self.bytes_reduced = 0
 
     def __deepcopy__(self, memo):
@@ -70,7 +71,11 @@ class DataParallelGrads:
         for j, v in enumerate(local_live):
             if v:
                 row[mice[j]] = 1
-        flags = torch.tensor(row, dtype=torch.int32).to(dev, non_blocking=True)
+        host = torch.tensor(row, dtype=torch.int32)
+        if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            host = host.pin_memory()               # memcpy node of a captured step: re-read at every replay
+            self._pinned.append(host)
+        flags = host.to(dev, non_blocking=True)
         self.works.append(dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group, async_op=True))
         self._flags = flags
 

@@ -129,6 +129,26 @@ timeg("gemm readout_dgrad", lambda: gemm(st, dtype=1, A=dz_mn, B=wq, b_mn=1, lda
                                          b_zstride=half * Kg, a_zmode=1, b_zmode=1, M=Mbt, N=Kg, K=half, Z=G, D=dxm, d_dtype=0,
                                          ldd=K, d_zstride=Kg),
       2 * G * half * Mbt * Kg, Mbt * G * half_pad * 2 + G * half * Kg * 2 + Mbt * K * 4)
+# point-wise expansion / projection GEMMs at the block shapes (HBM-bound: report GB/s next to TFLOP/s)
+for tag, ci, H, W, s in shapes:
+    mid, Mi = ci * 7, B * T * H * W
+    Mo = Mi // (s * s)
+    Xb = torch.randn(Mi, ci, device=dev).to(bf)
+    Wp = (torch.randn(mid, ci, device=dev) * 0.1).to(bf)
+    Eo = torch.empty(Mi, mid, device=dev, dtype=bf)
+    timeg(f"gemm pw_fwd {tag}", lambda: gemm(st, dtype=1, A=Xb, B=Wp, lda=ci, ldb=ci, M=Mi, N=mid, K=ci, Z=1, D=Eo, d_dtype=1,
+                                             ldd=mid), 2 * Mi * mid * ci, (Mi * ci + mid * ci + Mi * mid) * 2)
+    dXo = torch.empty(Mi, ci, device=dev)
+    timeg(f"gemm pw_dgrad {tag}", lambda: gemm(st, dtype=1, A=Eo, B=Wp, b_mn=1, lda=mid, ldb=ci, M=Mi, N=ci, K=mid, Z=1, D=dXo,
+                                               d_dtype=0, ldd=ci), 2 * Mi * mid * ci, Mi * mid * 2 + mid * ci * 2 + Mi * ci * 4)
+    Nsp = Mo // B
+    Aa = torch.randn(Mo, mid, device=dev).to(bf)
+    Wb = (torch.randn(B, ci, mid, device=dev) * 0.1).to(bf)
+    Yo = torch.empty(Mo, ci, device=dev, dtype=bf)
+    timeg(f"gemm pwl_fwd {tag}", lambda: gemm(st, dtype=1, A=Aa, B=Wb, lda=mid, ldb=mid, a_zstride=Nsp * mid, b_zstride=ci * mid,
+                                              a_zmode=1, b_zmode=1, M=Nsp, N=ci, K=mid, Z=B, D=Yo, d_dtype=1, ldd=ci,
+                                              d_zstride=Nsp * ci), 2 * Mo * mid * ci, (Mo * mid + B * ci * mid + Mo * ci) * 2)
+    del Xb, Eo, dXo, Aa, Yo
 for ci_, co_ in ((256, 1024), (1024, 2048), (2048, 4096)):
     xa = torch.randn(Mbt, ci_, device=dev).to(bf)
     wc = (torch.randn(co_, ci_ // G, device=dev) * 0.05).to(bf)
