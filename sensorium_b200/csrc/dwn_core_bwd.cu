@@ -746,6 +746,9 @@ tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restric
 // segments of an item (da, Tm_raw, S_raw; CCH*2 bytes each, contiguous in the channels-last layout) are fetched by
 // cp.async.bulk into a 2-stage shared-memory ring, so the bytes in flight do not depend on registers or occupancy;
 // thread = channel pair, whole-T column in registers, same arithmetic as tdw_bwd_kernel.
+// Warp-specialised: the LAST warp is the producer (waits for a stage to be released, issues its copies); the CCH/64
+// consumer warps wait on the stage's "full" barrier, compute, and release it with one arrival per warp on its "empty"
+// barrier — no CTA-wide barrier in the item loop (ncu: 2.8 warps per issue slot were parked at __syncthreads).
 template <int TT>
 __global__ void __launch_bounds__(256, 2)
 tdw_bwd_bulk_kernel(bf16* __restrict__ dth, const bf16* __restrict__ tm, const bf16* __restrict__ s_raw,
@@ -760,18 +763,20 @@ tdw_bwd_bulk_kernel(bf16* __restrict__ dth, const bf16* __restrict__ tm, const b
   const int c0 = blockIdx.y * CCH, c = c0 + tid * 2;
   bf16* buf = reinterpret_cast<bf16*>(smraw);  // [NS][3][tn][CCH]
   const size_t stage_elems = (size_t)3 * tn * CCH;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + NS * stage_elems * sizeof(bf16));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + NS * stage_elems * sizeof(bf16));   // full[NS], empty[NS]
+  uint64_t* ebars = bars + NS;
   const long npos = (long)B * HW;
   const long tstride = (long)HW * C;
   const long bstride = (long)Tn * tstride;
   const int G = gridDim.x;
+  const int ncw = CCH / 64;                      // consumer warps; warp ncw is the producer
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) bk_mbar_init(&bars[s], 1);
+    for (int s = 0; s < NS; ++s) { bk_mbar_init(&bars[s], 1); bk_mbar_init(&ebars[s], (uint32_t)ncw); }
     bk_mbar_init_fence();
   }
   __syncthreads();
   const uint32_t seg_bytes = (uint32_t)(CCH * sizeof(bf16));
-  auto issue = [&](long pos, int stage) {  // all lanes of warp 0
+  auto issue = [&](long pos, int stage) {  // all lanes of the producer warp
     const long b = pos / HW, hw = pos - b * HW;
     const long base = b * bstride + hw * C + c0;
     if (lane == 0) bk_mbar_expect_tx(&bars[stage], 3u * (uint32_t)tn * seg_bytes);
@@ -784,10 +789,18 @@ tdw_bwd_bulk_kernel(bf16* __restrict__ dth, const bf16* __restrict__ tm, const b
     }
   };
   long pos = blockIdx.x;
-  if (warp == 0) {
-    if (pos < npos) issue(pos, 0);
-    if (pos + G < npos) issue(pos + G, 1);
-  }
+  f32x2 st2[7];
+#pragma unroll
+  for (int q = 0; q < 7; ++q) st2[q] = 0ull;
+  if (warp == ncw) {
+    // ================= producer warp =================
+    int it = 0;
+    for (; pos < npos; pos += G, ++it) {
+      const int stage = it & 1;
+      if (it >= NS) bk_mbar_wait(&ebars[stage], (uint32_t)(((it >> 1) - 1) & 1));
+      issue(pos, stage);
+    }
+  } else {
   f32x2 a3, b3, d3, w2[5], p0_2, p1_2, q0_3, q1_3, mu2, rs2;
   {
     float av[2], bv[2], dv[2], p0[2], p1[2], q0[2], q1[2], m2[2], r2[2];
@@ -812,9 +825,6 @@ tdw_bwd_bulk_kernel(bf16* __restrict__ dth, const bf16* __restrict__ tm, const b
 #pragma unroll
     for (int k = 0; k < 5; ++k) w2[k] = pk2(wgt[c * 5 + k], wgt[(c + 1) * 5 + k]);
   }
-  f32x2 st2[7];
-#pragma unroll
-  for (int q = 0; q < 7; ++q) st2[q] = 0ull;
   // the per-sample SE term of the NEXT item is fetched one item ahead (no dependent global load per item)
   f32x2 dm_next = 0ull;
   if (pos < npos) {
@@ -874,12 +884,14 @@ tdw_bwd_bulk_kernel(bf16* __restrict__ dth, const bf16* __restrict__ tm, const b
         ffma2(st2[1], o, xh);
       }
     }
-    __syncthreads();  // everybody is done with this stage
-    if (warp == 0 && pos + 2L * G < npos) issue(pos + 2L * G, stage);
+    __syncwarp();     // every lane of this warp has consumed its columns of the stage
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bk_smem_u32(&ebars[stage])) : "memory");
   }
+  }  // consumer warps
   float st[7][2];
 #pragma unroll
   for (int q = 0; q < 7; ++q) upk2(st2[q], st[q][0], st[q][1]);
+  // the producer warp's zeros land in a second (unused) lane slice of the scratch: ln = 1 sums slice 0 only
   block_reduce_channels<7, 2>(st, reinterpret_cast<float*>(smraw), CCH / 2, 1, partial + (long)blockIdx.x * 7 * C, C, c0);
 }
 
@@ -887,16 +899,17 @@ static bool tdw_bwd_bulk_launch(void* dth, const void* tm, const void* s_raw, co
                                 const float* coef2, const float* wgt, const float* dmean, float* partial, int P, int B,
                                 int Tn, int HW, int C, cudaStream_t st) {
   if (C % 16 != 0) return false;
-  int CCH = 0;  // channels per CTA: a divisor of C, multiple of 64 (whole warps of channel pairs), <= 512
-  for (int cand = 512; cand >= 64; cand -= 64)
+  int CCH = 0;  // channels per CTA: a divisor of C, multiple of 64 (whole warps of channel pairs), <= 448 (7 consumer
+  //               warps + the producer warp = 256 threads)
+  for (int cand = 448; cand >= 64; cand -= 64)
     if (C % cand == 0) { CCH = cand; break; }
   if (CCH == 0) return false;
   const size_t stage = (size_t)3 * Tn * CCH * sizeof(bf16);
   size_t sm = 2 * stage + 64;
-  const size_t sm_red = (size_t)(CCH / 2) * 14 * sizeof(float);
+  const size_t sm_red = (size_t)(CCH / 2 + 32) * 14 * sizeof(float) * 2;  // two lane slices (consumers, producer warp)
   if (sm_red > sm) sm = sm_red;
   if (sm > 110 * 1024) return false;
-  dim3 grid(P, C / CCH), block(CCH / 2);
+  dim3 grid(P, C / CCH), block(CCH / 2 + 32);  // + the producer warp
 #define GOB(TTV)                                                                                                   \
   {                                                                                                                \
     auto k = tdw_bwd_bulk_kernel<TTV>;                                                                             \
@@ -1187,7 +1200,10 @@ static int sdw_bwd_v3_launch(const void* dsh, const void* s_raw, const void* e_r
   if (nbsh < 0) return 1;
   const int NR = S == 1 ? THI + 2 : THI / 2 + 1;
   const int RPI = 2 * S, NIT = (NR + RPI - 1) / RPI;
-  size_t sm = 2 * (size_t)NIT * 256 * 16 + (size_t)THI * 128 * 16 + ((size_t)NR * (Wo + 2) + 7) * CC * sizeof(float);
+  // the v3 kernel (stride 2) double-buffers its E tile; the v5 kernel (stride 1) keeps one
+  const size_t e_bufs = S == 2 ? 2 : 1;
+  size_t sm = 2 * (size_t)NIT * 256 * 16 + e_bufs * (size_t)THI * 128 * 16 +
+              ((size_t)NR * (Wo + 2) + 7) * CC * sizeof(float);
   const size_t sm_red = (size_t)256 * 11 * 4 * sizeof(float);
   if (sm_red > sm) sm = sm_red;
   const int nchunks = C / CC;

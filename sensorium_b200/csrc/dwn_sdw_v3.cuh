@@ -95,6 +95,7 @@ sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, c
   const int wq = (tid & (vpr - 1)) >> cvsh;
   const int lcv = tid & (cvn - 1);
   const int act_off0 = (r_first * WP + wq + 1) * CC + lcv * 8;
+  const int h0 = (tid & 4) ? 4 : 0;
   constexpr int act_step = RPI * WP * CC;
   const long g_off0 = ((long)r_first * W + wq) * C + c0 + lcv * 8;
   const long g_step = (long)RPI * W * C;
@@ -177,8 +178,10 @@ sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, c
           o0 = make_float4(v[0], v[1], v[2], v[3]);
           o1 = make_float4(v[4], v[5], v[6], v[7]);
         }
-        *reinterpret_cast<float4*>(dst + it * act_step) = o0;
-        *reinterpret_cast<float4*>(dst + it * act_step + 4) = o1;
+        // conflict-free order of the two 16-byte stores: a thread owns 32 contiguous bytes, so within a quarter-warp lanes
+        // l and l+4 hit the same banks when both store their first half; odd groups of four store the second half first
+        *reinterpret_cast<float4*>(dst + it * act_step + h0) = h0 ? o1 : o0;
+        *reinterpret_cast<float4*>(dst + it * act_step + (4 - h0)) = h0 ? o0 : o1;
       }
     }
     __syncthreads();
@@ -254,8 +257,8 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
   constexpr int EVEC = THI * 128;  // E tile: THI rows x (W*CC/8 = 128) 16-byte vectors
   bf16* rawD = reinterpret_cast<bf16*>(smem_v3);
   bf16* rawS = rawD + (size_t)NVEC * 8;
-  bf16* rawE = rawS + (size_t)NVEC * 8;
-  float* tile = reinterpret_cast<float*>(rawE + (size_t)EVEC * 8);
+  bf16* rawE = rawS + (size_t)NVEC * 8;  // [2][EVEC*8]: the E tile of item k+1 streams in while item k is convolved
+  float* tile = reinterpret_cast<float*>(rawE + (size_t)2 * EVEC * 8);
   float* sco = tile + (size_t)NR * WP * CC;
   const int r_first = tid / VPR;
   const int two = (tid & (VPR - 1)) >> cvsh;  // output column handled in the staging passes
@@ -319,21 +322,24 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
   // E tile staging: vector i = tid + it*256 -> row 2*it + (tid>>7), column vector tid&127
   const int e_r0 = tid >> 7;
   const long e_goff = (long)((tid & 127) >> cvsh) * C + c0 + lcv * 8;
-  int t = worker;
+  auto issue_e = [&](int t, int buf) {
+    const int p = t >> nbsh, hi0 = (t & nbm) * THI;
+    const bf16* eb = e_raw + ((long)p * H + hi0 + e_r0) * erow + e_goff;
+    bf16* dst = rawE + (size_t)buf * EVEC * 8;
+#pragma unroll
+    for (int it = 0; it < THI / 2; ++it) cp_async16(dst + (size_t)(tid + it * 256) * 8, eb + (long)(2 * it) * erow, true);
+  };
+  int t = worker, kbuf = 0;
   if (t < ntiles) issue(t);
   cp_async_commit();
-  for (; t < ntiles; t += nworkers) {
+  if (t < ntiles) issue_e(t, 0);
+  cp_async_commit();
+  for (; t < ntiles; t += nworkers, kbuf ^= 1) {
     const int p = t >> nbsh, hi0 = (t & nbm) * THI;
     const int ho_first = (S == 1) ? hi0 - 1 : hi0 / 2;
     bf16* dp = dE + (((long)p * H + hi0) * W + wi) * C + cch;
-    cp_async_wait<0>();
-    __syncthreads();  // raw dS/S tiles landed; previous stencil finished with `tile` and `rawE`
-    {  // E rows of this tile: in flight while the dS tile is transformed
-      const bf16* eb = e_raw + ((long)p * H + hi0 + e_r0) * erow + e_goff;
-#pragma unroll
-      for (int it = 0; it < THI / 2; ++it) cp_async16(rawE + (size_t)(tid + it * 256) * 8, eb + (long)(2 * it) * erow, true);
-      cp_async_commit();
-    }
+    cp_async_wait<1>();  // the raw dS/S tiles of this item (the E tile, committed after them, may still be in flight)
+    __syncthreads();     // raw tiles visible; previous stencil finished with `tile` and with the other E buffer
     // ---- BN2 backward on the staged tile: dS_raw = a*g - d*x - b (zero outside the image)
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
@@ -367,11 +373,14 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
         *reinterpret_cast<float4*>(dst + (4 - h0)) = h0 ? o0 : o1;
       }
     }
-    cp_async_wait<0>();  // E tile landed
+    cp_async_wait<0>();  // E tile of this item landed (it was issued one item ago)
     __syncthreads();     // tile + E ready, raw dS/S buffers free
     if (t + nworkers < ntiles) issue(t + nworkers);
     cp_async_commit();
-    const bf16* esm = rawE + (size_t)wi * CC + cq * 4;  // row hl at + hl*W*CC
+    if (t + nworkers < ntiles) issue_e(t + nworkers, kbuf ^ 1);
+    cp_async_commit();
+    const bf16* rawEk = rawE + (size_t)kbuf * EVEC * 8;
+    const bf16* esm = rawEk + (size_t)wi * CC + cq * 4;  // row hl at + hl*W*CC
     // ---- transposed stencil + weight gradient, one input row at a time (E row prefetched one ahead)
     const ulonglong2 qa0 = *reinterpret_cast<const ulonglong2*>(sco + 3 * CC + cq * 4);
     const ulonglong2 qa1 = *reinterpret_cast<const ulonglong2*>(sco + 4 * CC + cq * 4);
