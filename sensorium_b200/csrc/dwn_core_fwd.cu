@@ -449,7 +449,8 @@ static int sdw_fwd_v3_launch(const void* in, const float* coef, const float* wgt
   const int nbsh = ilog2_exact(Ho / THO);
   if (nbsh < 0) return 1;
   const size_t nvec = (size_t)NR * vpr;
-  size_t sm = 3 * nvec * 16 + ((size_t)NR * (W + 2) + 2) * CC * sizeof(float);
+  size_t sm = 3 * nvec * 16 + ((size_t)NR * (W + 2) + 2) * CC * sizeof(bf16);  // raw ring + bf16 activated tile
+  if (sm < (size_t)256 * 2 * 4 * sizeof(float)) sm = (size_t)256 * 2 * 4 * sizeof(float);
   const int nchunks = C / CC;
   dim3 grid(P * nchunks), block(256);
 #define LAUNCH(THO_, RPI_, CC_)                                                                                \

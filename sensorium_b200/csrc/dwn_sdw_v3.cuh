@@ -87,15 +87,15 @@ sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, c
   // three raw tiles in a ring: while tile k is activated and convolved, tiles k+1 and k+2 are in flight
   // (two buffers kept only ~40 KB in flight per SM, below what the HBM latency needs)
   bf16* raw0 = reinterpret_cast<bf16*>(smem_v3);
-  float* act = reinterpret_cast<float*>(raw0 + (size_t)3 * NVEC * 8);
-  float* sco = act + (size_t)NR * WP * CC;  // [2][CC] BN1+SiLU constants (kept out of the register file)
+  // activated halo tile in bf16 (what torch's autocast feeds the depth-wise conv: SiLU output is bf16 there too).  An
+  // fp32 tile kept the shared-memory pipe at 82 % of its wavefront peak (ncu, round 2): STS and LDS bytes are halved
+  bf16* act = raw0 + (size_t)3 * NVEC * 8;
   // ---- loop-invariant coordinates of this thread inside one pass
   constexpr int vpr = 256 / RPI;                   // vectors per tile row
   const int r_first = tid / vpr;                   // 0 (RPI=1) or 0/1 (RPI=2)
   const int wq = (tid & (vpr - 1)) >> cvsh;
   const int lcv = tid & (cvn - 1);
   const int act_off0 = (r_first * WP + wq + 1) * CC + lcv * 8;
-  const int h0 = (tid & 4) ? 4 : 0;
   constexpr int act_step = RPI * WP * CC;
   const long g_off0 = ((long)r_first * W + wq) * C + c0 + lcv * 8;
   const long g_step = (long)RPI * W * C;
@@ -110,7 +110,7 @@ sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, c
   }
   constexpr int cqn = CC >> 2;
   const int cq = tid % cqn, wo = tid / cqn;
-  const float* act_rd = act + (wo * S) * CC + cq * 4;
+  const bf16* act_rd = act + (wo * S) * CC + cq * 4;
   constexpr int row_step = WP * CC;
   f32x2 w2[9][2];
 #pragma unroll
@@ -121,7 +121,7 @@ sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, c
   f32x2 st2[2][2] = {{0ull, 0ull}, {0ull, 0ull}};
   for (int i = tid; i < NR * 2 * CC; i += 256) {  // zero halo columns once
     const int r = i / (2 * CC), rem = i % (2 * CC);
-    act[(r * WP + ((rem / CC) ? (W + 1) : 0)) * CC + (rem % CC)] = 0.f;
+    act[(r * WP + ((rem / CC) ? (W + 1) : 0)) * CC + (rem % CC)] = __float2bfloat16_rn(0.f);
   }
   const int nbm = (1 << nbsh) - 1;
   const int ntiles = NP << nbsh;
@@ -154,15 +154,15 @@ sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, c
     // ---- BN1 + SiLU pass: raw bf16 -> act fp32 (zero rows outside the image: padding applies after the activation)
     {
       const bf16* rp = cur + tid * 8;
-      float* dst = act + act_off0;
+      bf16* dst = act + act_off0;
 #pragma unroll
       for (int it = 0; it < NIT; ++it) {
         const int hi = hi0 + r_first + it * RPI;
-        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
         if ((unsigned)hi < (unsigned)H) {
           const uint4 q = *reinterpret_cast<const uint4*>(rp + it * 2048);
           const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
-          float v[8];
+          uint32_t ow[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float lo, hi2;
@@ -173,27 +173,28 @@ sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, c
             upk2(h, h0, h1);
             f32x2 y = h;
             ffma2(y, h, pk2(tanh_approx(h0), tanh_approx(h1)));  // y = h + h*tanh(h)
-            upk2(y, v[2 * j], v[2 * j + 1]);
+            float y0, y1;
+            upk2(y, y0, y1);
+            ow[j] = pack_bf16x2(y0, y1);
           }
-          o0 = make_float4(v[0], v[1], v[2], v[3]);
-          o1 = make_float4(v[4], v[5], v[6], v[7]);
+          o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
-        // conflict-free order of the two 16-byte stores: a thread owns 32 contiguous bytes, so within a quarter-warp lanes
-        // l and l+4 hit the same banks when both store their first half; odd groups of four store the second half first
-        *reinterpret_cast<float4*>(dst + it * act_step + h0) = h0 ? o1 : o0;
-        *reinterpret_cast<float4*>(dst + it * act_step + (4 - h0)) = h0 ? o0 : o1;
+        *reinterpret_cast<uint4*>(dst + it * act_step) = o;   // one 16-byte store per thread, contiguous across lanes
       }
     }
     __syncthreads();
     // ---- stencil: sliding 3-row register window, packed fp32x2 FMAs
     f32x2 R[3][3][2];
     auto load_row = [&](int r) {
-      const float* src = act_rd + r * row_step;
+      const bf16* src = act_rd + r * row_step;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(src + kw * CC);
-        R[r % 3][kw][0] = q.x;
-        R[r % 3][kw][1] = q.y;
+        const uint2 q = *reinterpret_cast<const uint2*>(src + kw * CC);
+        float a0, a1, a2, a3;
+        unpack_bf16x2(q.x, a0, a1);
+        unpack_bf16x2(q.y, a2, a3);
+        R[r % 3][kw][0] = pk2(a0, a1);
+        R[r % 3][kw][1] = pk2(a2, a3);
       }
     };
     bf16* op = out + (((long)p * Ho + ho0) * Wo + wo) * C + c0 + cq * 4;
@@ -226,7 +227,7 @@ sdw_fwd_v3_kernel(const bf16* __restrict__ in, const float* __restrict__ coef, c
     float st[2][4];
     upk2(st2[0][0], st[0][0], st[0][1]); upk2(st2[0][1], st[0][2], st[0][3]);
     upk2(st2[1][0], st[1][0], st[1][1]); upk2(st2[1][1], st[1][2], st[1][3]);
-    block_reduce_channels<2, 4>(st, act, cqn, Wo, partial + (long)worker * 2 * C, C, c0);
+    block_reduce_channels<2, 4>(st, reinterpret_cast<float*>(smem_v3), cqn, Wo, partial + (long)worker * 2 * C, C, c0);
   }
 }
 
