@@ -206,6 +206,29 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
+def _shutdown(world, model=None):
+    """Release the captured graphs (they hold NCCL kernels when the data-parallel step was captured) before the process
+    group goes away; a watchdog ends the process if the NCCL teardown does not return (seen once on 2 GPUs with live
+    graphs) — the JSON line is already out at this point."""
+    import gc
+    import torch.distributed as dist
+    if model is not None:
+        model._graphs.clear()
+        model._graph_last = None
+    gc.collect()
+    torch.cuda.synchronize()
+    if world > 1:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        t = threading.Timer(20.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        try:
+            dist.destroy_process_group()
+        finally:
+            t.cancel()
+
+
 def _timed(fn, n, barrier, dev, world):
     """n calls of fn between barriers; device time (CUDA events) and wall clock, max over ranks."""
     import torch.distributed as dist
@@ -255,6 +278,9 @@ def bench_c4(dev, rank, world, barrier, steps=8, graph=True):
     for _ in range(3):
         m.train_step(host, None)
     ms = _timed(lambda: m.train_step(host, None), steps, barrier, dev, world)
+    m._graphs.clear()
+    if world > 1:
+        m.nn_module._dp = None
     del m, teacher
     torch.cuda.empty_cache()
     return {"value": BATCH * world * steps / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms / steps, "steps": steps,
@@ -445,8 +471,7 @@ def main():
         barrier()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _shutdown(world, model)
         return
 
     # ---- per-kernel table from the serialized profile steps
@@ -536,8 +561,7 @@ def main():
                                 "sample": "2 train steps of batch 8 after 1 warm-up (oracle port of the reference: "
                                           "fp32 fwd + MicePoissonLoss + bwd + torch AdamW + EMA on the host CPU)"}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _shutdown(world, model)
 
 
 if __name__ == "__main__":

@@ -152,8 +152,19 @@ class MouseModel(_Base):
         return (tuple(x.shape), tuple(w.shape), str(w.dtype), compact, tshape, live, distill, self.amp,
                 self.model_ema is not None)
 
+    def release_graphs(self) -> None:
+        """Drop every captured step (graph memory pool, static buffers).  Call before destroying the process group when
+        data-parallel steps were captured: the graphs hold NCCL kernels (also registered with atexit)."""
+        self._graphs.clear()
+        self._graph_last = None
+
     def _capture_step(self, key, batch):
         from . import _lib
+        if not self._graphs:
+            import atexit
+            import weakref
+            ref = weakref.ref(self)
+            atexit.register(lambda: ref() is not None and ref().release_graphs())
         x, (t, w) = batch
         dev = self.device
         compact, live = key[3], key[5]
