@@ -209,7 +209,8 @@ int dwn_window_blend(const float* pred, const float* blend, float* out, int n_ou
 int dwn_opt_chunk(void);
 int dwn_adamw(const void* tab, const int* chunk_tensor, const long* chunk_off, int nchunks, int* steps,
               const int* active, int nt, float lr, float wd, float b1, float b2, float eps, float ema_decay,
-              const float* lr_dev, void* stream);   /* lr_dev != NULL: learning rate read from device memory (CUDA graphs) */
+              const float* lr_dev, float* bc_scratch, void* stream);
+/* lr_dev != NULL: learning rate read from device memory (CUDA graphs); bc_scratch: 2*nt floats (bias corrections) */
 int dwn_ema(const void* tab, const int* chunk_tensor, const long* chunk_off, int nchunks, float decay, void* stream);
 int dwn_scale(float* x, long n, float s, void* stream);
 

@@ -89,7 +89,7 @@ SIGNATURES = {
     "dwn_pw_bwd_prep": "ppppppp" + "ii" + "p",
     "dwn_pw_wgrad_finalize": "ppppppp" + "ii" + "p",
     # optimizer / EMA
-    "dwn_adamw": "ppp" + "i" + "pp" + "i" + "ffffff" + "pp",
+    "dwn_adamw": "ppp" + "i" + "pp" + "i" + "ffffff" + "ppp",
     "dwn_ema": "ppp" + "i" + "f" + "p",
     "dwn_scale": "plfp",
 }

@@ -15,15 +15,22 @@ struct DwnTensorEntry {  // 64 bytes, built by the host as an int64[8] row
 
 constexpr int OPT_CHUNK = 16384;
 
-// steps[t] += active[t]  (per-tensor step counters: tensors without a gradient are skipped entirely)
-__global__ void adamw_step_kernel(int* __restrict__ steps, const int* __restrict__ active, int nt) {
+// steps[t] += active[t]  (per-tensor step counters: tensors without a gradient are skipped entirely), and the two bias
+// corrections of the new step count, bc[t] = {1 - b1^t, sqrt(1 - b2^t)}: computed once per tensor here instead of once
+// per 16 k-element chunk in the update kernel (two double-precision pow() in front of every CTA's first load)
+__global__ void adamw_step_kernel(int* __restrict__ steps, const int* __restrict__ active, int nt, float b1, float b2,
+                                  float* __restrict__ bc) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < nt && (!active || active[t])) steps[t] += 1;
+  if (t >= nt) return;
+  int st = steps[t];
+  if (!active || active[t]) steps[t] = ++st;
+  bc[2 * t] = (float)(1.0 - pow((double)b1, (double)st));
+  bc[2 * t + 1] = (float)sqrt(1.0 - pow((double)b2, (double)st));
 }
 
 __global__ void __launch_bounds__(256) adamw_kernel(const DwnTensorEntry* __restrict__ tab,
                                                     const int* __restrict__ chunk_tensor,
-                                                    const long* __restrict__ chunk_off, const int* __restrict__ steps,
+                                                    const long* __restrict__ chunk_off, const float* __restrict__ bc,
                                                     const int* __restrict__ active, float lr, float wd, float b1, float b2,
                                                     float eps, float ema_decay, const float* __restrict__ lr_dev) {
   // lr_dev != nullptr: the learning rate is read from device memory (a captured CUDA graph must see the scheduler's
@@ -34,15 +41,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(const DwnTensorEntry* __rest
   const DwnTensorEntry e = tab[t];
   const long off = chunk_off[blockIdx.x];
   const long end = min(off + (long)OPT_CHUNK, e.n);
-  __shared__ float s_c[2];
-  if (threadIdx.x == 0) {
-    const double st = (double)steps[t];
-    s_c[0] = (float)(1.0 - pow((double)b1, st));
-    s_c[1] = (float)sqrt(1.0 - pow((double)b2, st));
-  }
-  __syncthreads();
-  const float step_size = lr / s_c[0];
-  const float bc2s = s_c[1];
+  const float step_size = lr / bc[2 * t];
+  const float bc2s = bc[2 * t + 1];
   const float decay = 1.0f - lr * wd;
   auto update = [&](float g, float& p, float& m, float& v) {
     p = p * decay;
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const DwnTensorEntry* __rest
   const uintptr_t bits = (uintptr_t)e.p | (uintptr_t)e.g | (uintptr_t)e.m | (uintptr_t)e.v | (uintptr_t)e.ema |
                          ((uintptr_t)e.shadow << 1);
   const long nvec = (bits & 15) == 0 ? (end - off) / 4 : 0;
-#pragma unroll 2
+#pragma unroll 4
   for (long q = threadIdx.x; q < nvec; q += blockDim.x) {
     const long i = off + 4 * q;
     const float4 g4 = *reinterpret_cast<const float4*>(e.g + i);
@@ -99,12 +99,12 @@ __global__ void __launch_bounds__(256) adamw_kernel(const DwnTensorEntry* __rest
 
 extern "C" int dwn_adamw(const void* tab, const int* chunk_tensor, const long* chunk_off, int nchunks, int* steps,
                          const int* active, int nt, float lr, float wd, float b1, float b2, float eps, float ema_decay,
-                         const float* lr_dev, void* stream) {
+                         const float* lr_dev, float* bc_scratch, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  adamw_step_kernel<<<(nt + 127) / 128, 128, 0, st>>>(steps, active, nt);
+  adamw_step_kernel<<<(nt + 127) / 128, 128, 0, st>>>(steps, active, nt, b1, b2, bc_scratch);
   DWN_LAUNCH_CHECK();
-  adamw_kernel<<<nchunks, 256, 0, st>>>((const DwnTensorEntry*)tab, chunk_tensor, chunk_off, steps, active, lr, wd, b1, b2,
-                                        eps, ema_decay, lr_dev);
+  adamw_kernel<<<nchunks, 256, 0, st>>>((const DwnTensorEntry*)tab, chunk_tensor, chunk_off, bc_scratch, active, lr, wd, b1,
+                                        b2, eps, ema_decay, lr_dev);
   DWN_LAUNCH_CHECK();
   return 0;
 }

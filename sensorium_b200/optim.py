@@ -54,7 +54,8 @@ class FusedAdamW(torch.optim.Optimizer):
              # device copy of the learning rate for captured steps.  Allocated HERE, outside any capture: a tensor
              # allocated inside a capture shares its address with earlier temporaries of the same graph, which would
              # overwrite a value written before the replay
-             "lr_dev": torch.zeros((1,), dtype=torch.float32, device=dev)}
+             "lr_dev": torch.zeros((1,), dtype=torch.float32, device=dev),
+             "bc": torch.zeros((2 * len(params),), dtype=torch.float32, device=dev)}
         off = 0
         for i, p in enumerate(params):
             st = self.state[p]
@@ -139,7 +140,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 # (sync_graph_lr) before every replay, so LR schedulers keep working
                 lr_dev = c["lr_dev"]
             call("dwn_adamw", c["tab"], ct, co, nch, c["steps"], active, len(params), float(group["lr"]),
-                 float(group["weight_decay"]), float(b1), float(b2), float(group["eps"]), 0.0, lr_dev,
+                 float(group["weight_decay"]), float(b1), float(b2), float(group["eps"]), 0.0, lr_dev, c["bc"],
                  torch.cuda.current_stream(dev).cuda_stream, _tag="adamw", _bytes=sum(p.numel() for p in params) * 30)
             for p in params:
                 sh = getattr(p, "_dwn_shadow", None)
