@@ -350,7 +350,7 @@ def main():
     from sensorium_b200 import _lib, engine
     from sensorium_b200.argus_models import MouseModel
     from sensorium_b200.ema import ModelEma
-    from sensorium_b200.synthetic import compact_from_dense
+    from sensorium_b200.synthetic import compact_from_dense, raw_from_dense
     from sensorium_b200.utils import init_weights
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -389,6 +389,8 @@ def main():
     comp, ids = compact_from_dense(tg, w)
     host_dense = (x.pin_memory(), ([t.pin_memory() for t in tg], w.pin_memory()))
     host_compact = (host_dense[0], (comp.pin_memory(), ids.pin_memory()))
+    video, scal = raw_from_dense(x)
+    host_raw = ((video.pin_memory(), scal.pin_memory()), host_compact[1])
     dev_x = x.to(dev)
     dev_comp, dev_ids = comp.to(dev), ids.to(dev)
     live = (w != 0).any(0).tolist()
@@ -437,7 +439,8 @@ def main():
             model.train_step(host, None)
         return _timed(lambda: model.train_step(host, None), args.e2e_steps, barrier, dev, world)
 
-    e2e_ms = e2e(host_compact)
+    e2e_ms = e2e(host_raw)
+    e2e_compact_ms = e2e(host_compact)
     e2e_dense_ms = e2e(host_dense)
     sampler.stop_flag = True
 
@@ -525,7 +528,8 @@ def main():
 
     clips = BATCH * world * args.steps
     value = clips / (ms * 1e-3)
-    h2d = x.numel() * 4 + comp.numel() * 4 + ids.numel() * 8
+    h2d = video.numel() + scal.numel() * 4 + comp.numel() * 4 + ids.numel() * 8
+    h2d_compact = x.numel() * 4 + comp.numel() * 4 + ids.numel() * 8
     h2d_dense = x.numel() * 4 + sum(t.numel() for t in tg) * 4 + w.numel() * 4
     line = {
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -534,8 +538,11 @@ def main():
         "config": bench_config(world),
         "e2e": {"value": BATCH * world * args.e2e_steps / (e2e_ms * 1e-3), "unit": "clips/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": args.e2e_steps,
-                "path": "MouseModel.train_step(pinned host batch: clips + compact per-sample targets + mouse ids) -> "
-                        "loss.item()"},
+                "path": "MouseModel.train_step(pinned host batch: raw uint8 frames + per-frame scalars + compact per-sample "
+                        "targets + mouse ids; clips and dense targets are assembled on the device) -> loss.item()"},
+        "e2e_dense_clips": {"value": BATCH * world * args.e2e_steps / (e2e_compact_ms * 1e-3), "unit": "clips/s",
+                            "h2d_bytes_per_step": h2d_compact, "d2h_bytes_per_step": 4,
+                            "path": "same call with the reference's dense fp32 clip tensor and compact targets"},
         "e2e_dense": {"value": BATCH * world * args.e2e_steps / (e2e_dense_ms * 1e-3), "unit": "clips/s",
                       "h2d_bytes_per_step": h2d_dense, "d2h_bytes_per_step": 4,
                       "path": "same call with the reference's dense batch form (ten mostly-zero target tensors)"},

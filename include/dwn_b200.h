@@ -186,6 +186,9 @@ int dwn_window_gather(const float* inp, float* clips, int Cn, int L, long HW, in
 int dwn_assemble_clips(const void* video, int video_dtype, const float* behavior, const float* pupil, float* clips,
                        int L, int Hv, int Wv, int H, int W, float fill, int size, int step, int last0, int nw,
                        void* stream);
+/* batch form: video (B, T, Hv, Wv) fp32 / uint8, scalars (B, 4, T) fp32 -> clips (B, 5, T, H, W) fp32 (inputs.py:22-36) */
+int dwn_assemble_batch(const void* video, int video_dtype, const float* scalars, float* clips, int B, int T, int Hv,
+                       int Wv, int H, int W, float fill, void* stream);
 /* streaming CorrelationMetric (metrics.py:11-31, 49-74).  acc: (n, 5) doubles
  * {sum x, sum y, sum xy, sum x^2, sum y^2}, cnt: 1 double; samples with weights[b*wstride] == 0 are skipped. */
 int dwn_corr_update(const float* pred, const float* target, const float* weights, int wstride, int B, int n, int T,

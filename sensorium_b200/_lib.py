@@ -77,6 +77,7 @@ SIGNATURES = {
     "dwn_window_blend": "ppp" + "iiiiii" + "l" + "p",
     "dwn_window_gather": "pp" + "ii" + "l" + "iiii" + "p",
     "dwn_assemble_clips": "pippp" + "iiiii" + "f" + "iiii" + "p",
+    "dwn_assemble_batch": "pipp" + "iiiiii" + "f" + "p",
     "dwn_corr_update": "ppp" + "iiii" + "pp" + "p",
     "dwn_corr_finalize": "pp" + "i" + "d" + "pp" + "p",
     "dwn_cutmix": "pppp" + "i" + "l" + "ii" + "p",

@@ -81,6 +81,30 @@ class MouseModel(_Base):
                 call("dwn_distill_fill", t, teacher[m].float().contiguous(), mask, nm, m, B, t.numel() // B, st)
             call("dwn_distill_weights", mice_weights, mask, dweight, B * nm, st)
 
+    def _assemble_input(self, x):
+        """The network input from either batch form: the reference's dense clip tensor (B, 5, T, H, W), or the raw form
+        ``(video (B, T, Hv, Wv) uint8 / fp32, scalars (B, 4, T) fp32)`` — unpadded frames plus behaviour / pupil-centre
+        values per frame — which is padded and stacked on the device exactly like StackInputsProcessor (inputs.py:22-36,
+        ``params["inputs_processor"]`` gives the canvas size and fill value).  1.2 MB instead of 42 MB of H2D per batch."""
+        if torch.is_tensor(x):
+            return x
+        video, scalars = x
+        if not video.is_cuda:
+            raise RuntimeError("raw clips must be on the CUDA device before assembly")
+        name, kw = self.params.get("inputs_processor", ("stack_inputs", {"size": (64, 64), "pad_fill_value": 0.0}))
+        if name != "stack_inputs":
+            raise ValueError(f"raw clip batches need the 'stack_inputs' processor, got '{name}'")
+        W, H = kw["size"]
+        if video.dtype not in (torch.uint8, torch.float32):
+            video = video.float()
+        video = video.contiguous()
+        scalars = scalars.float().contiguous()
+        B, T, Hv, Wv = video.shape
+        out = torch.empty((B, 5, T, H, W), dtype=torch.float32, device=video.device)
+        call("dwn_assemble_batch", video, 2 if video.dtype == torch.uint8 else 0, scalars, out, B, T, Hv, Wv, H, W,
+             float(kw.get("pad_fill_value", 0.0)), torch.cuda.current_stream(video.device).cuda_stream)
+        return out
+
     def _to_device_overlapped(self, chunk_batch):
         """deep_to(batch, device, non_blocking=True) (argus_models.py:49) with the target / weight copies (80 % of the
         host->device bytes, not needed before the loss) issued on a side stream so they overlap the forward pass.
@@ -132,7 +156,10 @@ class MouseModel(_Base):
             x, (t, w) = batch
         except (TypeError, ValueError):
             return None
-        if not torch.is_tensor(x) or not torch.is_tensor(w):
+        raw = not torch.is_tensor(x)
+        if raw and not (isinstance(x, (list, tuple)) and len(x) == 2 and all(torch.is_tensor(v) for v in x)):
+            return None
+        if not torch.is_tensor(w):
             return None
         compact = torch.is_tensor(t)
         n_mice = len(self.nn_module.cfg["readout_outputs"])
@@ -149,7 +176,8 @@ class MouseModel(_Base):
         else:
             live = tuple((w != 0).any(0).tolist())
         tshape = tuple(t.shape) if compact else tuple(tuple(v.shape) for v in t)
-        return (tuple(x.shape), tuple(w.shape), str(w.dtype), compact, tshape, live, distill, self.amp,
+        xshape = tuple((tuple(v.shape), str(v.dtype)) for v in x) if raw else (tuple(x.shape), str(x.dtype))
+        return (xshape, tuple(w.shape), str(w.dtype), compact, tshape, live, distill, self.amp,
                 self.model_ema is not None)
 
     def release_graphs(self) -> None:
@@ -169,7 +197,8 @@ class MouseModel(_Base):
         dev = self.device
         compact, live = key[3], key[5]
         ent = State()
-        ent.x = torch.empty(x.shape, dtype=x.dtype, device=dev)
+        ent.x = torch.empty(x.shape, dtype=x.dtype, device=dev) if torch.is_tensor(x) else [
+            torch.empty(v.shape, dtype=v.dtype, device=dev) for v in x]
         ent.t = torch.empty(t.shape, dtype=t.dtype, device=dev) if compact else [
             torch.empty(v.shape, dtype=v.dtype, device=dev) for v in t]
         ent.w = torch.empty(w.shape, dtype=w.dtype, device=dev)
@@ -185,8 +214,9 @@ class MouseModel(_Base):
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
                 if compact:
                     target = collate_on_device(ent.t, ent.w, self.nn_module.cfg["readout_outputs"])
-                self.add_distill_predictions(ent.x, target)
-                prediction = self.nn_module(ent.x)
+                xin = self._assemble_input(ent.x)
+                self.add_distill_predictions(xin, target)
+                prediction = self.nn_module(xin)
                 loss = self.loss(prediction, target)
             self.grad_scaler.scale(loss).backward()
             self.optimizer.step()
@@ -205,7 +235,11 @@ class MouseModel(_Base):
         from . import _lib
         from .engine import bump_generation
         x, (t, w) = batch
-        ent.x.copy_(x, non_blocking=True)
+        if torch.is_tensor(x):
+            ent.x.copy_(x, non_blocking=True)
+        else:
+            for d, s_ in zip(ent.x, x):
+                d.copy_(s_, non_blocking=True)
         if torch.is_tensor(t):
             ent.t.copy_(t, non_blocking=True)
         else:
@@ -269,6 +303,7 @@ class MouseModel(_Base):
                 elif pre_hint is not None and self.iter_size == 1:  # batch prefetched by DevicePrefetcher
                     self.loss.set_live_hint(pre_hint)
             input, target, ready = self._to_device_overlapped(chunk_batch)
+            input = self._assemble_input(input)
 
             def dense():
                 nonlocal target, compact

@@ -62,6 +62,51 @@ extern "C" int dwn_assemble_clips(const void* video, int video_dtype, const floa
   return 0;
 }
 
+// Training-batch form of f1: B independent clips.  video (B, T, Hv, Wv) fp32 / uint8 (frames already gathered by the
+// loader, unpadded), scalars (B, 4, T) fp32 = behaviour (2) + pupil centre (2) per frame -> clips (B, 5, T, H, W) fp32:
+// StackInputsProcessor (inputs.py:22-36) per sample, on the device.  42 MB of H2D per batch of 32 become 1.2 MB.
+template <typename VT>
+__global__ void assemble_batch_kernel(const VT* __restrict__ video, const float* __restrict__ scalars,
+                                      float* __restrict__ clips, int T, int Hv, int Wv, int H, int W, int top, int left,
+                                      float fill, long total) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long r = i / W;
+    const int h = (int)(r % H); r /= H;
+    const int t = (int)(r % T); r /= T;
+    const int c = (int)(r % 5);
+    const long b = r / 5;
+    float v;
+    if (c == 0) {
+      const int hv = h - top, wv = w - left;
+      v = (hv >= 0 && hv < Hv && wv >= 0 && wv < Wv) ? (float)video[((b * T + t) * Hv + hv) * Wv + wv] : fill;
+    } else {
+      v = scalars[(b * 4 + (c - 1)) * T + t];
+    }
+    clips[i] = v;
+  }
+}
+extern "C" int dwn_assemble_batch(const void* video, int video_dtype, const float* scalars, float* clips, int B, int T,
+                                  int Hv, int Wv, int H, int W, float fill, void* stream) {
+  DWN_REQUIRE(Hv <= H && Wv <= W, "dwn_assemble_batch: video %dx%d larger than the %dx%d canvas", Hv, Wv, H, W);
+  if (B <= 0) return 0;
+  const int top = (H - Hv) / 2, left = (W - Wv) / 2;
+  const long total = (long)B * 5 * T * H * W;
+  int gx = (int)((total + 255) / 256);
+  if (gx > 148 * 16) gx = 148 * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (video_dtype == 0)
+    assemble_batch_kernel<float><<<gx, 256, 0, st>>>((const float*)video, scalars, clips, T, Hv, Wv, H, W, top, left, fill,
+                                                     total);
+  else if (video_dtype == 2)
+    assemble_batch_kernel<unsigned char><<<gx, 256, 0, st>>>((const unsigned char*)video, scalars, clips, T, Hv, Wv, H, W,
+                                                             top, left, fill, total);
+  else
+    return dwn_fail("dwn_assemble_batch: video_dtype %d unsupported (0 = fp32, 2 = uint8)", video_dtype);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // f2: acc[n][5] (double) += { sum x, sum y, sum xy, sum x^2, sum y^2 } over the samples with weight != 0 and all T frames
 //     (x = prediction, y = target); cnt[0] += T * #samples.  One warp per neuron, fixed reduction order: deterministic.

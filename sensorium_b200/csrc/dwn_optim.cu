@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const DwnTensorEntry* __rest
   const uintptr_t bits = (uintptr_t)e.p | (uintptr_t)e.g | (uintptr_t)e.m | (uintptr_t)e.v | (uintptr_t)e.ema |
                          ((uintptr_t)e.shadow << 1);
   const long nvec = (bits & 15) == 0 ? (end - off) / 4 : 0;
-#pragma unroll 4
+#pragma unroll 2
   for (long q = threadIdx.x; q < nvec; q += blockDim.x) {
     const long i = off + 4 * q;
     const float4 g4 = *reinterpret_cast<const float4*>(e.g + i);

@@ -49,6 +49,16 @@ def compact_from_dense(targets, weights):
     return comp, ids
 
 
+def raw_from_dense(x: torch.Tensor):
+    """Dense clip batch (B, 5, T, S, S) of ``synthetic_clip`` -> the raw form ``MouseModel.train_step`` also accepts:
+    (video (B, T, 36*S/64, S) uint8, scalars (B, 4, T) fp32)."""
+    size = x.shape[-1]
+    lo, hi = (size - 36 * size // 64) // 2, (size - 36 * size // 64) // 2 + 36 * size // 64
+    video = x[:, 0, :, lo:hi, :].to(torch.uint8).contiguous()
+    scalars = x[:, 1:, :, 0, 0].contiguous()
+    return video, scalars
+
+
 def synthetic_trial(length: int = 300, seed: int = 0):
     """Raw trial as the reference stores it (predictors.py:36-40): video (36, 64, L) uint8, behaviour (2, L), pupil
     centre (2, L) float32."""

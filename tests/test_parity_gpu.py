@@ -768,3 +768,50 @@ def test_train_fold_writes_a_reference_style_checkpoint(dev, tmp_path):
     pr = Predictor(best, device="cuda:0")
     out = pr.model.predict(O.synthetic_clip(1, 16, 32, seed=3), 0)
     assert out.shape == (1, TINY_OUTS[0], 16) and bool(torch.isfinite(out).all())
+
+
+def test_train_step_raw_clips_equal_dense(dev):
+    """The raw batch form — (video (B, T, Hv, Wv) uint8, scalars (B, 4, T)) — is padded / stacked on the device
+    (dwn_assemble_batch == StackInputsProcessor per sample, inputs.py:22-36): bit-exact clips, and a train step (eager
+    and captured) that is bit-identical to the dense form."""
+    from sensorium_b200._lib import call
+    from sensorium_b200.argus_models import MouseModel
+    from sensorium_b200.synthetic import compact_from_dense, raw_from_dense
+    from sensorium_b200.utils import init_weights
+    x = O.synthetic_clip(3, 16, 32, seed=5)
+    video, scal = raw_from_dense(x)
+    assert video.dtype == torch.uint8 and video.shape == (3, 16, 18, 32) and scal.shape == (3, 4, 16)
+    want = torch.stack([O.stack_inputs(video[b].permute(1, 2, 0), scal[b, :2], scal[b, 2:], size=(32, 32)) for b in range(3)])
+    assert torch.equal(want, x)
+    out = torch.empty((3, 5, 16, 32, 32), device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    call("dwn_assemble_batch", video.to(dev), 2, scal.to(dev), out, 3, 16, 18, 32, 32, 32, 0.0, st)
+    assert torch.equal(out.cpu(), x)
+    vf = video.float() + 0.25                                     # fp32 video and a non-zero fill value
+    call("dwn_assemble_batch", vf.to(dev), 0, scal.to(dev), out, 3, 16, 18, 32, 32, 32, 7.5, st)
+    want = torch.stack([O.stack_inputs(vf[b].permute(1, 2, 0), scal[b, :2], scal[b, 2:], size=(32, 32), fill=7.5) for b in range(3)])
+    assert torch.equal(out.cpu(), want)
+
+    kw = dict(TINY_KW, drop_path_rate=0.0, drop_rate=0.0)
+
+    def run(raw, graph):
+        params = {"nn_module": ("dwiseneuro", {"readout_outputs": TINY_OUTS, **kw}), "loss": ("mice_poisson", {}),
+                  "optimizer": ("AdamW", {"lr": 2e-3, "weight_decay": 0.05}), "device": "cuda:0", "amp": True,
+                  "iter_size": 1, "cuda_graph": graph,
+                  "inputs_processor": ("stack_inputs", {"size": (32, 32), "pad_fill_value": 0.0})}
+        torch.manual_seed(0)
+        m = MouseModel(params)
+        init_weights(m.nn_module)
+        losses = []
+        for i in range(3):
+            xb = O.synthetic_clip(4, 16, 32, seed=80 + i)
+            tg, w = O.synthetic_targets(4, TINY_OUTS, 16, seed=90)
+            losses.append(m.train_step((raw_from_dense(xb) if raw else xb, compact_from_dense(tg, w)), None)["loss"])
+        return m, losses
+
+    m0, l0 = run(False, False)
+    for raw, graph in ((True, False), (True, True)):
+        m1, l1 = run(raw, graph)
+        assert l0 == l1, (raw, graph, l0, l1)
+        for a, b in zip(m0.nn_module.state_dict().values(), m1.nn_module.state_dict().values()):
+            assert torch.equal(a, b)
