@@ -90,8 +90,9 @@ int dwn_fold_gate(const float* w, const float* gate, void* out, int B, int N, in
 /* ---- residual epilogue: drop-path + nearest/cyclic shortcut + BN_sc + next PE (dwiseneuro.py:125-144) --- */
 int dwn_block_out(const void* y_raw, const float* coef4, const float* dp, const float* xin, const float* coef_sc,
                   const float* pe_t, const float* pe_h, const float* pe_w, float* out, void* out_bf, float* partial,
-                  int P, int next_stride, int B, int Tn, int Ho, int Wo, int Ci, int Co, int stride, int dtype,
-                  void* stream);
+                  int P, int next_stride, int B, int Tn, int Ho, int Wo, int Ci, int Co, int stride, int Hi, int Wi,
+                  int dtype, void* stream);   /* Ho = ceil(Hi / stride): the nearest map floor(dst * Hi / Ho) of
+                                                  F.interpolate (dwiseneuro.py:127-129) also for sizes the stride does not divide */
 int dwn_pool_hw(const float* in, float* out, void* out_bf, int BT, int HW, int C, void* stream);
 
 /* ---- cortex (dwiseneuro.py:195-234) and readout input (:276) ------------------------------------------ */
@@ -108,7 +109,7 @@ int dwn_bn_bwd_finalize(const float* partial, int P, int NQ, int q0, double coun
                         float* bcoef, int C, void* stream);                                /* dwiseneuro.py:9-22 */
 int dwn_block_bwd_reduce(const float* dO, const void* y_raw, const float* coef4, const float* dp, const float* xin,
                          const float* coef_sc, float* partial, int P, int B, int Tn, int Ho, int Wo, int Ci, int Co,
-                         int stride, int dtype, void* stream);                              /* dwiseneuro.py:136-144 */
+                         int stride, int Hi, int Wi, int dtype, void* stream);                              /* dwiseneuro.py:136-144 */
 int dwn_block_bwd_dy(const float* dO, const void* y_raw, const float* coef4, const float* bcoef4, const float* dp,
                      void* dY, long Mo, long rows_per_b, int Co, int dtype, void* stream);
 int dwn_block_in_bwd(const float* dXpw, const float* dO, const float* xin, const float* coef_sc, const float* bcoef_sc,

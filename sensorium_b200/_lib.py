@@ -41,7 +41,7 @@ SIGNATURES = {
     "dwn_se_pool": "pppp" + "iiiii" + "p",
     "dwn_se_mlp": "pii" + "ppppppp" + "iii" + "p",
     "dwn_fold_gate": "ppp" + "iiii" + "p",
-    "dwn_block_out": "ppppp" + "ppp" + "ppp" + "iiiiiiiiii" + "p",
+    "dwn_block_out": "ppppp" + "ppp" + "ppp" + "iiiiiiiiiiii" + "p",
     "dwn_pool_hw": "ppp" + "iii" + "p",
     "dwn_cortex_out": "ppppppp" + "iiiiii" + "p",
     "dwn_readout_prep": "pppp" + "iiii" + "p",
@@ -49,7 +49,7 @@ SIGNATURES = {
     "dwn_split3": "pplp",
     # backward
     "dwn_bn_bwd_finalize": "piiidpppip",
-    "dwn_block_bwd_reduce": "ppppppp" + "iiiiiiiii" + "p",
+    "dwn_block_bwd_reduce": "ppppppp" + "iiiiiiiiiii" + "p",
     "dwn_block_bwd_dy": "pppppp" + "llii" + "p",
     "dwn_block_in_bwd": "ppppppp" + "iiiiiii" + "p",
     "dwn_block_in_bwd_stem": "pppppppp" + "iiiiiii" + "p",

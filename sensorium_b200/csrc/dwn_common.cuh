@@ -304,6 +304,33 @@ struct FastDiv {
   __device__ __forceinline__ int mod(int x) const { return sh >= 0 ? (x & (d - 1)) : (x % d); }
 };
 
+// Index map of F.interpolate(mode="nearest", size=out) along one axis (interpolate_shortcut, dwiseneuro.py:125-129, where
+// out = ceil(in / stride)): ATen's nearest_neighbor_compute_source_index with scale = (float)in / out, i.e.
+// src(dst) = min(floorf(dst * scale), in - 1).  When in == out * s it is the integer map dst * s (every real shape:
+// the reference pads its clips to 64 x 64); the float form covers sizes the stride does not divide, bit-exactly.
+// For out <= in the map is strictly increasing, so it has an inverse on its image (dst(), used by the backward scatter
+// and by the producers that take BatchNorm statistics over exactly the gathered positions).
+struct NearestMap {
+  int in, out, s;
+  float scale;
+  __host__ __device__ NearestMap() : in(1), out(1), s(1), scale(1.f) {}
+  __host__ NearestMap(int in_, int out_)
+      : in(in_), out(out_), s((out_ > 0 && in_ % out_ == 0) ? in_ / out_ : 0), scale((float)in_ / (float)out_) {}
+  __device__ __forceinline__ int src(int d) const {
+    if (s) return d * s;
+    const int v = (int)floorf((float)d * scale);
+    return v < in - 1 ? v : in - 1;
+  }
+  __device__ __forceinline__ int dst(int x) const {  // -1: position x is not gathered
+    if (s) return (x % s == 0) ? x / s : -1;
+    const int d0 = (int)((float)x / scale);
+    for (int d = (d0 > 0 ? d0 - 1 : 0); d <= d0 + 1 && d < out; ++d)
+      if (src(d) == x) return d;
+    return -1;
+  }
+};
+static inline int dwn_ceil_div(int a, int b) { return (a + b - 1) / b; }
+
 static inline int dwn_largest_divisor_le(int n, int cap) {
   int best = 1;
   for (int d = 1; d <= cap && d <= n; ++d)

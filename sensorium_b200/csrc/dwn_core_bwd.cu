@@ -50,7 +50,7 @@ __global__ void block_bwd_reduce_kernel(const float* __restrict__ dO, const T* _
                                         const float* __restrict__ coef4, const float* __restrict__ dp,
                                         const float* __restrict__ xin, const float* __restrict__ coef_sc,
                                         float* __restrict__ partial, int B, int Tn, int Ho, int Wo, int Ci, int Co,
-                                        int stride, int cqc, FastDiv dw, FastDiv dh, FastDiv dt) {
+                                        NearestMap mh, NearestMap mw, int cqc, FastDiv dw, FastDiv dh, FastDiv dt) {
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
   const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
@@ -65,7 +65,7 @@ __global__ void block_bwd_reduce_kernel(const float* __restrict__ dO, const T* _
     rs[j] = coef_sc[3 * Co + c + j];
   }
   float st[4][4] = {};
-  const int Hi = Ho * stride, Wi = Wo * stride;
+  const int Hi = mh.in, Wi = mw.in;
   const int Mo = B * Tn * Ho * Wo;
   // the three streamed quads go through a per-thread cp.async pipeline (ThreadPipe, dwn_sdw_v3.cuh)
   constexpr int DEPTH = 8;
@@ -78,7 +78,7 @@ __global__ void block_bwd_reduce_kernel(const float* __restrict__ dO, const T* _
       const int hq = dh.mod(r1), bt = dh.div(r1);
       cp_async16_ok(pipe.slot(k, 0), dO + (long)m * Co + c);
       pipe_issue_quad<T>(pipe.slot(k, 1), y_raw + (long)m * Co + c);
-      cp_async16_ok(pipe.slot(k, 2), xin + (((long)bt * Hi + hq * stride) * Wi + wq * stride) * Ci + ci);
+      cp_async16_ok(pipe.slot(k, 2), xin + (((long)bt * Hi + mh.src(hq)) * Wi + mw.src(wq)) * Ci + ci);
     }
     cp_async_commit();
   };
@@ -109,7 +109,10 @@ __global__ void block_bwd_reduce_kernel(const float* __restrict__ dO, const T* _
 
 extern "C" int dwn_block_bwd_reduce(const float* dO, const void* y_raw, const float* coef4, const float* dp,
                                     const float* xin, const float* coef_sc, float* partial, int P, int B, int Tn, int Ho,
-                                    int Wo, int Ci, int Co, int stride, int dtype, void* stream) {
+                                    int Wo, int Ci, int Co, int stride, int Hi, int Wi, int dtype, void* stream) {
+  DWN_REQUIRE(Ho == dwn_ceil_div(Hi, stride) && Wo == dwn_ceil_div(Wi, stride),
+              "dwn_block_bwd_reduce: output %dx%d is not ceil(%dx%d / %d)", Ho, Wo, Hi, Wi, stride);
+  const NearestMap mh(Hi, Ho), mw(Wi, Wo);
   int cqc = dwn_largest_divisor_le(Co / 4, 64), ln = 256 / cqc;
   dim3 grid(P, (Co / 4) / cqc), block(cqc * ln);
   size_t sm = (size_t)block.x * 16 * sizeof(float);
@@ -119,11 +122,11 @@ extern "C" int dwn_block_bwd_reduce(const float* dO, const void* y_raw, const fl
   if (dtype == DWN_DT_F32)
     block_bwd_reduce_kernel<float><<<grid, block, sm, (cudaStream_t)stream>>>(dO, (const float*)y_raw, coef4, dp, xin,
                                                                               coef_sc, partial, B, Tn, Ho, Wo, Ci, Co,
-                                                                              stride, cqc, FastDiv(Wo), FastDiv(Ho), FastDiv(Tn));
+                                                                              mh, mw, cqc, FastDiv(Wo), FastDiv(Ho), FastDiv(Tn));
   else
     block_bwd_reduce_kernel<bf16><<<grid, block, sm, (cudaStream_t)stream>>>(dO, (const bf16*)y_raw, coef4, dp, xin,
                                                                              coef_sc, partial, B, Tn, Ho, Wo, Ci, Co,
-                                                                             stride, cqc, FastDiv(Wo), FastDiv(Ho), FastDiv(Tn));
+                                                                             mh, mw, cqc, FastDiv(Wo), FastDiv(Ho), FastDiv(Tn));
   DWN_LAUNCH_CHECK();
   return 0;
 }
@@ -179,8 +182,8 @@ template <int STEM_CIN>  // > 0: this is block 0 -> accumulate the stem reductio
 __global__ void block_in_bwd_kernel(const float* __restrict__ dXpw, const float* __restrict__ dO,
                                     const float* __restrict__ xin, const float* __restrict__ coef_sc,
                                     const float* __restrict__ bcoef_sc, const float* __restrict__ colbias,
-                                    float* __restrict__ dXin, int B, int Tn, int Hi, int Wi, int Ci, int Co, int stride,
-                                    int cqc, FastDiv dw, FastDiv dh, const float* __restrict__ x_in,
+                                    float* __restrict__ dXin, int B, int Tn, int Hi, int Wi, int Ci, int Co, NearestMap mh,
+                                    NearestMap mw, int cqc, FastDiv dw, FastDiv dh, const float* __restrict__ x_in,
                                     float* __restrict__ stem_partial) {
   extern __shared__ float smem[];
   constexpr int SQ = STEM_CIN > 0 ? STEM_CIN + 1 : 1;
@@ -190,7 +193,7 @@ __global__ void block_in_bwd_kernel(const float* __restrict__ dXpw, const float*
   const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
   const int c = (blockIdx.y * cqc + cq) * 4;
   const int Mi = B * Tn * Hi * Wi;
-  const int Ho = Hi / stride, Wo = Wi / stride;
+  const int Ho = mh.out, Wo = mw.out;
   const int nrep = (Co - c + Ci - 1) / Ci;  // output channels fed by input channel c: c, c+Ci, ...
   // dx_sc = sum_rep a*g - dd*x - bb   (BN_sc backward, cyclic channel tile summed)
   float a[2][4], bb[4] = {0.f, 0.f, 0.f, 0.f}, dd[4] = {0.f, 0.f, 0.f, 0.f};
@@ -223,8 +226,9 @@ __global__ void block_in_bwd_kernel(const float* __restrict__ dXpw, const float*
       cp_async16_ok(pipe.slot(k, 0), dXpw + (long)m * Ci + c);
       const int wq = dw.mod(m), r1 = dw.div(m);
       const int hq = dh.mod(r1), bt = dh.div(r1);
-      if ((hq % stride) == 0 && (wq % stride) == 0) {
-        const long mo = ((long)bt * Ho + hq / stride) * Wo + wq / stride;
+      const int ho = mh.dst(hq), wo = mw.dst(wq);  // >= 0: this position feeds the (nearest-gathered) shortcut
+      if (ho >= 0 && wo >= 0) {
+        const long mo = ((long)bt * Ho + ho) * Wo + wo;
         cp_async16_ok(pipe.slot(k, 1), xin + (long)m * Ci + c);
         cp_async16_ok(pipe.slot(k, 2), dO + mo * Co + c);
         if (nrep > 1) cp_async16_ok(pipe.slot(k, 3), dO + mo * Co + c + Ci);
@@ -248,8 +252,8 @@ __global__ void block_in_bwd_kernel(const float* __restrict__ dXpw, const float*
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] -= cb[j];
     const int wq = dw.mod(m), r1 = dw.div(m);
-    const int hq = dh.mod(r1), bt = dh.div(r1);
-    if ((hq % stride) == 0 && (wq % stride) == 0) {
+    const int hq = dh.mod(r1);
+    if (mh.dst(hq) >= 0 && mw.dst(wq) >= 0) {
       float x[4], g[4];
       quad_from(*pipe.slot(kk, 1), x);
       quad_from(*pipe.slot(kk, 2), g);
@@ -288,9 +292,9 @@ extern "C" int dwn_block_in_bwd(const float* dXpw, const float* dO, const float*
   dim3 grid(592, (Ci / 4) / cqc), block(cqc * ln);
   const size_t sm = ThreadPipe<4, 4>::bytes(block.x);
   cudaFuncSetAttribute(block_in_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  block_in_bwd_kernel<0><<<grid, block, sm, (cudaStream_t)stream>>>(dXpw, dO, xin, coef_sc, bcoef_sc, colbias, dXin, B, Tn,
-                                                                   Hi, Wi, Ci, Co, stride, cqc, FastDiv(Wi), FastDiv(Hi),
-                                                                   nullptr, nullptr);
+  block_in_bwd_kernel<0><<<grid, block, sm, (cudaStream_t)stream>>>(
+      dXpw, dO, xin, coef_sc, bcoef_sc, colbias, dXin, B, Tn, Hi, Wi, Ci, Co, NearestMap(Hi, dwn_ceil_div(Hi, stride)),
+      NearestMap(Wi, dwn_ceil_div(Wi, stride)), cqc, FastDiv(Wi), FastDiv(Hi), nullptr, nullptr);
   DWN_LAUNCH_CHECK();
   return 0;
 }
@@ -307,8 +311,8 @@ extern "C" int dwn_block_in_bwd_stem(const float* dXpw, const float* dO, const f
   if (ThreadPipe<4, 4>::bytes(block.x) > sm) sm = ThreadPipe<4, 4>::bytes(block.x);
   cudaFuncSetAttribute(block_in_bwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   block_in_bwd_kernel<5><<<grid, block, sm, (cudaStream_t)stream>>>(
-      dXpw, dO, xin, coef_sc, bcoef_sc, colbias, nullptr, B, Tn, Hi, Wi, Ci, Co, stride, cqc, FastDiv(Wi), FastDiv(Hi), x_in,
-      stem_partial);
+      dXpw, dO, xin, coef_sc, bcoef_sc, colbias, nullptr, B, Tn, Hi, Wi, Ci, Co, NearestMap(Hi, dwn_ceil_div(Hi, stride)),
+      NearestMap(Wi, dwn_ceil_div(Wi, stride)), cqc, FastDiv(Wi), FastDiv(Hi), x_in, stem_partial);
   DWN_LAUNCH_CHECK();
   return 0;
 }
@@ -969,7 +973,7 @@ sdw_bwd_kernel(const T* __restrict__ dsh, const T* __restrict__ s_raw, const T* 
   constexpr int V = VecT<T>::V;
   constexpr int NR = S == 1 ? THI + 2 : THI / 2 + 1;
   extern __shared__ float tile[];
-  const int Ho = H / S, Wo = W / S, WP = Wo + 2;
+  const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S, WP = Wo + 2;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int chunk = blockIdx.x % nchunks, worker = blockIdx.x / nchunks, nworkers = gridDim.x / nchunks;
   const int c0 = chunk * CC;
@@ -1006,7 +1010,7 @@ sdw_bwd_kernel(const T* __restrict__ dsh, const T* __restrict__ s_raw, const T* 
   const int colA = (S == 1) ? 0 : (odd_w ? (wi + 1) / 2 : wi / 2);
   const int colB = (wi - 1) / 2;  // only used when odd_w (kw = 2)
   float st[11][4] = {};
-  const int nb = H / THI;
+  const int nb = (H + THI - 1) / THI;  // the last band may be partial (H not a multiple of THI)
   const int ntiles = NP * nb;
   const int nvec = NR * WP * cvn;
   for (int t = worker; t < ntiles; t += nworkers) {
@@ -1047,11 +1051,12 @@ sdw_bwd_kernel(const T* __restrict__ dsh, const T* __restrict__ s_raw, const T* 
     auto row_body = [&](const int hl, auto par_c) {
       constexpr int PAR = decltype(par_c)::value;
       const int hi = hi0 + hl;
+      if (hi >= H) return;  // partial last band
       float e[4], ea[4], sg[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
       const long eoff = (((long)p * H + hi) * W + wi) * C + cch;
 #pragma unroll
       for (int j = 0; j < 4; ++j) e[j] = e_nxt[j];
-      if (hl + 1 < THI) ldq(e_raw + eoff + (long)W * C, e_nxt);
+      if (hl + 1 < THI && hi + 1 < H) ldq(e_raw + eoff + (long)W * C, e_nxt);
       {
         const float4 q0 = *reinterpret_cast<const float4*>(sco + 3 * CC + cq * 4);
         const float4 q1 = *reinterpret_cast<const float4*>(sco + 4 * CC + cq * 4);
@@ -1143,13 +1148,12 @@ static int sdw_bwd_launch(const void* dsh, const void* s_raw, const void* e_raw,
                           const float* coef1, const float* wgt, void* dE, float* partial, int P, int NP, int H, int W,
                           int C, cudaStream_t st) {
   constexpr int V = VecT<T>::V;
-  const int Wo = W / S;
+  const int Wo = (W + S - 1) / S;
   int CC = 1024 / W;
   if (CC > 128) CC = 128;
   while (CC >= 8 && (C % CC != 0)) CC /= 2;
   DWN_REQUIRE(CC >= 8 && C % CC == 0 && (CC / 4) * W <= 256, "dwn_sdw_bwd: unsupported C=%d W=%d", C, W);
-  int THI = (H % 8 == 0) ? 8 : (H % 4 == 0 ? 4 : 2);
-  DWN_REQUIRE(H % THI == 0, "dwn_sdw_bwd: H must be even");
+  int THI = (H % 8 == 0) ? 8 : (H % 4 == 0 ? 4 : 2);  // odd H: bands of 2 rows, the last one partial
   const int NR = S == 1 ? THI + 2 : THI / 2 + 1;
   size_t sm = ((size_t)NR * (Wo + 2) + 7) * CC * sizeof(float);
   size_t sm_red = (size_t)(CC / 4) * W * 11 * 4 * sizeof(float);
@@ -1187,6 +1191,7 @@ template <int S>
 static int sdw_bwd_v3_launch(const void* dsh, const void* s_raw, const void* e_raw, const float* coef2,
                              const float* bcoef2, const float* coef1, const float* wgt, void* dE, float* partial, int P,
                              int NP, int H, int W, int C, cudaStream_t st) {
+  if (H % S != 0 || W % S != 0) return 1;  // ceil-sized outputs take the generic kernel
   const int Wo = W / S;
   int CC = 1024 / W;
   if (CC > 128) CC = 128;

@@ -183,8 +183,8 @@ template <int CIN>
 __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ coef,
                                 const float* __restrict__ pe_t, const float* __restrict__ pe_h,
                                 const float* __restrict__ pe_w, float* __restrict__ out, bf16* __restrict__ out_bf,
-                                float* __restrict__ partial, int next_stride, int B, int Tn, int H, int W, int C0,
-                                int cqc, FastDiv dw, FastDiv dh, FastDiv dplane) {
+                                float* __restrict__ partial, NearestMap nh, NearestMap nw, int B, int Tn, int H, int W,
+                                int C0, int cqc, FastDiv dw, FastDiv dh, FastDiv dplane) {
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
   const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
@@ -238,7 +238,7 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
       // (inputs with many repeated values round coherently: mean(Xb) - mean(X) does not average out)
 #pragma unroll
       for (int j = 0; j < 4; ++j) st[2][j] += out_bf ? __bfloat162float(__float2bfloat16_rn(o[j])) : o[j];
-      if (partial && (hq % next_stride == 0) && (wq % next_stride == 0)) {
+      if (partial && nh.dst(hq) >= 0 && nw.dst(wq) >= 0) {  // positions the next block's shortcut gathers
 #pragma unroll
         for (int j = 0; j < 4; ++j) { st[0][j] += o[j]; st[1][j] = fmaf(o[j], o[j], st[1][j]); }
       }
@@ -260,7 +260,8 @@ extern "C" int dwn_stem_fwd(const float* x, const float* w, const float* coef, c
 #define CASE(N)                                                                                                   \
   case N:                                                                                                         \
     stem_fwd_kernel<N><<<grid, block, sm, (cudaStream_t)stream>>>(x, w, coef, pe_t, pe_h, pe_w, out, (bf16*)out_bf, \
-                                                                  partial, next_stride, B, Tn, H, W, C0, cqc,      \
+                                                                  partial, NearestMap(H, dwn_ceil_div(H, next_stride)),  \
+                                                                  NearestMap(W, dwn_ceil_div(W, next_stride)), B, Tn, H, W, C0, cqc, \
                                                                   FastDiv(W), FastDiv(H), FastDiv(Tn * H * W));        \
     break;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
@@ -287,7 +288,7 @@ sdw_fwd_kernel(const T* __restrict__ in, const float* __restrict__ coef, const f
   constexpr int V = VecT<T>::V;
   constexpr int NR = (THO - 1) * S + 3;
   extern __shared__ float tile[];
-  const int Ho = H / S, Wo = W / S, WP = W + 2;
+  const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S, WP = W + 2;  // conv k=3 pad=1 stride S: ceil(size / S)
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int chunk = blockIdx.x % nchunks, worker = blockIdx.x / nchunks, nworkers = gridDim.x / nchunks;
   const int c0 = chunk * CC;
@@ -398,7 +399,7 @@ template <typename T, int S>
 static int sdw_fwd_launch(const void* in, const float* coef, const float* wgt, void* out, float* partial, int P, int NP,
                           int H, int W, int C, cudaStream_t st) {
   constexpr int V = VecT<T>::V;
-  const int Ho = H / S, Wo = W / S;
+  const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S;
   int CC = 1024 / Wo;  // (CC/4)*Wo = 256 threads
   if (CC > 128) CC = 128;
   while (CC >= 8 && (C % CC != 0)) CC /= 2;
@@ -433,6 +434,7 @@ static int sdw_fwd_launch(const void* in, const float* coef, const float* wgt, v
 template <int S>
 static int sdw_fwd_v3_launch(const void* in, const float* coef, const float* wgt, void* out, float* partial, int P, int NP,
                              int H, int W, int C, cudaStream_t st) {
+  if (H % S != 0 || W % S != 0) return 1;  // ceil-sized outputs take the generic kernel
   const int Ho = H / S, Wo = W / S;
   int CC = 1024 / Wo;
   if (CC > 128) CC = 128;
@@ -480,7 +482,6 @@ extern "C" int dwn_sdw_fwd(const void* in, const float* coef, const float* wgt, 
                            int H, int W, int C, int stride, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DWN_REQUIRE(stride == 1 || stride == 2, "dwn_sdw_fwd: stride %d unsupported", stride);
-  DWN_REQUIRE(H % stride == 0 && W % stride == 0, "dwn_sdw_fwd: H,W must be divisible by stride");
   if (dtype == DWN_DT_F32)
     return stride == 1 ? sdw_fwd_launch<float, 1>(in, coef, wgt, out, partial, P, NP, H, W, C, st)
                        : sdw_fwd_launch<float, 2>(in, coef, wgt, out, partial, P, NP, H, W, C, st);
@@ -845,8 +846,8 @@ __global__ void block_out_kernel(const T* __restrict__ y_raw, const float* __res
                                  const float* __restrict__ xin, const float* __restrict__ coef_sc,
                                  const float* __restrict__ pe_t, const float* __restrict__ pe_h,
                                  const float* __restrict__ pe_w, float* __restrict__ out, bf16* __restrict__ out_bf,
-                                 float* __restrict__ partial, int next_stride, int B, int Tn, int Ho, int Wo, int Ci,
-                                 int Co, int stride, int cqc, FastDiv dw, FastDiv dh, FastDiv dt) {
+                                 float* __restrict__ partial, NearestMap nh, NearestMap nw, int B, int Tn, int Ho, int Wo,
+                                 int Ci, int Co, NearestMap mh, NearestMap mw, int cqc, FastDiv dw, FastDiv dh, FastDiv dt) {
   extern __shared__ float smem[];
   const int tid = threadIdx.x;
   const int cq = tid % cqc, lane = tid / cqc, ln = blockDim.x / cqc;
@@ -861,7 +862,7 @@ __global__ void block_out_kernel(const T* __restrict__ y_raw, const float* __res
     hs[j] = coef_sc[Co + c + j];
   }
   float st[3][4] = {};
-  const int Hi = Ho * stride, Wi = Wo * stride;
+  const int Hi = mh.in, Wi = mw.in;
   const int Mo = B * Tn * Ho * Wo;
   // the two streamed operands (Y_raw quad, shortcut quad) go through a per-thread cp.async pipeline (see ThreadPipe):
   // with ~90 registers only 2 CTAs fit per SM and plain loads kept < 25 KB in flight per SM
@@ -874,7 +875,7 @@ __global__ void block_out_kernel(const T* __restrict__ y_raw, const float* __res
       const int wq = dw.mod(m), r1 = dw.div(m);
       const int hq = dh.mod(r1), bt = dh.div(r1);
       pipe_issue_quad<T>(pipe.slot(k, 0), y_raw + (long)m * Co + c);
-      cp_async16_ok(pipe.slot(k, 1), xin + (((long)bt * Hi + hq * stride) * Wi + wq * stride) * Ci + ci);
+      cp_async16_ok(pipe.slot(k, 1), xin + (((long)bt * Hi + mh.src(hq)) * Wi + mw.src(wq)) * Ci + ci);
     }
     cp_async_commit();
   };
@@ -905,7 +906,7 @@ __global__ void block_out_kernel(const T* __restrict__ y_raw, const float* __res
     if (out_bf) stq(out_bf + (long)m * Co + c, o);
 #pragma unroll
     for (int j = 0; j < 4; ++j) st[2][j] += out_bf ? __bfloat162float(__float2bfloat16_rn(o[j])) : o[j];  // see stem_fwd_kernel
-    if (partial && (hq % next_stride == 0) && (wq % next_stride == 0)) {
+    if (partial && nh.dst(hq) >= 0 && nw.dst(wq) >= 0) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) { st[0][j] += o[j]; st[1][j] = fmaf(o[j], o[j], st[1][j]); }
     }
@@ -918,8 +919,11 @@ __global__ void block_out_kernel(const T* __restrict__ y_raw, const float* __res
 extern "C" int dwn_block_out(const void* y_raw, const float* coef4, const float* dp, const float* xin,
                              const float* coef_sc, const float* pe_t, const float* pe_h, const float* pe_w, float* out,
                              void* out_bf, float* partial, int P, int next_stride, int B, int Tn, int Ho, int Wo, int Ci,
-                             int Co, int stride, int dtype, void* stream) {
+                             int Co, int stride, int Hi, int Wi, int dtype, void* stream) {
   DWN_REQUIRE(Ci % 4 == 0 && Co % 4 == 0, "dwn_block_out: channels must be multiples of 4");
+  DWN_REQUIRE(Ho == dwn_ceil_div(Hi, stride) && Wo == dwn_ceil_div(Wi, stride),
+              "dwn_block_out: output %dx%d is not ceil(%dx%d / %d)", Ho, Wo, Hi, Wi, stride);
+  const NearestMap mh(Hi, Ho), mw(Wi, Wo), nh(Ho, dwn_ceil_div(Ho, next_stride)), nw(Wo, dwn_ceil_div(Wo, next_stride));
   int cqc = dwn_largest_divisor_le(Co / 4, 64), ln = 256 / cqc;
   dim3 grid(P, (Co / 4) / cqc), block(cqc * ln);
   size_t sm = (size_t)block.x * 12 * sizeof(float);
@@ -929,12 +933,12 @@ extern "C" int dwn_block_out(const void* y_raw, const float* coef4, const float*
   if (dtype == DWN_DT_F32)
     block_out_kernel<float><<<grid, block, sm, (cudaStream_t)stream>>>((const float*)y_raw, coef4, dp, xin, coef_sc, pe_t,
                                                                        pe_h, pe_w, out, (bf16*)out_bf, partial,
-                                                                       next_stride, B, Tn, Ho, Wo, Ci, Co, stride, cqc,
+                                                                       nh, nw, B, Tn, Ho, Wo, Ci, Co, mh, mw, cqc,
                                                                        FastDiv(Wo), FastDiv(Ho), FastDiv(Tn));
   else
     block_out_kernel<bf16><<<grid, block, sm, (cudaStream_t)stream>>>((const bf16*)y_raw, coef4, dp, xin, coef_sc, pe_t,
                                                                       pe_h, pe_w, out, (bf16*)out_bf, partial,
-                                                                      next_stride, B, Tn, Ho, Wo, Ci, Co, stride, cqc,
+                                                                      nh, nw, B, Tn, Ho, Wo, Ci, Co, mh, mw, cqc,
                                                                       FastDiv(Wo), FastDiv(Ho), FastDiv(Tn));
   DWN_LAUNCH_CHECK();
   return 0;

@@ -303,8 +303,6 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
     X = _empty((M0, C0), torch.float32, dev)
     Xb = _empty((M0, C0), torch.bfloat16, dev) if bf else None
     sc_part = _empty((_P, 3, C0), torch.float32, dev) if training else None
-    if H % strides[0] or W % strides[0]:
-        raise NotImplementedError("spatial size must be divisible by the block stride")
     call("dwn_stem_fwd", x, stem_conv.weight, coef0, pe[0], pe[1], pe[2], X, Xb, sc_part, _P, strides[0], B, Cin, T, H,
          W, C0, st, _tag="stem_fwd", _bytes=M0 * (Cin * 4 + C0 * (4 + (2 if bf else 0))))
     if save:
@@ -318,9 +316,8 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         co = feats[i + 1] if i < nb - 1 else feats[-1]
         s = strides[i]
         mid = ci * er
-        if Hi % s or Wi % s:
-            raise NotImplementedError("spatial size must be divisible by the block stride")
-        Ho, Wo = Hi // s, Wi // s
+        # conv (k=3, pad=1, stride s) and interpolate_shortcut (dwiseneuro.py:127-129) both produce ceil(size / s)
+        Ho, Wo = -(-Hi // s), -(-Wi // s)
         Mi, Mo, Nsp = B * T * Hi * Wi, B * T * Ho * Wo, T * Ho * Wo
         # 1. point-wise expansion (tcgen05 GEMM / SIMT fp32)
         wpw = blk.conv_pw[0].weight
@@ -403,7 +400,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         Xnb = _empty((Mo, co), torch.bfloat16, dev) if (bf and not last) else None
         nsc_part = _empty((_P, 3, co), torch.float32, dev) if (training and not last) else None
         call("dwn_block_out", Y, coef4, dp, X, coef_sc, pe[0], pe[1], pe[2], Xn, Xnb, nsc_part, _P,
-             1 if last else strides[i + 1], B, T, Ho, Wo, ci, co, s, dcode, st, _tag="block_out",
+             1 if last else strides[i + 1], B, T, Ho, Wo, ci, co, s, Hi, Wi, dcode, st, _tag="block_out",
              _bytes=Mo * (co * es + ci * 4 + co * (4 + (2 if bf else 0))))
         if save:
             sv.blocks.append(SimpleNamespace(X=X, Xb=Xb, E=E, S=S, Tm=Tm, A=A, Y=Y, Wb=Wb, coef1=coef1, coef2=coef2,

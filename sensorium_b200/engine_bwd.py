@@ -131,8 +131,8 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         ci, co, mid, s, rd = b.ci, b.co, b.mid, b.s, b.rd
         Mi, Mo, Nsp = B * T * b.Hi * b.Wi, B * T * b.Ho * b.Wo, T * b.Ho * b.Wo
         part = _empty((_P, 4, co), torch.float32, dev)
-        call("dwn_block_bwd_reduce", dO, b.Y, b.coef4, b.dp, b.X, b.coef_sc, part, _P, B, T, b.Ho, b.Wo, ci, co, s, dcode,
-             st, _tag="block_bwd_reduce", _bytes=Mo * (co * (4 + es) + ci * 4))
+        call("dwn_block_bwd_reduce", dO, b.Y, b.coef4, b.dp, b.X, b.coef_sc, part, _P, B, T, b.Ho, b.Wo, ci, co, s, b.Hi,
+             b.Wi, dcode, st, _tag="block_bwd_reduce", _bytes=Mo * (co * (4 + es) + ci * 4))
         bcoef4 = _bn_bwd(part, _P, 4, 0, Mo, blk.conv_pwl[1].bn, grads, co, st, dev)
         bcoef_sc = _bn_bwd(part, _P, 4, 2, Mo, blk.bn_sc.bn, grads, co, st, dev)
         dY = _empty((Mo, co), adt, dev)

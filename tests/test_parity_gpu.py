@@ -815,3 +815,53 @@ def test_train_step_raw_clips_equal_dense(dev):
         assert l0 == l1, (raw, graph, l0, l1)
         for a, b in zip(m0.nn_module.state_dict().values(), m1.nn_module.state_dict().values()):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("HW", [30, 27])
+def test_ceil_shortcut_for_sizes_the_stride_does_not_divide(dev, HW):
+    """interpolate_shortcut (dwiseneuro.py:125-129) resizes the shortcut to ceil(size / stride) with F.interpolate
+    (mode="nearest": source index floor(dst * in / out)), and the strided depth-wise conv (k=3, pad=1) produces the same
+    ceil size.  30 -> 15 -> 15 -> 8 exercises it in the last block, 27 -> 14 -> 14 -> 7 in the first and the last; train
+    mode forward, loss and every gradient against the oracle (fp32 <= 1e-4; bf16 outputs <= 2e-2)."""
+    x = O.synthetic_clip(3, 8, 32, seed=4)[..., :HW, :HW].contiguous().to(dev)
+    tg, w = O.synthetic_targets(3, TINY_OUTS, 8, seed=6)
+    tg, w = [t.to(dev) for t in tg], w.to(dev)
+    kw = dict(TINY_KW, drop_path_rate=0.0, drop_rate=0.0)
+    cfg = O.make_cfg(TINY_OUTS, **kw)
+    for mode, tol in (("fp32", FP32_TOL), ("bf16", BF16_TOL)):
+        from sensorium_b200 import DwiseNeuro
+        from sensorium_b200.utils import init_weights
+        torch.manual_seed(1)
+        net = DwiseNeuro(readout_outputs=TINY_OUTS, **kw)
+        init_weights(net)
+        net = net.to(dev).train()
+        net.precision = mode
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        names = [k for k, _ in net.named_parameters()]
+        for k in names:
+            sd[k].requires_grad_(True)
+        ref = O.dwiseneuro_forward(x, sd, cfg, None, True)
+        ref_loss = O.mice_poisson_loss(ref, tg, w)
+        ref_loss.backward()
+        out = net(x)
+        loss = O.mice_poisson_loss(out, tg, w)
+        loss.backward()
+        for a, b in zip(out, ref):
+            assert a.shape == b.shape and rel(a, b) < tol, (mode, rel(a, b))
+        for k, v in net.state_dict().items():
+            if "running_" in k:
+                assert rel(v, sd[k]) < tol, k
+        if mode == "fp32":
+            gmax = max(float(sd[k].grad.abs().max()) for k in names if sd[k].grad is not None)
+            for k, p in net.named_parameters():
+                if sd[k].grad is None:
+                    assert p.grad is None
+                    continue
+                err = float((p.grad - sd[k].grad).abs().max())
+                assert err <= tol * max(float(sd[k].grad.abs().max()), 3e-3 * gmax) + 1e-6 * gmax, (k, err)
+    # eval mode too (the predictor path), one readout
+    net.eval()
+    net.precision = "fp32"
+    with torch.no_grad():
+        sd_e = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        assert rel(net(x, 1), O.dwiseneuro_forward(x, sd_e, cfg, 1, False)) < FP32_TOL
