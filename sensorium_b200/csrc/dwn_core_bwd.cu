@@ -1149,9 +1149,8 @@ static int sdw_bwd_launch(const void* dsh, const void* s_raw, const void* e_raw,
                           int C, cudaStream_t st) {
   constexpr int V = VecT<T>::V;
   const int Wo = (W + S - 1) / S;
-  int CC = 1024 / W;
-  if (CC > 128) CC = 128;
-  while (CC >= 8 && (C % CC != 0)) CC /= 2;
+  int CC = 128;  // largest power of two that divides C with (CC/4)*W <= 256 threads
+  while (CC >= 8 && (C % CC != 0 || (CC / 4) * W > 256)) CC /= 2;
   DWN_REQUIRE(CC >= 8 && C % CC == 0 && (CC / 4) * W <= 256, "dwn_sdw_bwd: unsupported C=%d W=%d", C, W);
   int THI = (H % 8 == 0) ? 8 : (H % 4 == 0 ? 4 : 2);  // odd H: bands of 2 rows, the last one partial
   const int NR = S == 1 ? THI + 2 : THI / 2 + 1;

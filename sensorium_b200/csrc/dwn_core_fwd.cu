@@ -400,9 +400,8 @@ static int sdw_fwd_launch(const void* in, const float* coef, const float* wgt, v
                           int H, int W, int C, cudaStream_t st) {
   constexpr int V = VecT<T>::V;
   const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S;
-  int CC = 1024 / Wo;  // (CC/4)*Wo = 256 threads
-  if (CC > 128) CC = 128;
-  while (CC >= 8 && (C % CC != 0)) CC /= 2;
+  int CC = 128;  // largest power of two that divides C with (CC/4)*Wo <= 256 threads
+  while (CC >= 8 && (C % CC != 0 || (CC / 4) * Wo > 256)) CC /= 2;
   DWN_REQUIRE(CC >= 8 && C % CC == 0 && (CC / 4) * Wo <= 256, "dwn_sdw_fwd: unsupported C=%d W=%d", C, W);
   int THO = (S == 1 && Ho % 8 == 0) ? 8 : (Ho % 4 == 0 ? 4 : (Ho % 2 == 0 ? 2 : 1));
   const int NR = (THO - 1) * S + 3;

@@ -848,10 +848,13 @@ def test_ceil_shortcut_for_sizes_the_stride_does_not_divide(dev, HW):
         loss.backward()
         for a, b in zip(out, ref):
             assert a.shape == b.shape and rel(a, b) < tol, (mode, rel(a, b))
-        for k, v in net.state_dict().items():
-            if "running_" in k:
-                assert rel(v, sd[k]) < tol, k
         if mode == "fp32":
+            for k, v in net.state_dict().items():
+                if "running_var" in k:
+                    assert rel(v, sd[k]) < tol, k
+                elif "running_mean" in k:  # a mean is judged on the scale of the channel's standard deviation
+                    scale = max(float(sd[k].abs().max()), float(sd[k.replace("running_mean", "running_var")].sqrt().max()))
+                    assert float((v - sd[k]).abs().max()) < tol * scale, k
             gmax = max(float(sd[k].grad.abs().max()) for k in names if sd[k].grad is not None)
             for k, p in net.named_parameters():
                 if sd[k].grad is None:
