@@ -311,21 +311,25 @@ struct FastDiv {
 // For out <= in the map is strictly increasing, so it has an inverse on its image (dst(), used by the backward scatter
 // and by the producers that take BatchNorm statistics over exactly the gathered positions).
 struct NearestMap {
-  int in, out, s;
+  int in, out, sh;  // sh >= 0: in == out << sh (the stride is a power of two and divides the size): shifts only
   float scale;
-  __host__ __device__ NearestMap() : in(1), out(1), s(1), scale(1.f) {}
-  __host__ NearestMap(int in_, int out_)
-      : in(in_), out(out_), s((out_ > 0 && in_ % out_ == 0) ? in_ / out_ : 0), scale((float)in_ / (float)out_) {}
+  __host__ __device__ NearestMap() : in(1), out(1), sh(0), scale(1.f) {}
+  __host__ NearestMap(int in_, int out_) : in(in_), out(out_), sh(-1), scale((float)in_ / (float)out_) {
+    for (int k = 0; k < 8; ++k)
+      if (in_ == (out_ << k)) sh = k;
+  }
   __device__ __forceinline__ int src(int d) const {
-    if (s) return d * s;
+    if (sh >= 0) return d << sh;
     const int v = (int)floorf((float)d * scale);
     return v < in - 1 ? v : in - 1;
   }
   __device__ __forceinline__ int dst(int x) const {  // -1: position x is not gathered
-    if (s) return (x % s == 0) ? x / s : -1;
+    if (sh >= 0) return (x & ((1 << sh) - 1)) == 0 ? (x >> sh) : -1;
     const int d0 = (int)((float)x / scale);
-    for (int d = (d0 > 0 ? d0 - 1 : 0); d <= d0 + 1 && d < out; ++d)
-      if (src(d) == x) return d;
+    for (int d = (d0 > 0 ? d0 - 1 : 0); d <= d0 + 1 && d < out; ++d) {
+      const int v = (int)floorf((float)d * scale);
+      if ((v < in - 1 ? v : in - 1) == x) return d;
+    }
     return -1;
   }
 };
