@@ -24,8 +24,11 @@ def test_reference_arm_prints_one_json_line():
 
 
 def test_committed_gpu_bench_line_has_every_contract_key():
-    d = json.loads((ROOT / "profiles" / "r1_bench_final_default.json").read_text().splitlines()[0])
-    assert BASE_KEYS | {"gpu_launches", "clocks", "roofline", "cpu_baseline"} <= set(d)
+    d = json.loads((ROOT / "profiles" / "r2_bench_final_default.json").read_text().splitlines()[0])
+    assert BASE_KEYS | {"gpu_launches", "clocks", "roofline", "cpu_baseline", "eager_b200", "c4", "infer", "gemm"} <= set(d)
+    assert d["eager_b200"]["ms_per_step"] > d["ms_per_step"] and d["c4"]["value"] > 0
+    assert d["infer"]["models"] == 7 and d["infer"]["bf16"]["value"] > d["infer"]["fp32"]["value"] > 0
+    assert all("frac_of_bf16_peak" in v for k, v in d["gemm"].items() if not k.startswith("_"))
     assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["dtype"] == "bf16"
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     r = d["roofline"]
