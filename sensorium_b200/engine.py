@@ -26,7 +26,20 @@ BN_MOM, BN_EPS = 0.1, 1e-5
 _P = 592          # partial-stat rows for kernels whose grid.y may be 1 (4 CTAs / SM)
 _P_SDW = 148      # spatial dw kernels have >= 3 channel chunks in grid.y
 _P_MOM = 296
-_J_SE = 16
+_J_SE = 8           # se_pool CTAs per sample: 256 CTAs = one balanced wave (16 -> 512 CTAs = 1.15 waves at 3 CTAs/SM: 4.7 vs 5.9 TB/s)
+
+
+def _p_tdw(nelem: int) -> int:
+    """Persistent CTAs per channel chunk of the temporal depth-wise kernels: 592 for the large early blocks, 148 where a
+    launch moves < 150 M elements (blocks 4-8 at C2; measured with tests/gpu_checks/kbench.py, KB_P sweep: the late
+    blocks gain 5-15 % with fewer, longer-lived CTAs, the early blocks lose 35 %)."""
+    return _P if nelem > 150_000_000 else 148
+
+
+def _p_sdw(nelem_in: int) -> int:
+    """Same for the spatial depth-wise kernels (KB_PS sweep): 74 workers per channel chunk unless the input tile stream is
+    the 940 M-element block-0 tensor."""
+    return _P_SDW if nelem_in > 600_000_000 else 74
 
 _plans = weakref.WeakKeyDictionary()
 
@@ -352,15 +365,17 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         # 2. spatial depth-wise (BN1+SiLU on load)
         S = _empty((Mo, mid), adt, dev)
         part = _empty((_P, 2, mid), torch.float32, dev) if training else None
-        call("dwn_sdw_fwd", E, coef1, blk.spat_covn_dw[0].weight, S, part, _P_SDW, B * T, Hi, Wi, mid, s, dcode, st,
+        psdw = _p_sdw(Mi * mid)
+        call("dwn_sdw_fwd", E, coef1, blk.spat_covn_dw[0].weight, S, part, psdw, B * T, Hi, Wi, mid, s, dcode, st,
              _tag="sdw_fwd", _bytes=(Mi + Mo) * mid * es)
-        coef2 = _bn_coef(blk.spat_covn_dw[1].bn, part, _P_SDW, Mo, mid, 0, training, st, dev)
+        coef2 = _bn_coef(blk.spat_covn_dw[1].bn, part, psdw, Mo, mid, 0, training, st, dev)
         # 3. temporal depth-wise (BN2+SiLU on load)
         Tm = _empty((Mo, mid), adt, dev)
         part = _empty((_P, 2, mid), torch.float32, dev) if training else None
-        call("dwn_tdw_fwd", S, coef2, blk.temp_covn_dw[0].weight, Tm, part, _P, B, T, Ho * Wo, mid, dcode, st,
+        ptdw = _p_tdw(Mo * mid)
+        call("dwn_tdw_fwd", S, coef2, blk.temp_covn_dw[0].weight, Tm, part, ptdw, B, T, Ho * Wo, mid, dcode, st,
              _tag="tdw_fwd", _bytes=2 * Mo * mid * es)
-        coef3 = _bn_coef(blk.temp_covn_dw[1].bn, part, _P, Mo, mid, 0, training, st, dev)
+        coef3 = _bn_coef(blk.temp_covn_dw[1].bn, part, ptdw, Mo, mid, 0, training, st, dev)
         # 4. squeeze-excite: a = SiLU(BN3(Tm)), gate folded into per-sample projection weights
         rd = blk.se.conv_reduce.weight.shape[0]
         pool_part = _empty((B, _J_SE, mid), torch.float32, dev)

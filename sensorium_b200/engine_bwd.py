@@ -14,11 +14,11 @@ import torch
 
 from . import _lib
 from ._lib import call, gemm
-from .engine import (BF16, F32, _P, _P_SDW, _empty, _fork, _join, _nullctx, _shadow, _side_streams, _split_k,
-                     _stream)
+from .engine import (BF16, F32, _P, _P_SDW, _empty, _fork, _join, _nullctx, _p_sdw, _p_tdw, _shadow, _side_streams,
+                     _split_k, _stream)
 
 _J_CORTEX = 32
-_J_TDW = 37
+_J_TDW = 9   # tdw_bwd_reduce CTAs per sample (kbench KB_JTDW sweep: 9 is best at every block size)
 
 
 def _bn_bwd(part, P, NQ, q0, count, bn, grads, C, st, dev):
@@ -166,22 +166,24 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         call("dwn_tdw_bwd_reduce", da, b.Tm, b.coef3, dmean, Nsp, part, _J_TDW, B, mid, dcode, st, _tag="tdw_bwd_reduce",
              _bytes=2 * Mo * mid * es)
         bcoef3 = _bn_bwd(part, B * _J_TDW, 2, 0, Mo, blk.temp_covn_dw[1].bn, grads, mid, st, dev)
-        part7 = _empty((_P, 7, mid), torch.float32, dev)
-        call("dwn_tdw_bwd", da, b.Tm, b.S, b.coef3, bcoef3, b.coef2, blk.temp_covn_dw[0].weight, dmean, part7, _P, B, T,
+        ptdw = _p_tdw(Mo * mid)
+        part7 = _empty((ptdw, 7, mid), torch.float32, dev)
+        call("dwn_tdw_bwd", da, b.Tm, b.S, b.coef3, bcoef3, b.coef2, blk.temp_covn_dw[0].weight, dmean, part7, ptdw, B, T,
              b.Ho * b.Wo, mid, dcode, st, _tag="tdw_bwd", _bytes=4 * Mo * mid * es)
-        bcoef2 = _bn_bwd(part7, _P, 7, 0, Mo, blk.spat_covn_dw[1].bn, grads, mid, st, dev)
+        bcoef2 = _bn_bwd(part7, ptdw, 7, 0, Mo, blk.spat_covn_dw[1].bn, grads, mid, st, dev)
         dwt = torch.empty_like(blk.temp_covn_dw[0].weight)
-        call("dwn_dw_wgrad_finalize", part7, _P, 7, 2, 5, dwt, mid, st)
+        call("dwn_dw_wgrad_finalize", part7, ptdw, 7, 2, 5, dwt, mid, st)
         grads[blk.temp_covn_dw[0].weight] = dwt
         # spatial dw backward (da now holds d s_hat)
         dE = _empty((Mi, mid), adt, dev)
-        part11 = _empty((_P_SDW, 11, mid), torch.float32, dev)
-        call("dwn_sdw_bwd", da, b.S, b.E, b.coef2, bcoef2, b.coef1, blk.spat_covn_dw[0].weight, dE, part11, _P_SDW, B * T,
+        psdw = _p_sdw(Mi * mid)
+        part11 = _empty((psdw, 11, mid), torch.float32, dev)
+        call("dwn_sdw_bwd", da, b.S, b.E, b.coef2, bcoef2, b.coef1, blk.spat_covn_dw[0].weight, dE, part11, psdw, B * T,
              b.Hi, b.Wi, mid, s, dcode, st, _tag="sdw_bwd", _bytes=(2 * Mo + 2 * Mi) * mid * es)
         del da
-        bcoef1 = _bn_bwd(part11, _P_SDW, 11, 0, Mi, blk.conv_pw[1].bn, grads, mid, st, dev)
+        bcoef1 = _bn_bwd(part11, psdw, 11, 0, Mi, blk.conv_pw[1].bn, grads, mid, st, dev)
         dws = torch.empty_like(blk.spat_covn_dw[0].weight)
-        call("dwn_dw_wgrad_finalize", part11, _P_SDW, 11, 2, 9, dws, mid, st)
+        call("dwn_dw_wgrad_finalize", part11, psdw, 11, 2, 9, dws, mid, st)
         grads[blk.spat_covn_dw[0].weight] = dws
         wpw = blk.conv_pw[0].weight
         dXpw = _empty((Mi, ci), torch.float32, dev)

@@ -50,7 +50,8 @@ def bcoef(C):
 shapes = [  # (tag, ci, H, W, stride)
     ("blk0", 64, 64, 64, 2), ("blk1", 64, 32, 32, 1), ("blk4", 128, 32, 32, 2), ("blk5", 128, 16, 16, 1),
     ("blk7", 256, 16, 16, 2), ("blk8", 256, 8, 8, 1)]
-P, PS = 592, 148
+import os
+P, PS = int(os.environ.get("KB_P", 592)), int(os.environ.get("KB_PS", 148))
 for tag, ci, H, W, s in shapes:
     mid = ci * 7
     Ho, Wo = H // s, W // s
@@ -67,11 +68,13 @@ for tag, ci, H, W, s in shapes:
     es = 2
     timeit(f"sdw_fwd {tag}", lambda: call("dwn_sdw_fwd", E, c1, ws, S, part, PS, B * T, H, W, mid, s, 1, st), (Mi + Mo) * mid * es)
     timeit(f"tdw_fwd {tag}", lambda: call("dwn_tdw_fwd", S, c2, wt, Tm, part, P, B, T, Ho * Wo, mid, 1, st), 2 * Mo * mid * es)
-    pp = torch.empty(B, 16, mid, device=dev)
-    timeit(f"se_pool {tag}", lambda: call("dwn_se_pool", Tm, c3, A, pp, 16, B, T * Ho * Wo, mid, 1, st), 2 * Mo * mid * es)
+    JSE = int(os.environ.get("KB_JSE", 16))
+    pp = torch.empty(B, JSE, mid, device=dev)
+    timeit(f"se_pool {tag}", lambda: call("dwn_se_pool", Tm, c3, A, pp, JSE, B, T * Ho * Wo, mid, 1, st), 2 * Mo * mid * es)
     da = torch.randn(Mo, mid, device=dev).to(torch.bfloat16)
     dmean = torch.randn(B, mid, device=dev) * 0.01
-    timeit(f"tdw_bwd_reduce {tag}", lambda: call("dwn_tdw_bwd_reduce", da, Tm, c3, dmean, T * Ho * Wo, part, 37, B, mid, 1, st), 2 * Mo * mid * es)
+    JT = int(os.environ.get("KB_JTDW", 37))
+    timeit(f"tdw_bwd_reduce {tag}", lambda: call("dwn_tdw_bwd_reduce", da, Tm, c3, dmean, T * Ho * Wo, part, JT, B, mid, 1, st), 2 * Mo * mid * es)
     timeit(f"tdw_bwd {tag}", lambda: call("dwn_tdw_bwd", da, Tm, S, c3, b3, c2, wt, dmean, part, P, B, T, Ho * Wo, mid, 1, st), 4 * Mo * mid * es)
     dE = torch.empty_like(E)
     timeit(f"sdw_bwd {tag}", lambda: call("dwn_sdw_bwd", da, S, E, c2, b2, c1, ws, dE, part, PS, B * T, H, W, mid, s, 1, st), (2 * Mo + 2 * Mi) * mid * es)
