@@ -292,6 +292,15 @@ extern "C" int dwn_block_in_bwd(const float* dXpw, const float* dO, const float*
   dim3 grid(592, (Ci / 4) / cqc), block(cqc * ln);
   const size_t sm = ThreadPipe<4, 4>::bytes(block.x);
   cudaFuncSetAttribute(block_in_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  {  // grid-stride kernel: exactly one resident wave (592 CTAs were 1.33 waves at 3 CTAs per SM: a third of the run
+     // time had two thirds of the SMs idle)
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, block_in_bwd_kernel<0>, (int)block.x, sm) == cudaSuccess &&
+        occ > 0) {
+      int gx = occ * dwn_num_sms() / (int)grid.y;
+      if (gx >= 1) grid.x = gx;
+    }
+  }
   block_in_bwd_kernel<0><<<grid, block, sm, (cudaStream_t)stream>>>(
       dXpw, dO, xin, coef_sc, bcoef_sc, colbias, dXin, B, Tn, Hi, Wi, Ci, Co, NearestMap(Hi, dwn_ceil_div(Hi, stride)),
       NearestMap(Wi, dwn_ceil_div(Wi, stride)), cqc, FastDiv(Wi), FastDiv(Hi), nullptr, nullptr);
