@@ -116,8 +116,9 @@ int dwn_block_in_bwd(const float* dXpw, const float* dO, const float* xin, const
                      const float* colbias, float* dXin, int B, int Tn, int Hi, int Wi, int Ci, int Co, int stride,
                      void* stream);                                                        /* dwiseneuro.py:125-134 */
 int dwn_block_in_bwd_stem(const float* dXpw, const float* dO, const float* xin, const float* coef_sc,
-                          const float* bcoef_sc, const float* colbias, const float* x_in, float* stem_partial, int B, int Tn,
-                          int Hi, int Wi, int Ci, int Co, int stride, void* stream);  /* block 0 + stem reductions fused */
+                          const float* bcoef_sc, const float* colbias, const float* x_in, float* stem_partial, int P, int B, int Tn,
+                          int Hi, int Wi, int Ci, int Co, int stride, void* stream);
+int dwn_block_in_bwd_stem_rows(int Ci);   /* P that fills exactly one resident wave (stem_partial has P rows) */  /* block 0 + stem reductions fused */
 int dwn_stem_bwd_finalize(const float* partial, int P, const double* mom, const float* w, const float* coef, float* dw,
                           float* dgamma, float* dbeta, int B, int cin, long plane, int C0, void* stream);
 int dwn_pool_bwd(const float* dP, float* dX, long BT, int HW, int C, void* stream);       /* dwiseneuro.py:374,400 */

@@ -52,7 +52,7 @@ SIGNATURES = {
     "dwn_block_bwd_reduce": "ppppppp" + "iiiiiiiiiii" + "p",
     "dwn_block_bwd_dy": "pppppp" + "llii" + "p",
     "dwn_block_in_bwd": "ppppppp" + "iiiiiii" + "p",
-    "dwn_block_in_bwd_stem": "pppppppp" + "iiiiiii" + "p",
+    "dwn_block_in_bwd_stem": "pppppppp" + "iiiiiiii" + "p",
     "dwn_stem_bwd_finalize": "pi" + "pppppp" + "iili" + "p",
     "dwn_pool_bwd": "pp" + "lii" + "p",
     "dwn_se_bwd": "ppppppp" + "pppppppp" + "iiii" + "p",
@@ -115,7 +115,8 @@ def lib():
 
 
 def exported_symbols():
-    return ["dwn_last_error", "dwn_abi_version", "dwn_sm_count", "dwn_gemm", *SIGNATURES.keys()]
+    return ["dwn_last_error", "dwn_abi_version", "dwn_sm_count", "dwn_gemm", "dwn_block_in_bwd_stem_rows",
+            "dwn_pw_bwd_prep_scratch", "dwn_opt_chunk", *SIGNATURES.keys()]
 
 
 def _ptr(x):

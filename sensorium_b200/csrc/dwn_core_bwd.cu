@@ -309,13 +309,27 @@ extern "C" int dwn_block_in_bwd(const float* dXpw, const float* dO, const float*
 }
 
 // block 0 variant: the gradient w.r.t. the stem output is consumed on the fly by the stem reductions
-// (partial[592][6][Ci], same layout as dwn_stem_bwd) and never written to HBM.  in_channels == 5 only.
+// (partial[P][6][Ci], same layout as dwn_stem_bwd) and never written to HBM.  in_channels == 5 only.
+// P = grid rows; dwn_block_in_bwd_stem_rows() returns the value that fills exactly one resident wave.
+extern "C" int dwn_block_in_bwd_stem_rows(int Ci) {
+  int cqc = dwn_largest_divisor_le(Ci / 4, 64), ln = 256 / cqc;
+  const int threads = cqc * ln, ny = (Ci / 4) / cqc;
+  size_t sm = (size_t)threads * 24 * sizeof(float);
+  if (ThreadPipe<4, 4>::bytes(threads) > sm) sm = ThreadPipe<4, 4>::bytes(threads);
+  cudaFuncSetAttribute(block_in_bwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, block_in_bwd_kernel<5>, threads, sm) != cudaSuccess || occ < 1)
+    return 592;
+  const int p = occ * dwn_num_sms() / ny;
+  return p >= 1 ? p : 592;
+}
 extern "C" int dwn_block_in_bwd_stem(const float* dXpw, const float* dO, const float* xin, const float* coef_sc,
                                      const float* bcoef_sc, const float* colbias, const float* x_in, float* stem_partial,
-                                     int B, int Tn, int Hi, int Wi, int Ci, int Co, int stride, void* stream) {
+                                     int P, int B, int Tn, int Hi, int Wi, int Ci, int Co, int stride, void* stream) {
   DWN_REQUIRE(Co <= 2 * Ci, "dwn_block_in_bwd_stem: channel tiling factor > 2 unsupported");
   int cqc = dwn_largest_divisor_le(Ci / 4, 64), ln = 256 / cqc;
-  dim3 grid(592, (Ci / 4) / cqc), block(cqc * ln);
+  DWN_REQUIRE(P > 0, "dwn_block_in_bwd_stem: P must be positive");
+  dim3 grid(P, (Ci / 4) / cqc), block(cqc * ln);
   size_t sm = (size_t)block.x * 24 * sizeof(float);
   if (ThreadPipe<4, 4>::bytes(block.x) > sm) sm = ThreadPipe<4, 4>::bytes(block.x);
   cudaFuncSetAttribute(block_in_bwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

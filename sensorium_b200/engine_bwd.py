@@ -224,9 +224,10 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         stem_fused = i == 0 and mod.core.stem[0].weight.shape[1] == 5
         if stem_fused:
             # block 0: the gradient w.r.t. the stem output feeds the stem reductions directly (never stored)
-            stem_part = _empty((_P, 6, ci), torch.float32, dev)
-            call("dwn_block_in_bwd_stem", dXpw, dO, b.X, b.coef_sc, bcoef_sc, colbias, sv.x, stem_part, B, T, b.Hi, b.Wi,
-                 ci, co, s, st, _tag="block_in_bwd", _bytes=Mi * ci * 8 + Mo * co * 4 + Mi * 20)
+            p_stem = _lib.lib().dwn_block_in_bwd_stem_rows(ci)
+            stem_part = _empty((p_stem, 6, ci), torch.float32, dev)
+            call("dwn_block_in_bwd_stem", dXpw, dO, b.X, b.coef_sc, bcoef_sc, colbias, sv.x, stem_part, p_stem, B, T,
+                 b.Hi, b.Wi, ci, co, s, st, _tag="block_in_bwd", _bytes=Mi * ci * 8 + Mo * co * 4 + Mi * 20)
             dO = None
         else:
             dXin = _empty((Mi, ci), torch.float32, dev)
@@ -243,7 +244,7 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
     dw = torch.empty_like(stem_conv.weight)
     dgam, dbet = torch.empty_like(stem_bn.weight), torch.empty_like(stem_bn.bias)
     if dO is None:
-        call("dwn_stem_bwd_finalize", stem_part, _P, sv.stem.mom, stem_conv.weight, sv.stem.coef, dw, dgam, dbet, B, cin,
+        call("dwn_stem_bwd_finalize", stem_part, p_stem, sv.stem.mom, stem_conv.weight, sv.stem.coef, dw, dgam, dbet, B, cin,
              sv.T * sv.H * sv.W, C0, st)
     else:
         part = _empty((_P, cin + 1, C0), torch.float32, dev)

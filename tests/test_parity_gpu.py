@@ -868,3 +868,44 @@ def test_ceil_shortcut_for_sizes_the_stride_does_not_divide(dev, HW):
     with torch.no_grad():
         sd_e = {k: v.detach().clone() for k, v in net.state_dict().items()}
         assert rel(net(x, 1), O.dwiseneuro_forward(x, sd_e, cfg, 1, False)) < FP32_TOL
+
+
+def test_fused_adamw_state_dict_roundtrip(dev):
+    """FusedAdamW.state_dict() carries only torch's own per-parameter entries (exp_avg, exp_avg_sq, step) — no raw
+    pointers, no launch caches — and an optimizer restored with load_state_dict continues bit-identically (the flat
+    moment buffers are rebuilt from the loaded state)."""
+    from sensorium_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+
+    def params():
+        g = torch.Generator().manual_seed(3)
+        return [torch.nn.Parameter(torch.randn(s, generator=g).to(dev)) for s in ((33, 7), (5,), (64, 16, 1))]
+
+    def grads(step):
+        g = torch.Generator().manual_seed(100 + step)
+        return [torch.randn(s, generator=g).to(dev) for s in ((33, 7), (5,), (64, 16, 1))]
+
+    pa = params()
+    oa = FusedAdamW(pa, lr=1e-2, weight_decay=0.05)
+    for st in range(3):
+        for p, g in zip(pa, grads(st)):
+            p.grad = g if not (st == 1 and p.dim() == 1) else None   # one tensor skips a step
+        oa.step()
+    sd = oa.state_dict()
+    assert set(sd["param_groups"][0]) == {"lr", "betas", "eps", "weight_decay", "params"} | (
+        set(sd["param_groups"][0]) & {"foreach", "maximize", "capturable", "differentiable", "fused"})
+    for ent in sd["state"].values():
+        assert set(ent) == {"exp_avg", "exp_avg_sq", "step"}
+    assert [int(sd["state"][i]["step"]) for i in range(3)] == [3, 2, 3]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    ob = FusedAdamW(pb, lr=1e-2, weight_decay=0.05)
+    ob.load_state_dict({"state": {k: {kk: vv.clone() for kk, vv in v.items()} for k, v in sd["state"].items()},
+                        "param_groups": sd["param_groups"]})
+    for st in range(3, 5):
+        for p, q, g in zip(pa, pb, grads(st)):
+            p.grad, q.grad = g.clone(), g.clone()
+        oa.step()
+        ob.step()
+    for p, q in zip(pa, pb):
+        assert torch.equal(p, q)
+        assert torch.equal(oa.state[p]["exp_avg_sq"], ob.state[q]["exp_avg_sq"]) and int(ob.state[q]["step"]) == int(oa.state[p]["step"])
