@@ -106,7 +106,10 @@ int dwn_cast_bf16(const float* in, void* out, long n, void* stream);
  * The reference gets every gradient from torch autograd through the library kernels of dwiseneuro.py; the entry
  * points below are the hand-written backward of the same ops (formulas: SURVEY.md 7.4). */
 int dwn_bn_bwd_finalize(const float* partial, int P, int NQ, int q0, double count, float* dgamma, float* dbeta,
-                        float* bcoef, int C, void* stream);                                /* dwiseneuro.py:9-22 */
+                        float* bcoef, int C, void* stream);
+/* two BatchNorms whose sums share one partial table (quantities q0a.. and q0b..): one launch */
+int dwn_bn_bwd_finalize2(const float* partial, int P, int NQ, int q0a, int q0b, double count, float* dgammaA,
+                         float* dbetaA, float* bcoefA, float* dgammaB, float* dbetaB, float* bcoefB, int C, void* stream);                                /* dwiseneuro.py:9-22 */
 int dwn_block_bwd_reduce(const float* dO, const void* y_raw, const float* coef4, const float* dp, const float* xin,
                          const float* coef_sc, float* partial, int P, int B, int Tn, int Ho, int Wo, int Ci, int Co,
                          int stride, int Hi, int Wi, int dtype, void* stream);                              /* dwiseneuro.py:136-144 */

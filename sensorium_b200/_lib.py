@@ -49,6 +49,7 @@ SIGNATURES = {
     "dwn_split3": "pplp",
     # backward
     "dwn_bn_bwd_finalize": "piiidpppip",
+    "dwn_bn_bwd_finalize2": "piiiidppppppip",
     "dwn_block_bwd_reduce": "ppppppp" + "iiiiiiiiiii" + "p",
     "dwn_block_bwd_dy": "pppppp" + "llii" + "p",
     "dwn_block_in_bwd": "ppppppp" + "iiiiiii" + "p",

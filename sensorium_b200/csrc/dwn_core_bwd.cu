@@ -33,6 +33,37 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
   bcoef[C + c] = (float)(db / count);
 }
 
+// two BatchNorms whose sums live in the same partial table (the projection BN and the shortcut BN of a block, the two BNs
+// of a cortex layer): one launch, blockIdx.y selects the set
+__global__ void __launch_bounds__(1024) bn_bwd_finalize2_kernel(const float* __restrict__ partial, int P, int NQ, int q0a,
+                                                               int q0b, double count, float* __restrict__ dgA,
+                                                               float* __restrict__ dbA, float* __restrict__ bcA,
+                                                               float* __restrict__ dgB, float* __restrict__ dbB,
+                                                               float* __restrict__ bcB, int C) {
+  __shared__ double s_red[512];
+  const int c = blockIdx.x * 8 + (threadIdx.x & 7);
+  const bool second = blockIdx.y != 0;
+  const int q0 = second ? q0b : q0a;
+  double da, db;
+  finalize_colsum2(partial, P, NQ, q0, q0 + 1, C, c < C ? c : 0, c < C, s_red, da, db);
+  if (threadIdx.x >= 8 || c >= C) return;
+  float* dbeta = second ? dbB : dbA;
+  float* dgamma = second ? dgB : dgA;
+  float* bcoef = second ? bcB : bcA;
+  dbeta[c] = (float)da;
+  dgamma[c] = (float)db;
+  bcoef[c] = (float)(da / count);
+  bcoef[C + c] = (float)(db / count);
+}
+extern "C" int dwn_bn_bwd_finalize2(const float* partial, int P, int NQ, int q0a, int q0b, double count, float* dgammaA,
+                                    float* dbetaA, float* bcoefA, float* dgammaB, float* dbetaB, float* bcoefB, int C,
+                                    void* stream) {
+  bn_bwd_finalize2_kernel<<<dim3((C + 7) / 8, 2), 1024, 0, (cudaStream_t)stream>>>(partial, P, NQ, q0a, q0b, count, dgammaA,
+                                                                                   dbetaA, bcoefA, dgammaB, dbetaB, bcoefB, C);
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int dwn_bn_bwd_finalize(const float* partial, int P, int NQ, int q0, double count, float* dgamma,
                                    float* dbeta, float* bcoef, int C, void* stream) {
   bn_bwd_finalize_kernel<<<(C + 7) / 8, 1024, 0, (cudaStream_t)stream>>>(partial, P, NQ, q0, count, dgamma, dbeta,

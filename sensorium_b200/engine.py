@@ -210,10 +210,10 @@ def _eval_coef(bn, C, Cp, st, dev):
     return coef
 
 
-def _bn_coef(bn, partial, P, count, C, Cp, training, st, dev, NQ=2):
+def _bn_coef(bn, partial, P, count, C, Cp, training, st, dev, NQ=2, out=None):
     if not training:
         return _eval_coef(bn, C, Cp, st, dev)
-    coef = _empty((4, C), torch.float32, dev)
+    coef = _empty((4, C), torch.float32, dev) if out is None else out
     call("dwn_bn_finalize", partial, P, float(count), bn.weight, bn.bias, bn.running_mean, bn.running_var,
          bn.num_batches_tracked, BN_MOM, BN_EPS, 1, coef, C, Cp, NQ, st)
     return coef
@@ -336,7 +336,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         wpw = blk.conv_pw[0].weight
         E = _empty((Mi, mid), adt, dev)
         wsh = _shadow(wpw) if bf else wpw
-        gram = sx = None
+        gram = sx = coef_sc_early = None
         stats_side = []
         if training and bf:
             # BatchNorm statistics of E = X W^T from the Gram matrix of X (no pass over E), see dwn_pw_algebra.cu.
@@ -345,11 +345,14 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
             gram = _empty((ci, ci), torch.float32, dev)
             sx = _empty((ci,), torch.float32, dev)
             coef1 = _empty((4, mid), torch.float32, dev)
+            coef_sc_early = _empty((4, co), torch.float32, dev)
             bn1 = blk.conv_pw[1].bn
             stats_side = [] if SERIALIZE else [_stats_stream(dev)]
             _fork(stats_side, dev)
             with torch.cuda.stream(stats_side[0]) if stats_side else _nullctx():
                 sst = _stream(dev)
+                # the shortcut BatchNorm's table depends only on the block input as well: off the critical path
+                _bn_coef(blk.bn_sc.bn, sc_part, _P, Mo, co, ci, training, sst, dev, NQ=3, out=coef_sc_early)
                 call("dwn_partial_colsum", sc_part, _P, 3, 2, ci, sx, sst)
                 _, cgram = _gram(Xb, Mi, ci, sx, sst, dev, out=gram)
                 call("dwn_pw_stats", cgram, sx, wsh, float(Mi), bn1.weight, bn1.bias, bn1.running_mean,
@@ -404,7 +407,8 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
             _bytes=(Mo * mid + B * co * mid + Mo * co) * es)
         coef4 = _bn_coef(blk.conv_pwl[1].bn, _colstats(Y, Mo, co, co, dcode, st, dev) if training else None, _P, Mo, co,
                          0, training, st, dev)
-        coef_sc = _bn_coef(blk.bn_sc.bn, sc_part, _P, Mo, co, ci, training, st, dev, NQ=3)
+        coef_sc = coef_sc_early if coef_sc_early is not None else _bn_coef(blk.bn_sc.bn, sc_part, _P, Mo, co, ci, training,
+                                                                              st, dev, NQ=3)
         # 6. residual epilogue (+ drop-path, + PE of the next block, + stats of the next shortcut)
         dp = None
         if training and blk.drop_path_rate > 0.0:

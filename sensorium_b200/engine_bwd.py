@@ -31,6 +31,29 @@ def _bn_bwd(part, P, NQ, q0, count, bn, grads, C, st, dev):
     return bcoef
 
 
+def _bn_bwd2(part, P, NQ, q0a, q0b, count, bn_a, bn_b, grads, C, st, dev):
+    """Two BatchNorms over the same partial table in one launch (dwn_bn_bwd_finalize2)."""
+    out = []
+    for _ in range(2):
+        out.append((_empty((C,), torch.float32, dev), _empty((C,), torch.float32, dev), _empty((2, C), torch.float32, dev)))
+    (dga, dba, bca), (dgb, dbb, bcb) = out
+    call("dwn_bn_bwd_finalize2", part, P, NQ, q0a, q0b, float(count), dga, dba, bca, dgb, dbb, bcb, C, st)
+    grads[bn_a.weight], grads[bn_a.bias] = dga, dba
+    grads[bn_b.weight], grads[bn_b.bias] = dgb, dbb
+    return bca, bcb
+
+
+_wg_side = {}
+
+
+def _wgrad_stream(dev):
+    """Side stream of the weight-gradient chains (conv_pw wgrad GEMM -> split-K reduce -> finalize, depth-wise weight
+    finalizes): nothing downstream in backward depends on them, so they leave the critical path of the captured graph."""
+    if dev.index not in _wg_side:
+        _wg_side[dev.index] = torch.cuda.Stream(device=dev)
+    return _wg_side[dev.index]
+
+
 def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[Optional[torch.Tensor]]:
     cfg = mod.cfg
     bf = sv.mode == "bf16"
@@ -49,6 +72,35 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
     dp = getattr(mod, "_dp", None)
     if dp is not None:
         dp.begin([g is not None for g in grad_outs], dev, mice=[r.m for r in sv.readouts])
+
+    # weight-gradient side chain (at most one outstanding): `pending` keeps the tensors it reads alive until main has
+    # waited for it, so the allocator cannot hand their memory to a later main-stream allocation
+    from . import engine as _engine
+    wside = None if _engine.SERIALIZE else _wgrad_stream(dev)
+    pending: list = []
+    side_done = [None]
+
+    def join_wside():
+        if side_done[0] is not None:
+            torch.cuda.current_stream(dev).wait_event(side_done[0])
+            side_done[0] = None
+        pending.clear()
+
+    def run_on_wside(fn, keep):
+        """fn(stream_handle) on the side stream after everything main has enqueued so far."""
+        if wside is None:
+            fn(st)
+            return
+        join_wside()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        wside.wait_event(ev)
+        with torch.cuda.stream(wside):
+            fn(_stream(dev))
+        done = torch.cuda.Event()
+        done.record(wside)
+        side_done[0] = done
+        pending.extend(keep)
 
     # ---------------- readouts -------------------------------------------------------------------
     K = cfg["cortex_features"][-1]
@@ -98,8 +150,7 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         I, O = c.I, c.O
         part = _empty((_J_CORTEX, 4, O), torch.float32, dev)
         call("dwn_cortex_bwd_reduce", dOut, c.Y, c.coef, c.dp, c.x, c.coef_sc, part, _J_CORTEX, Mbt, T, I, O, G, dcode, st)
-        bcoef = _bn_bwd(part, _J_CORTEX, 4, 0, Mbt, layer.bn.bn, grads, O, st, dev)
-        bcoef_sc = _bn_bwd(part, _J_CORTEX, 4, 2, Mbt, layer.bn_sc.bn, grads, O, st, dev)
+        bcoef, bcoef_sc = _bn_bwd2(part, _J_CORTEX, 4, 0, 2, Mbt, layer.bn.bn, layer.bn_sc.bn, grads, O, st, dev)
         dY = _empty((Mbt, O), adt, dev)
         call("dwn_cortex_bwd_dy", dOut, c.Y, c.coef, bcoef, c.dp, dY, Mbt, T, O, G, dcode, st)
         dW = _empty((O, I // G, 1), torch.float32, dev)
@@ -133,8 +184,7 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         part = _empty((_P, 4, co), torch.float32, dev)
         call("dwn_block_bwd_reduce", dO, b.Y, b.coef4, b.dp, b.X, b.coef_sc, part, _P, B, T, b.Ho, b.Wo, ci, co, s, b.Hi,
              b.Wi, dcode, st, _tag="block_bwd_reduce", _bytes=Mo * (co * (4 + es) + ci * 4))
-        bcoef4 = _bn_bwd(part, _P, 4, 0, Mo, blk.conv_pwl[1].bn, grads, co, st, dev)
-        bcoef_sc = _bn_bwd(part, _P, 4, 2, Mo, blk.bn_sc.bn, grads, co, st, dev)
+        bcoef4, bcoef_sc = _bn_bwd2(part, _P, 4, 0, 2, Mo, blk.conv_pwl[1].bn, blk.bn_sc.bn, grads, co, st, dev)
         dY = _empty((Mo, co), adt, dev)
         call("dwn_block_bwd_dy", dO, b.Y, b.coef4, bcoef4, b.dp, dY, Mo, Nsp, co, dcode, st, _tag="block_bwd_dy",
              _bytes=Mo * co * (4 + 2 * es))
@@ -172,8 +222,7 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
              b.Ho * b.Wo, mid, dcode, st, _tag="tdw_bwd", _bytes=4 * Mo * mid * es)
         bcoef2 = _bn_bwd(part7, ptdw, 7, 0, Mo, blk.spat_covn_dw[1].bn, grads, mid, st, dev)
         dwt = torch.empty_like(blk.temp_covn_dw[0].weight)
-        call("dwn_dw_wgrad_finalize", part7, ptdw, 7, 2, 5, dwt, mid, st)
-        grads[blk.temp_covn_dw[0].weight] = dwt
+        grads[blk.temp_covn_dw[0].weight] = dwt                 # filled by the side chain below
         # spatial dw backward (da now holds d s_hat)
         dE = _empty((Mi, mid), adt, dev)
         psdw = _p_sdw(Mi * mid)
@@ -183,8 +232,7 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         del da
         bcoef1 = _bn_bwd(part11, psdw, 11, 0, Mi, blk.conv_pw[1].bn, grads, mid, st, dev)
         dws = torch.empty_like(blk.spat_covn_dw[0].weight)
-        call("dwn_dw_wgrad_finalize", part11, psdw, 11, 2, 9, dws, mid, st)
-        grads[blk.spat_covn_dw[0].weight] = dws
+        grads[blk.spat_covn_dw[0].weight] = dws                 # filled by the side chain below
         wpw = blk.conv_pw[0].weight
         dXpw = _empty((Mi, ci), torch.float32, dev)
         tiles = math.ceil(mid / 128) * math.ceil(ci / 256)
@@ -196,6 +244,20 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         if bf and b.gram is not None:
             # BN1 backward folded into the GEMMs (dE holds G = dE_pre; E is never read): dwn_pw_algebra.cu
             wsh = _shadow(wpw)
+            psum = _empty((mid, ci), torch.float32, dev)
+
+            def wchain(sst, dE=dE, b=b, blk=blk, part7=part7, part11=part11, ptdw=ptdw, psdw=psdw, dwt=dwt, dws=dws,
+                       wpart=wpart, psum=psum, dwpw=dwpw, wsh=wsh, bcoef1=bcoef1, rows=rows, Zs=Zs, mid=mid, ci=ci, Mi=Mi):
+                # weight gradients of this block: nothing downstream in backward reads them
+                gemm(sst, dtype=dcode, A=dE, B=b.Xb, a_mn=1, b_mn=1, lda=mid, ldb=ci, a_zstride=rows * mid,
+                     b_zstride=rows * ci, a_zmode=1, b_zmode=1, M=mid, N=ci, K=rows, Z=Zs, D=wpart, d_dtype=F32, ldd=ci,
+                     d_zstride=mid * ci, _tag="pw_wgrad", _bytes=Mi * (mid + ci) * es + Zs * mid * ci * 4)
+                call("dwn_reduce_rows", wpart, Zs, mid * ci, psum, sst)
+                call("dwn_pw_wgrad_finalize", psum, b.coef1, bcoef1, wsh, b.gram, b.sx, dwpw, mid, ci, sst)
+                call("dwn_dw_wgrad_finalize", part7, ptdw, 7, 2, 5, dwt, mid, sst)
+                call("dwn_dw_wgrad_finalize", part11, psdw, 11, 2, 9, dws, mid, sst)
+
+            run_on_wside(wchain, [dE, part7, part11, wpart, psum, bcoef1, wsh])
             wprime = _empty((mid, ci), torch.bfloat16, dev)
             negq = _empty((ci, ci), torch.bfloat16, dev)
             colbias = _empty((ci,), torch.float32, dev)
@@ -204,13 +266,9 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
             gemm(st, dtype=dcode, A=dE, B=wprime, b_mn=1, lda=mid, ldb=ci, M=Mi, N=ci, K=mid, Z=1, A2=b.Xb, B2=negq,
                  lda2=ci, ldb2=ci, K2=ci, D=dXpw, d_dtype=F32, ldd=ci, _tag="pw_dgrad",
                  _bytes=Mi * mid * es + mid * ci * es + Mi * ci * (4 + es))
-            gemm(st, dtype=dcode, A=dE, B=b.Xb, a_mn=1, b_mn=1, lda=mid, ldb=ci, a_zstride=rows * mid,
-                 b_zstride=rows * ci, a_zmode=1, b_zmode=1, M=mid, N=ci, K=rows, Z=Zs, D=wpart, d_dtype=F32, ldd=ci,
-                 d_zstride=mid * ci, _tag="pw_wgrad", _bytes=Mi * (mid + ci) * es + Zs * mid * ci * 4)
-            psum = _empty((mid, ci), torch.float32, dev)
-            call("dwn_reduce_rows", wpart, Zs, mid * ci, psum, st)
-            call("dwn_pw_wgrad_finalize", psum, b.coef1, bcoef1, wsh, b.gram, b.sx, dwpw, mid, ci, st)
         else:
+            call("dwn_dw_wgrad_finalize", part7, ptdw, 7, 2, 5, dwt, mid, st)
+            call("dwn_dw_wgrad_finalize", part11, psdw, 11, 2, 9, dws, mid, st)
             call("dwn_bn_bwd_apply", dE, b.E, b.coef1, bcoef1, Mi, mid, dcode, st, _tag="bn_bwd_apply",
                  _bytes=3 * Mi * mid * es)
             gemm(st, dtype=dcode, A=dE, B=_shadow(wpw) if bf else wpw, b_mn=1, lda=mid, ldb=ci, M=Mi, N=ci, K=mid, Z=1,
@@ -235,8 +293,10 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
                  _tag="block_in_bwd", _bytes=Mi * ci * 12 + Mo * co * 4)
             dO = dXin
         if dp is not None:
+            join_wside()  # the exchange reads this block's weight gradients
             dp.reduce(grads, list(blk.parameters()))
 
+    join_wside()
     # ---------------- stem -----------------------------------------------------------------------
     stem_conv, stem_bn = mod.core.stem[0], mod.core.stem[1].bn
     cin = stem_conv.weight.shape[1]
