@@ -79,12 +79,15 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
     wside = None if _engine.SERIALIZE else _wgrad_stream(dev)
     pending: list = []
     side_done = [None]
+    deferred: list = []   # data-parallel: parameter groups whose exchange waits for the side chain that produces them
 
     def join_wside():
         if side_done[0] is not None:
             torch.cuda.current_stream(dev).wait_event(side_done[0])
             side_done[0] = None
         pending.clear()
+        while deferred:
+            dp.reduce(grads, deferred.pop(0))
 
     def run_on_wside(fn, keep):
         """fn(stream_handle) on the side stream after everything main has enqueued so far."""
@@ -293,8 +296,11 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
                  _tag="block_in_bwd", _bytes=Mi * ci * 12 + Mo * co * 4)
             dO = dXin
         if dp is not None:
-            join_wside()  # the exchange reads this block's weight gradients
-            dp.reduce(grads, list(blk.parameters()))
+            # the exchange reads this block's weight gradients, which the side chain is still producing: it is issued at
+            # the next join (one block later, same order on every rank)
+            deferred.append(list(blk.parameters()))
+            if wside is None or side_done[0] is None:
+                join_wside()
 
     join_wside()
     # ---------------- stem -----------------------------------------------------------------------
