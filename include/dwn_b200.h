@@ -21,6 +21,7 @@ extern "C" {
 const char* dwn_last_error(void);
 int dwn_abi_version(void);
 int dwn_sm_count(void);
+int dwn_set_sm_budget(int n);   /* SMs the persistent kernels size their grids for (0 = all): leaves room for NCCL */
 
 /* ---- GEMM: D[z] (MxN) = A[z] (MxK) * B[z]^T (NxK) -------------------------------------------------
  * replaces nn.Conv3d 1x1x1 / nn.Conv1d k=1 (grouped) forward, dgrad and wgrad

@@ -116,7 +116,7 @@ def lib():
 
 
 def exported_symbols():
-    return ["dwn_last_error", "dwn_abi_version", "dwn_sm_count", "dwn_gemm", "dwn_block_in_bwd_stem_rows",
+    return ["dwn_last_error", "dwn_abi_version", "dwn_sm_count", "dwn_set_sm_budget", "dwn_gemm", "dwn_block_in_bwd_stem_rows",
             "dwn_pw_bwd_prep_scratch", "dwn_opt_chunk", *SIGNATURES.keys()]
 
 

@@ -12,6 +12,7 @@ int dwn_fail(const char* fmt, ...) {
   return -1;
 }
 
+static int g_sm_budget = 0;
 int dwn_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -20,7 +21,14 @@ int dwn_num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
+}
+// Number of SMs the persistent kernels (GEMM tile loop, one-wave grids) size themselves for; 0 = all.  Data-parallel
+// backward leaves a few SMs to the concurrently running NCCL kernels: a persistent CTA that cannot become resident
+// next to an NCCL CTA would otherwise wait for the whole collective.
+extern "C" int dwn_set_sm_budget(int n) {
+  g_sm_budget = n > 0 ? n : 0;
+  return 0;
 }
 
 extern "C" const char* dwn_last_error() { return g_err; }

@@ -70,8 +70,13 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         raise NotImplementedError("sensorium_b200: backward is implemented for train mode (batch-stat BatchNorm)")
 
     dp = getattr(mod, "_dp", None)
+    nsm = _lib.lib().dwn_sm_count()
     if dp is not None:
         dp.begin([g is not None for g in grad_outs], dev, mice=[r.m for r in sv.readouts])
+        if getattr(dp, "sm_reserve", 0) > 0:
+            _lib.lib().dwn_set_sm_budget(max(nsm - dp.sm_reserve, 32))
+            nsm = _lib.lib().dwn_sm_count()
+    PB = 4 * nsm  # rows of the per-CTA partial tables (= persistent CTAs per channel chunk) of the trunk kernels
 
     # weight-gradient side chain (at most one outstanding): `pending` keeps the tensors it reads alive until main has
     # waited for it, so the allocator cannot hand their memory to a later main-stream allocation
@@ -184,10 +189,10 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         blk = mod.core.blocks[2 * i + 1]
         ci, co, mid, s, rd = b.ci, b.co, b.mid, b.s, b.rd
         Mi, Mo, Nsp = B * T * b.Hi * b.Wi, B * T * b.Ho * b.Wo, T * b.Ho * b.Wo
-        part = _empty((_P, 4, co), torch.float32, dev)
-        call("dwn_block_bwd_reduce", dO, b.Y, b.coef4, b.dp, b.X, b.coef_sc, part, _P, B, T, b.Ho, b.Wo, ci, co, s, b.Hi,
+        part = _empty((PB, 4, co), torch.float32, dev)
+        call("dwn_block_bwd_reduce", dO, b.Y, b.coef4, b.dp, b.X, b.coef_sc, part, PB, B, T, b.Ho, b.Wo, ci, co, s, b.Hi,
              b.Wi, dcode, st, _tag="block_bwd_reduce", _bytes=Mo * (co * (4 + es) + ci * 4))
-        bcoef4, bcoef_sc = _bn_bwd2(part, _P, 4, 0, 2, Mo, blk.conv_pwl[1].bn, blk.bn_sc.bn, grads, co, st, dev)
+        bcoef4, bcoef_sc = _bn_bwd2(part, PB, 4, 0, 2, Mo, blk.conv_pwl[1].bn, blk.bn_sc.bn, grads, co, st, dev)
         dY = _empty((Mo, co), adt, dev)
         call("dwn_block_bwd_dy", dO, b.Y, b.coef4, bcoef4, b.dp, dY, Mo, Nsp, co, dcode, st, _tag="block_bwd_dy",
              _bytes=Mo * co * (4 + 2 * es))
@@ -215,11 +220,12 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
              b_zmode=1, M=Nsp, N=mid, K=co, Z=B, D=da, d_dtype=dcode, ldd=mid, d_zstride=Nsp * mid, _tag="pwl_dgrad",
              _bytes=(Mo * co + B * co * mid + Mo * mid) * es)
         # temporal dw backward
-        part = _empty((B * _J_TDW, 2, mid), torch.float32, dev)
-        call("dwn_tdw_bwd_reduce", da, b.Tm, b.coef3, dmean, Nsp, part, _J_TDW, B, mid, dcode, st, _tag="tdw_bwd_reduce",
+        jt = _J_TDW if 2 * nsm >= B * _J_TDW else max(1, 2 * nsm // B)   # one resident wave (2 CTAs per SM)
+        part = _empty((B * jt, 2, mid), torch.float32, dev)
+        call("dwn_tdw_bwd_reduce", da, b.Tm, b.coef3, dmean, Nsp, part, jt, B, mid, dcode, st, _tag="tdw_bwd_reduce",
              _bytes=2 * Mo * mid * es)
-        bcoef3 = _bn_bwd(part, B * _J_TDW, 2, 0, Mo, blk.temp_covn_dw[1].bn, grads, mid, st, dev)
-        ptdw = _p_tdw(Mo * mid)
+        bcoef3 = _bn_bwd(part, B * jt, 2, 0, Mo, blk.temp_covn_dw[1].bn, grads, mid, st, dev)
+        ptdw = _p_tdw(Mo * mid) * nsm // 148
         part7 = _empty((ptdw, 7, mid), torch.float32, dev)
         call("dwn_tdw_bwd", da, b.Tm, b.S, b.coef3, bcoef3, b.coef2, blk.temp_covn_dw[0].weight, dmean, part7, ptdw, B, T,
              b.Ho * b.Wo, mid, dcode, st, _tag="tdw_bwd", _bytes=4 * Mo * mid * es)
@@ -303,6 +309,8 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
                 join_wside()
 
     join_wside()
+    if dp is not None and getattr(dp, "sm_reserve", 0) > 0:
+        _lib.lib().dwn_set_sm_budget(0)
     # ---------------- stem -----------------------------------------------------------------------
     stem_conv, stem_bn = mod.core.stem[0], mod.core.stem[1].bn
     cin = stem_conv.weight.shape[1]

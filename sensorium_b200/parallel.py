@@ -36,6 +36,9 @@ class DataParallelGrads:
         self.active: Optional[torch.Tensor] = None
         self._avg = dist.get_backend(group) == "nccl"  # gloo (CPU tests) has no ReduceOp.AVG
         self._pm_dev = None
+        # SMs left to the NCCL kernels while backward runs next to the exchange (engine_bwd sizes its persistent grids for
+        # the rest); 0 = none
+        self.sm_reserve = int(__import__("os").environ.get("DWN_DP_SM_RESERVE", "0"))
         self._pinned: List = []
         self.bytes_reduced = 0
 
