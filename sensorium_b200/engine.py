@@ -368,7 +368,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         # 2. spatial depth-wise (BN1+SiLU on load)
         S = _empty((Mo, mid), adt, dev)
         part = _empty((_P, 2, mid), torch.float32, dev) if training else None
-        psdw = _p_sdw(Mi * mid)
+        psdw = _p_sdw(Mi * mid) if bf else _P_SDW   # the fp32 (generic) kernel is latency-bound: it wants every CTA it can get
         call("dwn_sdw_fwd", E, coef1, blk.spat_covn_dw[0].weight, S, part, psdw, B * T, Hi, Wi, mid, s, dcode, st,
              _tag="sdw_fwd", _bytes=(Mi + Mo) * mid * es)
         coef2 = _bn_coef(blk.spat_covn_dw[1].bn, part, psdw, Mo, mid, 0, training, st, dev)
