@@ -46,16 +46,27 @@ class ModelEma(nn.Module):
             self._chunks = _chunk_tables([e.numel() for e in ev], _lib.lib().dwn_opt_chunk(), dev)
             self._key = key
             self._nelem = sum(e.numel() for e in ev)
+            # the same update split in two launches: the readout entries (95 % of the bytes) and the rest — MouseModel
+            # runs the first part early, under backward (see FusedAdamW.early_step)
+            names = list(self.ema.state_dict().keys())
+            self._parts = {}
+            for part, sel in (("readouts", [i for i, n in enumerate(names) if n.startswith("readouts.")]),
+                              ("rest", [i for i, n in enumerate(names) if not n.startswith("readouts.")])):
+                if sel:
+                    self._parts[part] = (torch.tensor([rows[i] for i in sel], dtype=torch.int64).to(dev),
+                                         _chunk_tables([ev[i].numel() for i in sel], _lib.lib().dwn_opt_chunk(), dev),
+                                         sum(ev[i].numel() for i in sel))
         return ev[0].device
 
     @torch.no_grad()
-    def update(self, model):
+    def update(self, model, part: str = "all"):
+        """``part``: "all" (the reference's update), or "readouts" / "rest" — the same update in two launches."""
         dev = self._tables(model)
         if dev.type != "cuda":
             raise RuntimeError("sensorium_b200.ModelEma runs on CUDA only: no CPU fallback")
-        ct, co, nch = self._chunks
-        call("dwn_ema", self._tab, ct, co, nch, float(self.decay), torch.cuda.current_stream(dev).cuda_stream,
-             _tag="ema", _bytes=self._nelem * 12)
+        tab, (ct, co, nch), nelem = (self._tab, self._chunks, self._nelem) if part == "all" else self._parts[part]
+        call("dwn_ema", tab, ct, co, nch, float(self.decay), torch.cuda.current_stream(dev).cuda_stream,
+             _tag="ema" if part == "all" else "ema_" + part, _bytes=nelem * 12)
         from .engine import bump_generation
         bump_generation()
         # weights of the EMA module changed behind autograd's back: drop stale bf16 shadows

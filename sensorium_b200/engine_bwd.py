@@ -151,6 +151,11 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         dX.zero_()
     if dp is not None:
         dp.reduce_readouts(grads, mice=[r.m for r in sv.readouts])
+    early = getattr(mod, "_early_step", None)
+    if early is not None and dp is None and wside is not None and live:
+        # the readout gradients (95 % of the parameters) are final here: their AdamW + EMA update runs on a side stream
+        # under the remaining ~16 ms of backward, whose kernels leave HBM bandwidth unused (MouseModel.train_step)
+        early(grads, [p_ for r, _ in live for p_ in mod.readouts[r.m].layer[1].parameters()])
 
     # ---------------- cortex ---------------------------------------------------------------------
     dOut = dX

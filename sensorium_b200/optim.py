@@ -40,6 +40,7 @@ class FusedAdamW(torch.optim.Optimizer):
         # NOT in param_groups, so state_dict() carries only torch's own {exp_avg, exp_avg_sq, step} per parameter
         self._cache = {}
         self._active_cache = {}
+        self._early_done: set = set()
 
     def _flatten(self, gi, params):
         """Flat exp_avg / exp_avg_sq / step buffers; ``state[p]`` entries are views into them.  State that is already
@@ -78,15 +79,45 @@ class FusedAdamW(torch.optim.Optimizer):
         self._cache = {}
         self._active_cache = {}
 
-    def _table(self, c, params, dev):
+    def _table(self, c, params, dev, grads=None):
         rows = []
         for p in params:
             st = self.state[p]
             sh = getattr(p, "_dwn_shadow", None)
-            g = p.grad
+            g = p.grad if grads is None else grads.get(p)
             rows.append([p.data_ptr(), g.data_ptr() if g is not None else 0, st["exp_avg"].data_ptr(),
                          st["exp_avg_sq"].data_ptr(), sh[1].data_ptr() if sh is not None else 0, 0, p.numel(), 0])
         return _h2d(torch.tensor(rows, dtype=torch.int64), dev, c)
+
+    @torch.no_grad()
+    def early_step(self, subset, grads) -> None:
+        """AdamW update of ``subset`` (parameters of group 0) from ``grads[p]`` BEFORE the rest of backward has run —
+        MouseModel issues it for the readouts on a side stream as soon as their gradients exist.  The following
+        ``step()`` skips these tensors.  Same kernel, same per-tensor step counters: the result is identical to a
+        single late step."""
+        group = self.param_groups[0]
+        params = [p for p in group["params"] if p.requires_grad]
+        dev = params[0].device
+        c = self._cache.get(0)
+        if c is None or c["steps"].numel() != len(params):
+            c = self._flatten(0, params)
+        chosen = {id(p) for p in subset if grads.get(p) is not None}
+        key = tuple(grads[p].data_ptr() if id(p) in chosen else 0 for p in params)
+        ent = c.get("early")
+        if ent is None or ent[0] != key:
+            tab = self._table(c, params, dev, grads={p: (grads[p] if id(p) in chosen else None) for p in params})
+            act = _h2d(torch.tensor([1 if id(p) in chosen else 0 for p in params], dtype=torch.int32), dev, c)
+            ent = c["early"] = (key, tab, act)
+        if torch.cuda.is_current_stream_capturing() and ent[1].device.type == "cuda":
+            pass  # tables created inside this capture are replayed by its memcpy nodes
+        ct, co, nch = c["chunks"]
+        b1, b2 = group["betas"]
+        lr_dev = c["lr_dev"] if torch.cuda.is_current_stream_capturing() else None
+        call("dwn_adamw", ent[1], ct, co, nch, c["steps"], ent[2], len(params), float(group["lr"]),
+             float(group["weight_decay"]), float(b1), float(b2), float(group["eps"]), 0.0, lr_dev, c["bc"],
+             torch.cuda.current_stream(dev).cuda_stream, _tag="adamw_early",
+             _bytes=sum(p.numel() for p in params if id(p) in chosen) * 30)
+        self._early_done = chosen
 
     def sync_graph_lr(self) -> None:
         """Push the current learning rates to the device scalars that captured optimizer steps read."""
@@ -120,7 +151,8 @@ class FusedAdamW(torch.optim.Optimizer):
                         p.grad = p.grad.float().contiguous()
                 c["tab"] = self._table(c, params, dev)
                 c["key"] = key_of()
-            act = tuple(p.grad is not None for p in params)
+            early = self._early_done if gi == 0 else set()
+            act = tuple(p.grad is not None and id(p) not in early for p in params)
             active = None
             provider = getattr(self, "active_provider", None)
             if provider is not None and provider.active is not None and provider.active.numel() == len(params):
@@ -146,6 +178,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 sh = getattr(p, "_dwn_shadow", None)
                 if sh is not None:
                     set_shadow(p, sh[1])
+        self._early_done = set()
         bump_generation()
         provider = getattr(self, "active_provider", None)
         if provider is not None and hasattr(provider, "consumed"):

@@ -697,10 +697,10 @@ def test_cuda_graph_train_step_is_bit_identical_to_eager(dev):
             out.append((x, compact_from_dense(tg, w) if i >= 4 and bool((w.sum(1) == 1).all()) else (tg, w)))
         return out
 
-    def run(graph):
+    def run(graph, early=False):
         params = {"nn_module": ("dwiseneuro", {"readout_outputs": TINY_OUTS, **kw}), "loss": ("mice_poisson", {}),
                   "optimizer": ("AdamW", {"lr": 2e-3, "weight_decay": 0.05}), "device": "cuda:0", "amp": True,
-                  "iter_size": 1, "cuda_graph": graph}
+                  "iter_size": 1, "cuda_graph": graph, "early_readout_step": early}
         torch.manual_seed(0)
         m = MouseModel(params)
         init_weights(m.nn_module)
@@ -714,6 +714,13 @@ def test_cuda_graph_train_step_is_bit_identical_to_eager(dev):
 
     m1, l1 = run(False)
     m2, l2 = run(True)
+    for graph in (False, True):   # the overlapped readout update (early AdamW + EMA on a side stream) is bit-identical too
+        m4, l4 = run(graph, early=True)
+        assert l4 == l1
+        for (k, a), b in zip(m1.nn_module.state_dict().items(), m4.nn_module.state_dict().values()):
+            assert torch.equal(a, b), k
+        for (k, a), b in zip(m1.model_ema.ema.state_dict().items(), m4.model_ema.ema.state_dict().values()):
+            assert torch.equal(a, b), k
     assert len(m2._graphs) >= 2 and not m1._graphs
     assert l1 == l2, (l1, l2)
     for (k, a), b in zip(m1.nn_module.state_dict().items(), m2.nn_module.state_dict().values()):
