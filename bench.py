@@ -427,6 +427,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     bytes_reduced = dp.bytes_reduced if dp is not None else 0
+    graphs_captured = len(model._graphs)
     if args.cuda_profiler_step:
         torch.cuda.profiler.start()
         device_step()
@@ -548,7 +549,7 @@ def main():
                       "path": "same call with the reference's dense batch form (ten mostly-zero target tensors)"},
         "gpu_launches": launches,
         "launch_mode": ("CUDA graph replay of the whole train step (captured per shape / set of mice present); "
-                        "gpu_launches counts the kernels inside the replayed graphs" if not args.no_cuda_graph else
+                        "gpu_launches counts the kernels inside the replayed graphs" if graphs_captured > 0 else
                         "one launch per kernel from Python (ctypes)"),
         "clocks": sampler.summary(),
         "roofline": roofline,
@@ -560,7 +561,7 @@ def main():
     if world > 1:
         line["comm"] = {"bytes_reduced_per_step": bytes_reduced, "collective": "ncclAllReduce(AVG) per bucket, overlapped "
                         "with backward", "nccl_max_ctas": args.nccl_max_ctas or "default",
-                        "captured_in_cuda_graph": bool(model._graphs) and not args.no_cuda_graph_dp}
+                        "captured_in_cuda_graph": graphs_captured > 0}
     line.update(extras)
     if not args.no_cpu_baseline and world == 1:
         val, threads, sec = cpu_reference_step(8, 2, 1)
