@@ -7,6 +7,8 @@
 #include "dwn_reduce.cuh"
 #include "dwn_sdw_v3.cuh"
 #include "dwn_bulk.cuh"
+#include "dwn_sdw_tma.cuh"
+#include <cstdlib>
 #include <type_traits>
 
 __global__ void stem_bwd_finalize_kernel(const float* __restrict__ partial, int P, int cin, const double* __restrict__ mom,
@@ -1294,7 +1296,21 @@ extern "C" int dwn_sdw_bwd(const void* dsh, const void* s_raw, const void* e_raw
     return stride == 1
                ? sdw_bwd_launch<float, 1>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st)
                : sdw_bwd_launch<float, 2>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st);
-  int rc = stride == 1
+  // TMA-staged kernels first (DWN_SDW_TMA=0 selects the cp.async kernels, DWN_SDW_THI the stride-2 tile height: A/B runs)
+  const char* env_tma = getenv("DWN_SDW_TMA");
+  const char* env_thi = getenv("DWN_SDW_THI");
+  const int tma_mode = env_tma ? atoi(env_tma) : 1;
+  const int thi_pref = env_thi ? atoi(env_thi) : 0;
+  int rc = 1;
+  // DWN_SDW_TMA: 0 = cp.async kernels, 1 = TMA kernels (stride 1: one-pass v7), 2 = TMA kernels (stride 1: two-pass v6)
+  if (tma_mode == 1 && stride == 1)
+    rc = sdw_bwd_v7_launch(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, thi_pref, st);
+  if (tma_mode && rc > 0)
+    rc = stride == 1 ? sdw_bwd_v6_launch<1>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, 8, st)
+                     : sdw_bwd_v6_launch<2>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C,
+                                            thi_pref, st);
+  if (rc <= 0) return rc;
+  rc = stride == 1
                ? sdw_bwd_v3_launch<1>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st)
                : sdw_bwd_v3_launch<2>(dsh, s_raw, e_raw, coef2, bcoef2, coef1, wgt, dE, partial, P, NP, H, W, C, st);
   if (rc <= 0) return rc;

@@ -1,0 +1,651 @@
+// TMA-staged spatial depth-wise backward (bf16 pipeline, sm_100a).
+//
+// Same arithmetic as sdw_bwd_v5_kernel (stride 1) / sdw_bwd_v3_kernel<2> (stride 2) of dwn_sdw_v3.cuh, different staging:
+// ncu (profiles/r2_ncu_full_stencils_after.csv) shows those kernels issue-bound at 16 warps per SM (0.45-0.59 instructions
+// per scheduler cycle, DRAM traffic == algorithmic bytes), and a third of their per-tile instructions were the per-thread
+// cp.async address chains (57 IMAD + 52 IADD3 + 17 ISETP for 14 LDGSTS per thread and tile in v5).  Here ONE elected thread
+// issues three cp.async.bulk.tensor.4d copies per tile - dS_hat and S_raw with their halo rows AND halo columns (the
+// out-of-bounds fill of the tensor map writes the zero padding), and the E tile - completion is tracked by mbarriers, and
+// the other 255 threads spend no instruction on staging.  The BN2-backward pass over the staged tile keeps its three
+// coefficient vectors in registers (stride 1) and takes row / column validity from per-thread bit masks computed once.
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <type_traits>
+#include "dwn_bulk.cuh"
+#include "dwn_common.cuh"
+#include "dwn_reduce.cuh"
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(bk_smem_u32(dst)), "l"(map), "r"(bk_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// orders this thread's generic-proxy accesses to shared memory before later async-proxy (TMA) writes to the same bytes
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bk_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bk_smem_u32(bar)) : "memory");
+}
+
+struct alignas(64) SdwBwdMaps {
+  CUtensorMap ds;  // dS_hat  [NP][Ho][Wo][C], box (CC, Wo+2, NR, 1)
+  CUtensorMap s;   // S_raw   same geometry
+  CUtensorMap e;   // E_raw   [NP][H][W][C],   box (CC, W, THI, 1)
+};
+
+template <int S, int THI, int CC>
+struct SdwBwdGeom {
+  static constexpr int W = 1024 / CC, Wo = W / S;
+  static constexpr int PADL = S == 1 ? 1 : 0;  // stride 1: tile column = wo + 1; stride 2: tile column = wo
+  static constexpr int WP = Wo + 2;
+  static constexpr int NR = S == 1 ? THI + 2 : THI / 2 + 1;
+  static constexpr int cvn = CC / 8;
+  static constexpr int NV = NR * WP * cvn;  // 16-byte vectors of one staged raw tile == the TMA box
+  static constexpr int NIT = (NV + 255) / 256;
+  static constexpr int RAW_BYTES = NV * 16;
+  static constexpr int RAW_PITCH = (RAW_BYTES + 127) / 128 * 128;
+  static constexpr int E_BYTES = THI * W * CC * 2;
+  static constexpr int NE = S == 2 ? 2 : 1;  // stride 2: the (4x larger) E tile of item k+1 streams in during item k
+  // fp32 tile in two planes: channels 0-3 of vector v at plane 0 + 16 v, channels 4-7 at plane 1 + 16 v.  With the plane pitch
+  // == 64 (mod 128) bytes the two 16-byte stores of the BN2-backward pass and the stencil's 8 / 16-byte loads (a pixel's
+  // channel pairs are spread over both planes) are bank-conflict free without reordering selects
+  static constexpr int PLANE_BYTES = (NV * 16 + 127) / 128 * 128 + 64;
+  static constexpr int TILE_BYTES = 2 * PLANE_BYTES;
+  static constexpr int NT = (S == 2 && THI <= 8) ? 2 : 1;  // small stride-2 tiles are double-buffered: one CTA barrier per item
+  static constexpr int SCO_FLOATS = 5 * CC;
+  static constexpr int OFF_E = 2 * RAW_PITCH;
+  static constexpr int OFF_TILE = OFF_E + NE * E_BYTES;
+  static constexpr int OFF_SCO = OFF_TILE + NT * TILE_BYTES;
+  static constexpr int OFF_BAR = (OFF_SCO + SCO_FLOATS * 4 + 15) / 16 * 16;
+  static constexpr int RED_BYTES = 256 * 11 * (S == 1 ? 2 : 4) * 4;
+  static constexpr int SMEM_USED = OFF_BAR + 64;
+  static constexpr int SMEM = SMEM_USED > RED_BYTES ? SMEM_USED : RED_BYTES;
+};
+
+template <int S, int THI, int CC>
+__global__ void __launch_bounds__(256, 2)
+sdw_bwd_v6_kernel(const __grid_constant__ SdwBwdMaps maps, const float* __restrict__ coef2,
+                  const float* __restrict__ bcoef2, const float* __restrict__ coef1, const float* __restrict__ wgt,
+                  bf16* __restrict__ dE, float* __restrict__ partial, int NP, int H, int C, int nchunks, int nbsh) {
+  using G = SdwBwdGeom<S, THI, CC>;
+  constexpr int W = G::W, WP = G::WP, NR = G::NR, cvn = G::cvn, NV = G::NV, NIT = G::NIT, NE = G::NE, NT = G::NT;
+  constexpr int PSF = cvn * 4, RSF = WP * PSF, PLF = G::PLANE_BYTES / 4;  // tile pixel / row / plane pitch in floats
+  extern __shared__ __align__(128) unsigned char smem_v6[];
+  bf16* rawD = reinterpret_cast<bf16*>(smem_v6);
+  bf16* rawS = reinterpret_cast<bf16*>(smem_v6 + G::RAW_PITCH);
+  bf16* rawE = reinterpret_cast<bf16*>(smem_v6 + G::OFF_E);
+  float* tile0 = reinterpret_cast<float*>(smem_v6 + G::OFF_TILE);
+  float* sco = reinterpret_cast<float*>(smem_v6 + G::OFF_SCO);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v6 + G::OFF_BAR);
+  uint64_t* fullDS = bars;
+  uint64_t* fullE = bars + 1;  // [NE]
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x % nchunks, worker = blockIdx.x / nchunks, nworkers = gridDim.x / nchunks;
+  const int c0 = chunk * CC;
+  const int lcv = tid & (cvn - 1);
+  if (tid == 0) {
+    bk_mbar_init(fullDS, 1);
+    for (int e = 0; e < NE; ++e) bk_mbar_init(fullE + e, 1);
+    bk_mbar_init_fence();
+  }
+  // ---- BN2-backward coefficients of this thread's 8 staged channels: dS_raw = a*g - d*x - b
+  //      stride 1: registers; stride 2 (4 channels per stencil thread: 80 live accumulator / weight registers): shared memory
+  constexpr bool COEF_REGS = false;
+  f32x2 ca[4], cb[4], cd[4];
+  if (COEF_REGS) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a[2], nb[2], nd[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = c0 + lcv * 8 + 2 * j + h;
+        const float sc = coef2[cc], mu = coef2[2 * C + cc], rs = coef2[3 * C + cc];
+        const float k1 = bcoef2[cc], k2 = bcoef2[C + cc];
+        a[h] = sc;
+        nb[h] = -sc * (k1 - mu * rs * k2);
+        nd[h] = -sc * rs * k2;
+      }
+      ca[j] = pk2(a[0], a[1]);
+      cb[j] = pk2(nb[0], nb[1]);
+      cd[j] = pk2(nd[0], nd[1]);
+    }
+  }
+  for (int i = tid; i < CC; i += 256) {
+    const int cc = c0 + i;
+    float q0, q1;
+    BnSilu<bf16>::prep(coef1[cc], coef1[C + cc], q0, q1);
+    if (COEF_REGS) {
+      sco[i] = q0;
+      sco[CC + i] = q1;
+    } else {
+      const float sc = coef2[cc], mu = coef2[2 * C + cc], rs = coef2[3 * C + cc];
+      const float k1 = bcoef2[cc], k2 = bcoef2[C + cc];
+      sco[i] = sc;
+      sco[CC + i] = -sc * (k1 - mu * rs * k2);
+      sco[2 * CC + i] = -sc * rs * k2;
+      sco[3 * CC + i] = q0;
+      sco[4 * CC + i] = q1;
+    }
+  }
+  // ---- validity of this thread's vectors in the BN2-backward pass, one bit per pass (tile-invariant):
+  //      in range / not a halo column / in the first / in the last staged row
+  uint32_t m_in = 0, m_col = 0, m_r0 = 0, m_rl = 0;
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int v = tid + it * 256;
+    if (v < NV) {
+      const int r = v / (WP * cvn), col = (v / cvn) % WP;
+      m_in |= 1u << it;
+      if (col >= G::PADL && col < G::PADL + G::Wo) m_col |= 1u << it;
+      if (r == 0) m_r0 |= 1u << it;
+      if (r == NR - 1) m_rl |= 1u << it;
+    }
+  }
+  const int nbm = (1 << nbsh) - 1;
+  const int ntiles = NP << nbsh;
+  auto issue_ds = [&](int t) {
+    const int p = t >> nbsh, hi0 = (t & nbm) * THI;
+    const int row0 = (S == 1) ? hi0 - 1 : hi0 / 2;
+    bk_mbar_expect_tx(fullDS, 2 * G::RAW_BYTES);
+    tma_load_4d(rawD, &maps.ds, fullDS, c0, -G::PADL, row0, p);
+    tma_load_4d(rawS, &maps.s, fullDS, c0, -G::PADL, row0, p);
+  };
+  auto issue_e = [&](int t, int e) {
+    const int p = t >> nbsh, hi0 = (t & nbm) * THI;
+    bk_mbar_expect_tx(fullE + e, G::E_BYTES);
+    tma_load_4d(reinterpret_cast<unsigned char*>(rawE) + (size_t)e * G::E_BYTES, &maps.e, fullE + e, c0, 0, hi0, p);
+  };
+  __syncthreads();  // barriers initialised, sco written
+  int t = worker;
+  if (tid == 0 && t < ntiles) {
+    issue_ds(t);
+    issue_e(t, 0);
+  }
+
+  // ---- stencil thread mapping and persistent accumulators
+  //   stride 1: one channel pair, two columns (wcol, wcol + W/2) in turn, sliding 3x3 register window (v5)
+  //   stride 2: four channels, one column; even / odd input columns split across warp groups (v3)
+  constexpr int VV = S == 1 ? 2 : 4;   // channels per stencil thread
+  constexpr int NP2 = VV / 2;          // channel pairs per stencil thread
+  constexpr int cxn = CC / VV;         // stencil threads per pixel
+  const int cx = tid % cxn, widx = tid / cxn;
+  const int cch = c0 + cx * VV;
+  f32x2 w2[9][NP2];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int h = 0; h < NP2; ++h) w2[k][h] = pk2(wgt[(cch + 2 * h) * 9 + k], wgt[(cch + 2 * h + 1) * 9 + k]);
+  f32x2 st2[11][NP2];
+#pragma unroll
+  for (int q = 0; q < 11; ++q)
+#pragma unroll
+    for (int h = 0; h < NP2; ++h) st2[q][h] = 0ull;
+  const long erow = (long)W * C;
+
+  for (uint32_t k = 0; t < ntiles; t += nworkers, ++k) {
+    const int p = t >> nbsh, band = t & nbm, hi0 = band * THI;
+    const bool has_next = t + nworkers < ntiles;
+    float* tile = tile0 + (NT == 2 ? (size_t)(k & 1) * (G::TILE_BYTES / 4) : 0);
+    if (NT == 1 && k > 0) {
+      // every warp has finished the previous item's stencil: the tile (and a single E buffer) can be overwritten
+      __syncthreads();
+    }
+    if (NE == 1 && k > 0 && tid == 0) issue_e(t, 0);  // in flight while the dS tile is transformed
+    bk_mbar_wait(fullDS, k & 1);
+    // ---- BN2 backward on the staged tile: dS_raw = a*g - d*x - b, zero in the padding
+    {
+      uint32_t mv = m_col;
+      if (S == 1 && band == 0) mv &= ~m_r0;
+      if (band == nbm) mv &= ~m_rl;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        if (it < NIT - 1 || ((m_in >> it) & 1)) {
+          float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+          if ((mv >> it) & 1) {
+            const uint4 qg = *reinterpret_cast<const uint4*>(rawD + (size_t)(tid + it * 256) * 8);
+            const uint4 qx = *reinterpret_cast<const uint4*>(rawS + (size_t)(tid + it * 256) * 8);
+            const uint32_t gg[4] = {qg.x, qg.y, qg.z, qg.w}, xx[4] = {qx.x, qx.y, qx.z, qx.w};
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float g0, g1, x0, x1;
+              unpack_bf16x2(gg[j], g0, g1);
+              unpack_bf16x2(xx[j], x0, x1);
+              f32x2 rr, a2, d2;
+              if (COEF_REGS) {
+                rr = cb[j]; a2 = ca[j]; d2 = cd[j];
+              } else {
+                a2 = ldp2(sco + lcv * 8 + 2 * j);
+                rr = ldp2(sco + CC + lcv * 8 + 2 * j);
+                d2 = ldp2(sco + 2 * CC + lcv * 8 + 2 * j);
+              }
+              ffma2(rr, a2, pk2(g0, g1));
+              ffma2(rr, d2, pk2(x0, x1));
+              upk2(rr, v[2 * j], v[2 * j + 1]);
+            }
+            o0 = make_float4(v[0], v[1], v[2], v[3]);
+            o1 = make_float4(v[4], v[5], v[6], v[7]);
+          }
+          float* dst = tile + (size_t)(tid + it * 256) * 4;
+          *reinterpret_cast<float4*>(dst) = o0;
+          *reinterpret_cast<float4*>(dst + PLF) = o1;
+        }
+      }
+    }
+    __syncthreads();           // tile complete; rawD / rawS (and, stride 2, the other E buffer and tile) are free
+    if (tid == 0 && has_next) {
+      issue_ds(t + nworkers);
+      if (NE == 2) issue_e(t + nworkers, (k + 1) & 1);
+    }
+    bk_mbar_wait(fullE + (NE == 2 ? (k & 1) : 0), NE == 2 ? ((k >> 1) & 1) : (k & 1));
+    const bf16* rawEk = rawE + (NE == 2 ? (size_t)(k & 1) * (G::E_BYTES / 2) : 0);
+
+    if constexpr (S == 1) {
+      // ---- transposed stencil + weight gradient: sliding 3x3 register window down the tile rows
+      constexpr int NCOL = 256 / cxn;
+      static_assert(NCOL * 2 == W, "two column halves per thread");
+      const f32x2 qa0 = ldp2(sco + (COEF_REGS ? 0 : 3 * CC) + cx * 2);
+      const f32x2 qa1 = ldp2(sco + (COEF_REGS ? CC : 4 * CC) + cx * 2);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int wi = widx + half * NCOL;
+        const bf16* esm = rawEk + (size_t)wi * CC + cx * 2;  // row hl at + hl*W*CC
+        // tap (kh,kw) of input row hl: tile row hl+2-kh, column -kw
+        const float* tb = tile + (cx & 2 ? PLF : 0) + ((wi + 2) * cvn + (cx >> 2)) * 4 + (cx & 1) * 2;
+        bf16* dp = dE + (((long)p * H + hi0) * W + wi) * C + cch;
+        f32x2 R[3][3];
+        auto load_row = [&](const int r) {
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) R[r % 3][kw] = ldp2(tb + r * RSF - kw * PSF);
+        };
+        load_row(0);
+        load_row(1);
+#pragma unroll
+        for (int hl = 0; hl < THI; ++hl) {
+          load_row(hl + 2);
+          const f32x2 e2 = ldp2(esm + hl * (W * CC));
+          f32x2 sg;
+          const f32x2 ea = bnsilu_grad2_bf16(e2, qa0, qa1, sg);
+          f32x2 acc = 0ull;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const f32x2 q = R[(hl + 2 - kh) % 3][kw];
+              ffma2(acc, w2[kh * 3 + kw][0], q);
+              ffma2(st2[2 + kh * 3 + kw][0], ea, q);
+            }
+          const f32x2 o = fmul2(acc, sg);
+          stp2(dp, o);
+          dp += erow;
+          // statistics on the raw E: sum(o) and sum(o*e); sum(o*xhat) is formed once per CTA after the tile loop
+          fadd2(st2[0][0], o);
+          ffma2(st2[1][0], o, e2);
+        }
+      }
+    } else {
+      const int wi = (widx % (W / 2)) * 2 + widx / (W / 2);
+      const bool odd_w = (wi & 1) != 0;
+      const int colA = odd_w ? (wi + 1) / 2 : wi / 2;
+      const int colB = (wi - 1) / 2;
+      bf16* dp = dE + (((long)p * H + hi0) * W + wi) * C + cch;
+      const bf16* esm = rawEk + (size_t)wi * CC + cx * 4;  // row hl at + hl*W*CC
+      const ulonglong2 qa0 = *reinterpret_cast<const ulonglong2*>(sco + 3 * CC + cx * 4);
+      const ulonglong2 qa1 = *reinterpret_cast<const ulonglong2*>(sco + 4 * CC + cx * 4);
+      const float* tbase = tile + (cx & 1 ? PLF : 0) + (cx >> 1) * 4;
+      auto row_body = [&](const int hl, auto par_c) {
+        constexpr int PAR = decltype(par_c)::value;
+        f32x2 e2[2], sg0, sg1;
+        ldq2(esm + hl * (W * CC), e2);
+        const f32x2 ea0 = bnsilu_grad2_bf16(e2[0], qa0.x, qa1.x, sg0);
+        const f32x2 ea1 = bnsilu_grad2_bf16(e2[1], qa0.y, qa1.y, sg1);
+        f32x2 acc0 = 0ull, acc1 = 0ull;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          if ((PAR == 0) != (kh == 1)) continue;
+          const int r = (kh == 1) ? hl / 2 : (kh == 0 ? (hl + 1) / 2 : (hl - 1) / 2);
+          const float* tr = tbase + r * RSF;
+          if (odd_w) {  // warp-uniform
+            const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(tr + colA * PSF);
+            ffma2(acc0, w2[kh * 3 + 0][0], q.x);
+            ffma2(acc1, w2[kh * 3 + 0][NP2 - 1], q.y);
+            ffma2(st2[2 + kh * 3 + 0][0], ea0, q.x);
+            ffma2(st2[2 + kh * 3 + 0][NP2 - 1], ea1, q.y);
+            const ulonglong2 q2 = *reinterpret_cast<const ulonglong2*>(tr + colB * PSF);
+            ffma2(acc0, w2[kh * 3 + 2][0], q2.x);
+            ffma2(acc1, w2[kh * 3 + 2][NP2 - 1], q2.y);
+            ffma2(st2[2 + kh * 3 + 2][0], ea0, q2.x);
+            ffma2(st2[2 + kh * 3 + 2][NP2 - 1], ea1, q2.y);
+          } else {
+            const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(tr + colA * PSF);
+            ffma2(acc0, w2[kh * 3 + 1][0], q.x);
+            ffma2(acc1, w2[kh * 3 + 1][NP2 - 1], q.y);
+            ffma2(st2[2 + kh * 3 + 1][0], ea0, q.x);
+            ffma2(st2[2 + kh * 3 + 1][NP2 - 1], ea1, q.y);
+          }
+        }
+        f32x2 o2[2];
+        o2[0] = fmul2(acc0, sg0);
+        o2[1] = fmul2(acc1, sg1);
+        stq2(dp, o2);
+        dp += erow;
+        fadd2(st2[0][0], o2[0]);
+        fadd2(st2[0][NP2 - 1], o2[1]);
+        ffma2(st2[1][0], o2[0], e2[0]);
+        ffma2(st2[1][NP2 - 1], o2[1], e2[1]);
+      };
+#pragma unroll 1
+      for (int hl = 0; hl < THI; hl += 2) {
+        row_body(hl, std::integral_constant<int, 0>{});
+        row_body(hl + 1, std::integral_constant<int, 1>{});
+      }
+    }
+  }
+  __syncthreads();  // nothing in flight (every issued copy was waited for); the staging buffers become the reduction scratch
+  float st[11][VV];
+#pragma unroll
+  for (int q = 0; q < 11; ++q)
+#pragma unroll
+    for (int h = 0; h < NP2; ++h) upk2(st2[q][h], st[q][2 * h], st[q][2 * h + 1]);
+#pragma unroll
+  for (int j = 0; j < VV; ++j)  // sum(o*xhat1) from the raw-E sums
+    st[1][j] = coef1[3 * C + cch + j] * (st[1][j] - coef1[2 * C + cch + j] * st[0][j]);
+  block_reduce_channels<11, VV>(st, reinterpret_cast<float*>(smem_v6), cxn, 256 / cxn, partial + (long)worker * 11 * C, C, c0);
+}
+
+
+// =================================================================================================
+// backward, stride 1, one pass (v7).  The two-pass form above (BN2-backward pass into an fp32 tile, then the stencil)
+// leaves a stride-1 CTA no room for a second E buffer next to its 43 KB tile, needs two CTA barriers per item and ran at
+// 0.42 instructions per scheduler cycle.  Here a thread owns ONE channel pair and ONE column, walks down THI rows with a
+// sliding 3x3 register window and applies dS_raw = a*g - d*x - b to the staged bf16 values as it loads them (each value is
+// transformed by the three threads that use it: +15 % instructions, but no tile, no second pass).  The padding is zero
+// in g and x (tensor-map fill), so only the constant term has to vanish there: per-thread column variants of b, and a
+// warp-uniform choice for the first / last staged row.  Both staged items (dS_hat, S_raw, E) are double-buffered: one CTA
+// barrier per item and the whole next item streams in while the current one is convolved.
+// =================================================================================================
+template <int THI, int CC>
+struct SdwBwd7Geom {
+  static constexpr int W = 512 / CC, WP = W + 2, NR = THI + 2;
+  static constexpr int RAW_BYTES = NR * WP * CC * 2;
+  static constexpr int RAW_PITCH = (RAW_BYTES + 127) / 128 * 128;
+  static constexpr int E_BYTES = THI * W * CC * 2;
+  static constexpr int STAGE_BYTES = 2 * RAW_PITCH + E_BYTES;
+  static constexpr int OFF_BAR = 2 * STAGE_BYTES;
+  static constexpr int RED_BYTES = 256 * 11 * 2 * 4;
+  static constexpr int SMEM_USED = OFF_BAR + 16;
+  static constexpr int SMEM = SMEM_USED > RED_BYTES ? SMEM_USED : RED_BYTES;
+};
+
+template <int THI, int CC>
+__global__ void __launch_bounds__(256, 2)
+sdw_bwd_v7_kernel(const __grid_constant__ SdwBwdMaps maps, const float* __restrict__ coef2,
+                  const float* __restrict__ bcoef2, const float* __restrict__ coef1, const float* __restrict__ wgt,
+                  bf16* __restrict__ dE, float* __restrict__ partial, int NP, int H, int C, int nchunks, int nbsh) {
+  using G = SdwBwd7Geom<THI, CC>;
+  constexpr int W = G::W, WP = G::WP, NR = G::NR;
+  constexpr int cpn = CC / 2;  // channel pairs per pixel == stencil threads per column
+  static_assert(cpn * W == 256, "one (channel pair, column) per thread");
+  extern __shared__ __align__(128) unsigned char smem_v7[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_v7 + G::OFF_BAR);  // [2]
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x % nchunks, worker = blockIdx.x / nchunks, nworkers = gridDim.x / nchunks;
+  const int c0 = chunk * CC;
+  const int cp = tid % cpn, wi = tid / cpn;
+  const int cch = c0 + cp * 2;
+  if (tid == 0) {
+    bk_mbar_init(full, 1);
+    bk_mbar_init(full + 1, 1);
+    bk_mbar_init_fence();
+  }
+  // BN2 backward of this thread's channel pair: dS_raw = a*g + nd*x + nb (nb dropped where the tap lies in the padding)
+  f32x2 ca, cd, cbk[3], qa0, qa1;
+  {
+    float a[2], nb[2], nd[2], q0[2], q1[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cc = cch + h;
+      const float sc = coef2[cc], mu = coef2[2 * C + cc], rs = coef2[3 * C + cc];
+      const float k1 = bcoef2[cc], k2 = bcoef2[C + cc];
+      a[h] = sc;
+      nb[h] = -sc * (k1 - mu * rs * k2);
+      nd[h] = -sc * rs * k2;
+      BnSilu<bf16>::prep(coef1[cc], coef1[C + cc], q0[h], q1[h]);
+    }
+    ca = pk2(a[0], a[1]);
+    cd = pk2(nd[0], nd[1]);
+    const f32x2 cb = pk2(nb[0], nb[1]);
+    cbk[0] = (wi == W - 1) ? 0ull : cb;  // tap kw = 0 reads column wi + 1
+    cbk[1] = cb;
+    cbk[2] = (wi == 0) ? 0ull : cb;      // tap kw = 2 reads column wi - 1
+    qa0 = pk2(q0[0], q0[1]);
+    qa1 = pk2(q1[0], q1[1]);
+  }
+  f32x2 w2[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w2[k] = pk2(wgt[cch * 9 + k], wgt[(cch + 1) * 9 + k]);
+  f32x2 st2[11];
+#pragma unroll
+  for (int q = 0; q < 11; ++q) st2[q] = 0ull;
+  const int nbm = (1 << nbsh) - 1;
+  const int ntiles = NP << nbsh;
+  const long erow = (long)W * C;
+  auto issue = [&](int t, int b) {
+    const int p = t >> nbsh, hi0 = (t & nbm) * THI;
+    unsigned char* base = smem_v7 + (size_t)b * G::STAGE_BYTES;
+    bk_mbar_expect_tx(full + b, 2 * G::RAW_BYTES + G::E_BYTES);
+    tma_load_4d(base, &maps.ds, full + b, c0, -1, hi0 - 1, p);
+    tma_load_4d(base + G::RAW_PITCH, &maps.s, full + b, c0, -1, hi0 - 1, p);
+    tma_load_4d(base + 2 * G::RAW_PITCH, &maps.e, full + b, c0, 0, hi0, p);
+  };
+  __syncthreads();  // barriers initialised
+  int t = worker;
+  if (tid == 0 && t < ntiles) issue(t, 0);
+  // element offset of this thread's tap kw = 0 in staged row 0 (padded column wi + 2), and of its E pixel
+  const int toff = (wi + 2) * CC + cp * 2;
+  const int eoff = wi * CC + cp * 2;
+  for (uint32_t k = 0; t < ntiles; t += nworkers, ++k) {
+    const int p = t >> nbsh, band = t & nbm, hi0 = band * THI;
+    const int b = k & 1;
+    __syncthreads();  // every warp has finished the previous item: its stage can be refilled
+    if (tid == 0 && t + nworkers < ntiles) issue(t + nworkers, b ^ 1);
+    const bf16* rawD = reinterpret_cast<const bf16*>(smem_v7 + (size_t)b * G::STAGE_BYTES);
+    const bf16* rawS = rawD + G::RAW_PITCH / 2;
+    const bf16* esm = rawD + G::RAW_PITCH + eoff;
+    const bf16* gD = rawD + toff;
+    const bf16* gS = rawS + toff;
+    bf16* dp = dE + (((long)p * H + hi0) * W + wi) * C + cch;
+    const bool top = band == 0, bot = band == nbm;
+    bk_mbar_wait(full + b, (k >> 1) & 1);
+    f32x2 R[3][3];
+    auto load_row = [&](const int r) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        f32x2 u = cbk[kw];
+        if (r == 0) u = top ? 0ull : u;            // rows outside the image: g = x = 0 (tensor-map fill), b must vanish too
+        if (r == NR - 1) u = bot ? 0ull : u;
+        ffma2(u, ca, ldp2(gD + r * (WP * CC) - kw * CC));
+        ffma2(u, cd, ldp2(gS + r * (WP * CC) - kw * CC));
+        R[r % 3][kw] = u;
+      }
+    };
+    load_row(0);
+    load_row(1);
+#pragma unroll
+    for (int hl = 0; hl < THI; ++hl) {
+      load_row(hl + 2);
+      const f32x2 e2 = ldp2(esm + hl * (W * CC));
+      f32x2 sg;
+      const f32x2 ea = bnsilu_grad2_bf16(e2, qa0, qa1, sg);
+      f32x2 acc = 0ull;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const f32x2 q = R[(hl + 2 - kh) % 3][kw];
+          ffma2(acc, w2[kh * 3 + kw], q);
+          ffma2(st2[2 + kh * 3 + kw], ea, q);
+        }
+      const f32x2 o = fmul2(acc, sg);
+      stp2(dp, o);
+      dp += erow;
+      fadd2(st2[0], o);
+      ffma2(st2[1], o, e2);
+    }
+  }
+  __syncthreads();
+  float st[11][2];
+#pragma unroll
+  for (int q = 0; q < 11; ++q) upk2(st2[q], st[q][0], st[q][1]);
+#pragma unroll
+  for (int j = 0; j < 2; ++j)  // sum(o*xhat1) from the raw-E sums
+    st[1][j] = coef1[3 * C + cch + j] * (st[1][j] - coef1[2 * C + cch + j] * st[0][j]);
+  block_reduce_channels<11, 2>(st, reinterpret_cast<float*>(smem_v7), cpn, W, partial + (long)worker * 11 * C, C, c0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: 4-D tensor maps of channels-last bf16 activations [NP][H][W][C], box (bc, bw, bh, 1), zero fill outside.
+// Encoding is pure (a function of pointer, shape and box), so maps are memoised in a small direct-mapped table.
+// ------------------------------------------------------------------------------------------------
+#include <mutex>
+struct SdwMapKey {
+  const void* ptr;
+  int C, W, H, NP, bc, bw, bh;
+  bool operator==(const SdwMapKey& o) const {
+    return ptr == o.ptr && C == o.C && W == o.W && H == o.H && NP == o.NP && bc == o.bc && bw == o.bw && bh == o.bh;
+  }
+};
+static inline int sdw_make_map4(CUtensorMap* out, const void* ptr, int C, int W, int H, int NP, int bc, int bw, int bh) {
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+  static std::mutex mu;
+  constexpr int NSLOT = 512;
+  static SdwMapKey keys[NSLOT];
+  static CUtensorMap vals[NSLOT];
+  static bool used[NSLOT];
+  const SdwMapKey key{ptr, C, W, H, NP, bc, bw, bh};
+  size_t h = (size_t)((uintptr_t)ptr >> 8) * 1000003u;
+  h ^= (size_t)C * 31 + (size_t)W * 131 + (size_t)H * 1031 + (size_t)NP * 7 + (size_t)bc * 8191 + (size_t)bw * 524287 + (size_t)bh * 65599;
+  const int slot = (int)(h % NSLOT);
+  std::lock_guard<std::mutex> lock(mu);
+  if (used[slot] && keys[slot] == key) {
+    *out = vals[slot];
+    return 0;
+  }
+  if (!enc) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !fp)
+      return dwn_fail("cuTensorMapEncodeTiled entry point not found");
+    enc = (PFN_cuTensorMapEncodeTiled_v12000)fp;
+  }
+  if (((uintptr_t)ptr & 15) || (C & 7)) return dwn_fail("sdw tensor map: pointer / channel count not 16-byte aligned");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NP};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return dwn_fail("cuTensorMapEncodeTiled(4d) failed (%d): dims=(%d,%d,%d,%d) box=(%d,%d,%d)", (int)r, C, W, H, NP, bc, bw, bh);
+  keys[slot] = key;
+  vals[slot] = *out;
+  used[slot] = true;
+  return 0;
+}
+
+static inline int sdw_ilog2_exact(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return (1 << s) == v ? s : -1;
+}
+
+// returns 1 if the shape is not eligible (the caller falls back to the cp.async kernels), 0 on success, -1 on error
+template <int S>
+static int sdw_bwd_v6_launch(const void* dsh, const void* s_raw, const void* e_raw, const float* coef2, const float* bcoef2,
+                             const float* coef1, const float* wgt, void* dE, float* partial, int P, int NP, int H, int W,
+                             int C, int thi_pref, cudaStream_t st) {
+  if (H % S != 0 || W % S != 0) return 1;
+  int CC = 1024 / W;
+  if (CC > 128 || CC < (S == 1 ? 32 : 16) || CC * W != 1024 || C % CC != 0) return 1;
+  // stride 2: 16-row items where the kernel is instantiated for them (CC 16 / 32: blocks 0 and 4 at C2; -4 % vs 8 rows)
+  int THI = thi_pref > 0 ? thi_pref : ((S == 2 && CC <= 32) ? 16 : 8);
+  if (S == 1 && THI > 8) THI = 8;
+  while (THI > 4 && (H % THI != 0)) THI /= 2;
+  if (H % THI != 0 || (S == 2 && THI < 4)) return 1;
+  const int nbsh = sdw_ilog2_exact(H / THI);
+  if (nbsh < 0) return 1;
+  const int Ho = H / S, Wo = W / S;
+  const int NR = S == 1 ? THI + 2 : THI / 2 + 1;
+  SdwBwdMaps maps;
+  if (sdw_make_map4(&maps.ds, dsh, C, Wo, Ho, NP, CC, Wo + 2, NR) != 0) return -1;
+  if (sdw_make_map4(&maps.s, s_raw, C, Wo, Ho, NP, CC, Wo + 2, NR) != 0) return -1;
+  if (sdw_make_map4(&maps.e, e_raw, C, W, H, NP, CC, W, THI) != 0) return -1;
+  const int nchunks = C / CC;
+  dim3 grid(P * nchunks), block(256);
+#define LAUNCH(THI_, CC_)                                                                                       \
+  {                                                                                                             \
+    constexpr int sm = SdwBwdGeom<S, THI_, CC_>::SMEM;                                                          \
+    if constexpr (sm <= 115712) { /* two CTAs per SM */                                                         \
+      auto k = sdw_bwd_v6_kernel<S, THI_, CC_>;                                                                 \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);                                 \
+      k<<<grid, block, sm, st>>>(maps, coef2, bcoef2, coef1, wgt, (bf16*)dE, partial, NP, H, C, nchunks, nbsh); \
+    } else return 1;                                                                                            \
+  }
+#define LAUNCH_CC(THI_)                                                                                         \
+  {                                                                                                             \
+    if (CC == 32) LAUNCH(THI_, 32) else if (CC == 64) LAUNCH(THI_, 64) else if (CC == 128) LAUNCH(THI_, 128)   \
+    else if constexpr (S == 2) { if (CC == 16) LAUNCH(THI_, 16) else return 1; }                                \
+    else return 1;                                                                                              \
+  }
+  if (THI == 4) LAUNCH_CC(4)
+  else if (THI == 8) LAUNCH_CC(8)
+  else if constexpr (S == 2) {  // 16-row tiles only where the two E buffers still leave room for two CTAs per SM
+    if (THI == 16 && CC == 16) LAUNCH(16, 16) else if (THI == 16 && CC == 32) LAUNCH(16, 32) else return 1;
+  } else return 1;
+#undef LAUNCH_CC
+#undef LAUNCH
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// stride 1, one-pass kernel: CC = 512 / W channels per CTA.  Returns 1 if the shape is not eligible.
+static int sdw_bwd_v7_launch(const void* dsh, const void* s_raw, const void* e_raw, const float* coef2, const float* bcoef2,
+                             const float* coef1, const float* wgt, void* dE, float* partial, int P, int NP, int H, int W,
+                             int C, int thi_pref, cudaStream_t st) {
+  if (W < 4 || W > 32 || 512 % W != 0) return 1;
+  const int CC = 512 / W;
+  if (C % CC != 0) return 1;
+  int THI = thi_pref > 0 ? thi_pref : (W == 32 ? 16 : 8);
+  while (THI > 4 && (H % THI != 0)) THI /= 2;
+  if (H % THI != 0) return 1;
+  const int nbsh = sdw_ilog2_exact(H / THI);
+  if (nbsh < 0) return 1;
+  SdwBwdMaps maps;
+  if (sdw_make_map4(&maps.ds, dsh, C, W, H, NP, CC, W + 2, THI + 2) != 0) return -1;
+  if (sdw_make_map4(&maps.s, s_raw, C, W, H, NP, CC, W + 2, THI + 2) != 0) return -1;
+  if (sdw_make_map4(&maps.e, e_raw, C, W, H, NP, CC, W, THI) != 0) return -1;
+  const int nchunks = C / CC;
+  dim3 grid(P * nchunks), block(256);
+#define LAUNCH(THI_, CC_)                                                                                       \
+  {                                                                                                             \
+    constexpr int sm = SdwBwd7Geom<THI_, CC_>::SMEM;                                                            \
+    if constexpr (sm <= 115712) { /* two CTAs per SM */                                                         \
+      auto k = sdw_bwd_v7_kernel<THI_, CC_>;                                                                    \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);                                 \
+      k<<<grid, block, sm, st>>>(maps, coef2, bcoef2, coef1, wgt, (bf16*)dE, partial, NP, H, C, nchunks, nbsh); \
+    } else return 1;                                                                                            \
+  }
+#define LAUNCH_CC(THI_)                                                                                         \
+  {                                                                                                             \
+    if (CC == 16) LAUNCH(THI_, 16) else if (CC == 32) LAUNCH(THI_, 32) else if (CC == 64) LAUNCH(THI_, 64)     \
+    else if (CC == 128) LAUNCH(THI_, 128) else return 1;                                                        \
+  }
+  if (THI == 4) LAUNCH_CC(4) else if (THI == 8) LAUNCH_CC(8) else if (THI == 16) LAUNCH_CC(16) else return 1;
+#undef LAUNCH_CC
+#undef LAUNCH
+  DWN_LAUNCH_CHECK();
+  return 0;
+}
