@@ -232,6 +232,28 @@ __device__ __forceinline__ void stp2(bf16* p, f32x2 v) {
   *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(a, b);
 }
 
+// store + return the value as the consumer will see it (bf16: rounded; fp32: unchanged).  The BatchNorm-backward sums of a
+// gradient must be taken over the ROUNDED values: the folded BN1 backward (dwn_pw_algebra.cu) subtracts mean terms from a
+// GEMM over the stored tensor, and only the stored tensor's own sums make that cancellation exact
+__device__ __forceinline__ f32x2 stp2_rnd(float* p, f32x2 v) { stp2(p, v); return v; }
+__device__ __forceinline__ f32x2 stp2_rnd(bf16* p, f32x2 v) {
+  float a, b;
+  upk2(v, a, b);
+  const uint32_t w = pack_bf16x2(a, b);
+  *reinterpret_cast<uint32_t*>(p) = w;
+  unpack_bf16x2(w, a, b);
+  return pk2(a, b);
+}
+__device__ __forceinline__ void stq2_rnd(float* p, f32x2 (&v)[2]) { stq2(p, v); }
+__device__ __forceinline__ void stq2_rnd(bf16* p, f32x2 (&v)[2]) {
+  float a, b, c, d;
+  upk2(v[0], a, b); upk2(v[1], c, d);
+  uint2 r; r.x = pack_bf16x2(a, b); r.y = pack_bf16x2(c, d);
+  *reinterpret_cast<uint2*>(p) = r;
+  unpack_bf16x2(r.x, a, b); unpack_bf16x2(r.y, c, d);
+  v[0] = pk2(a, b); v[1] = pk2(c, d);
+}
+
 // ---- reductions ----------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

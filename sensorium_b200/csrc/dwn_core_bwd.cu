@@ -789,8 +789,7 @@ tdw_bwd_kernel(T* __restrict__ dth, const T* __restrict__ tm, const T* __restric
             ffma2(st2[2 + k], sa2, dT[t]);
           }
         }
-        const f32x2 o = fmul2(acc, pk2(sg[0], sg[1]));
-        stp2(gp + u * tstride, o);
+        const f32x2 o = stp2_rnd(gp + u * tstride, fmul2(acc, pk2(sg[0], sg[1])));  // BN2-backward sums over the stored values
         fadd2(st2[0], o);
         ffma2(st2[1], o, pk2((s[0] - mu2[0]) * rs2[0], (s[1] - mu2[1]) * rs2[1]));
       }
@@ -936,8 +935,7 @@ tdw_bwd_bulk_kernel(bf16* __restrict__ dth, const bf16* __restrict__ tm, const b
             ffma2(st2[2 + k], sa2, dT[t]);
           }
         }
-        const f32x2 o = fmul2(acc, sgr);
-        stp2(gp + (long)u * tstride, o);
+        const f32x2 o = stp2_rnd(gp + (long)u * tstride, fmul2(acc, sgr));  // BN2-backward sums over the stored values
         fadd2(st2[0], o);
         f32x2 xh = mu2;
         ffma2(xh, s, rs2);

@@ -276,8 +276,7 @@ sdw_bwd_v6_kernel(const __grid_constant__ SdwBwdMaps maps, const float* __restri
               ffma2(acc, w2[kh * 3 + kw][0], q);
               ffma2(st2[2 + kh * 3 + kw][0], ea, q);
             }
-          const f32x2 o = fmul2(acc, sg);
-          stp2(dp, o);
+          const f32x2 o = stp2_rnd(dp, fmul2(acc, sg));  // statistics over the stored (rounded) values
           dp += erow;
           // statistics on the raw E: sum(o) and sum(o*e); sum(o*xhat) is formed once per CTA after the tile loop
           fadd2(st2[0][0], o);
@@ -328,7 +327,7 @@ sdw_bwd_v6_kernel(const __grid_constant__ SdwBwdMaps maps, const float* __restri
         f32x2 o2[2];
         o2[0] = fmul2(acc0, sg0);
         o2[1] = fmul2(acc1, sg1);
-        stq2(dp, o2);
+        stq2_rnd(dp, o2);  // o2 <- the stored (rounded) values
         dp += erow;
         fadd2(st2[0][0], o2[0]);
         fadd2(st2[0][NP2 - 1], o2[1]);
@@ -487,8 +486,7 @@ sdw_bwd_v7_kernel(const __grid_constant__ SdwBwdMaps maps, const float* __restri
           ffma2(acc, w2[kh * 3 + kw], q);
           ffma2(st2[2 + kh * 3 + kw], ea, q);
         }
-      const f32x2 o = fmul2(acc, sg);
-      stp2(dp, o);
+      const f32x2 o = stp2_rnd(dp, fmul2(acc, sg));  // statistics over the stored (rounded) values
       dp += erow;
       fadd2(st2[0], o);
       ffma2(st2[1], o, e2);

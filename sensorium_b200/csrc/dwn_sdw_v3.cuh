@@ -436,7 +436,7 @@ sdw_bwd_v3_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
       f32x2 o2[2];
       o2[0] = fmul2(acc0, sg0);
       o2[1] = fmul2(acc1, sg1);
-      stq2(dp + hl * erow, o2);
+      stq2_rnd(dp + hl * erow, o2);  // o2 <- the stored (rounded) values
       // statistics on the raw E: sum(o) and sum(o*e); sum(o*xhat) = rstd*(sum(o*e) - mean*sum(o)) is formed once
       // per CTA after the tile loop
       fadd2(st2[0][0], o2[0]);
@@ -627,8 +627,7 @@ sdw_bwd_v5_kernel(const bf16* __restrict__ dsh, const bf16* __restrict__ s_raw, 
             ffma2(acc, w2[kh * 3 + kw], q);
             ffma2(st2[2 + kh * 3 + kw], ea, q);
           }
-        const f32x2 o = fmul2(acc, sg);
-        stp2(dp + hl * orow, o);
+        const f32x2 o = stp2_rnd(dp + hl * orow, fmul2(acc, sg));  // the stored (rounded) value
         // statistics on the raw E: sum(o) and sum(o*e); sum(o*xhat) is formed once per CTA after the tile loop
         fadd2(st2[0], o);
         ffma2(st2[1], o, e2);
