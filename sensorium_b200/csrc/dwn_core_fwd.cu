@@ -4,6 +4,8 @@
 #include "dwn_reduce.cuh"
 #include "dwn_bulk.cuh"
 #include "dwn_sdw_v3.cuh"
+#include "dwn_sdw_fwd_tma.cuh"
+#include <cstdlib>
 
 // =================================================================================================
 // input moments: sums and second moments of the 5 input channels (NCDHW fp32 input).
@@ -484,8 +486,18 @@ extern "C" int dwn_sdw_fwd(const void* in, const float* coef, const float* wgt, 
   if (dtype == DWN_DT_F32)
     return stride == 1 ? sdw_fwd_launch<float, 1>(in, coef, wgt, out, partial, P, NP, H, W, C, st)
                        : sdw_fwd_launch<float, 2>(in, coef, wgt, out, partial, P, NP, H, W, C, st);
-  int rc = stride == 1 ? sdw_fwd_v3_launch<1>(in, coef, wgt, out, partial, P, NP, H, W, C, st)
-                       : sdw_fwd_v3_launch<2>(in, coef, wgt, out, partial, P, NP, H, W, C, st);
+  // TMA-staged kernels first (DWN_SDW_FWD_TMA=0 selects the cp.async kernels, DWN_SDW_FWD_THO the rows per item: A/B runs)
+  const char* env_tma = getenv("DWN_SDW_FWD_TMA");
+  const char* env_tho = getenv("DWN_SDW_FWD_THO");
+  int rc = 1;
+  if (!env_tma || atoi(env_tma) != 0) {
+    const int tho = env_tho ? atoi(env_tho) : 0;
+    rc = stride == 1 ? sdw_fwd_v6_launch<1>(in, coef, wgt, out, partial, P, NP, H, W, C, tho, st)
+                     : sdw_fwd_v6_launch<2>(in, coef, wgt, out, partial, P, NP, H, W, C, tho, st);
+    if (rc <= 0) return rc;
+  }
+  rc = stride == 1 ? sdw_fwd_v3_launch<1>(in, coef, wgt, out, partial, P, NP, H, W, C, st)
+                   : sdw_fwd_v3_launch<2>(in, coef, wgt, out, partial, P, NP, H, W, C, st);
   if (rc <= 0) return rc;
   return stride == 1 ? sdw_fwd_launch<bf16, 1>(in, coef, wgt, out, partial, P, NP, H, W, C, st)
                      : sdw_fwd_launch<bf16, 2>(in, coef, wgt, out, partial, P, NP, H, W, C, st);
