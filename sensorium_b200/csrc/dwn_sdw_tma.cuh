@@ -154,7 +154,13 @@ sdw_bwd_v6_kernel(const __grid_constant__ SdwBwdMaps maps, const float* __restri
   auto issue_e = [&](int t, int e) {
     const int p = t >> nbsh, hi0 = (t & nbm) * THI;
     bk_mbar_expect_tx(fullE + e, G::E_BYTES);
-    tma_load_4d(reinterpret_cast<unsigned char*>(rawE) + (size_t)e * G::E_BYTES, &maps.e, fullE + e, c0, 0, hi0, p);
+    unsigned char* dst = reinterpret_cast<unsigned char*>(rawE) + (size_t)e * G::E_BYTES;
+    if (S == 1) {
+      tma_load_4d(dst, &maps.e, fullE + e, c0, 0, hi0, p);
+    } else {  // even columns, then odd columns (the map walks W with element stride 2): the taps of a warp read contiguous pixels
+      tma_load_4d(dst, &maps.e, fullE + e, c0, 0, hi0, p);
+      tma_load_4d(dst + G::E_BYTES / 2, &maps.e, fullE + e, c0, 1, hi0, p);
+    }
   };
   __syncthreads();  // barriers initialised, sco written
   int t = worker;
@@ -289,14 +295,15 @@ sdw_bwd_v6_kernel(const __grid_constant__ SdwBwdMaps maps, const float* __restri
       const int colA = odd_w ? (wi + 1) / 2 : wi / 2;
       const int colB = (wi - 1) / 2;
       bf16* dp = dE + (((long)p * H + hi0) * W + wi) * C + cch;
-      const bf16* esm = rawEk + (size_t)wi * CC + cx * 4;  // row hl at + hl*W*CC
+      // E tile in two column planes [parity][THI][W/2][CC]: row hl at + hl*(W/2)*CC
+      const bf16* esm = rawEk + (odd_w ? G::E_BYTES / 4 : 0) + (size_t)(wi >> 1) * CC + cx * 4;
       const ulonglong2 qa0 = *reinterpret_cast<const ulonglong2*>(sco + 3 * CC + cx * 4);
       const ulonglong2 qa1 = *reinterpret_cast<const ulonglong2*>(sco + 4 * CC + cx * 4);
       const float* tbase = tile + (cx & 1 ? PLF : 0) + (cx >> 1) * 4;
       auto row_body = [&](const int hl, auto par_c) {
         constexpr int PAR = decltype(par_c)::value;
         f32x2 e2[2], sg0, sg1;
-        ldq2(esm + hl * (W * CC), e2);
+        ldq2(esm + hl * (W / 2 * CC), e2);
         const f32x2 ea0 = bnsilu_grad2_bf16(e2[0], qa0.x, qa1.x, sg0);
         const f32x2 ea1 = bnsilu_grad2_bf16(e2[1], qa0.y, qa1.y, sg1);
         f32x2 acc0 = 0ull, acc1 = 0ull;
@@ -509,21 +516,24 @@ sdw_bwd_v7_kernel(const __grid_constant__ SdwBwdMaps maps, const float* __restri
 #include <mutex>
 struct SdwMapKey {
   const void* ptr;
-  int C, W, H, NP, bc, bw, bh;
+  int C, W, H, NP, bc, bw, bh, sw;
   bool operator==(const SdwMapKey& o) const {
-    return ptr == o.ptr && C == o.C && W == o.W && H == o.H && NP == o.NP && bc == o.bc && bw == o.bw && bh == o.bh;
+    return ptr == o.ptr && C == o.C && W == o.W && H == o.H && NP == o.NP && bc == o.bc && bw == o.bw && bh == o.bh && sw == o.sw;
   }
 };
-static inline int sdw_make_map4(CUtensorMap* out, const void* ptr, int C, int W, int H, int NP, int bc, int bw, int bh) {
+// sw = element stride over the W dimension: sw = 2 with box width bw loads columns w0, w0 + 2, ... (bw / 2 of them, packed:
+// tests/gpu_checks/tma_stride_probe.cu), which de-interleaves even and odd columns for the stride-2 kernels
+static inline int sdw_make_map4(CUtensorMap* out, const void* ptr, int C, int W, int H, int NP, int bc, int bw, int bh,
+                                int sw = 1) {
   static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
   static std::mutex mu;
   constexpr int NSLOT = 512;
   static SdwMapKey keys[NSLOT];
   static CUtensorMap vals[NSLOT];
   static bool used[NSLOT];
-  const SdwMapKey key{ptr, C, W, H, NP, bc, bw, bh};
+  const SdwMapKey key{ptr, C, W, H, NP, bc, bw, bh, sw};
   size_t h = (size_t)((uintptr_t)ptr >> 8) * 1000003u;
-  h ^= (size_t)C * 31 + (size_t)W * 131 + (size_t)H * 1031 + (size_t)NP * 7 + (size_t)bc * 8191 + (size_t)bw * 524287 + (size_t)bh * 65599;
+  h ^= (size_t)C * 31 + (size_t)W * 131 + (size_t)H * 1031 + (size_t)NP * 7 + (size_t)bc * 8191 + (size_t)bw * 524287 + (size_t)bh * 65599 + (size_t)sw * 2654435761u;
   const int slot = (int)(h % NSLOT);
   std::lock_guard<std::mutex> lock(mu);
   if (used[slot] && keys[slot] == key) {
@@ -542,7 +552,7 @@ static inline int sdw_make_map4(CUtensorMap* out, const void* ptr, int C, int W,
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NP};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)sw, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -580,7 +590,7 @@ static int sdw_bwd_v6_launch(const void* dsh, const void* s_raw, const void* e_r
   SdwBwdMaps maps;
   if (sdw_make_map4(&maps.ds, dsh, C, Wo, Ho, NP, CC, Wo + 2, NR) != 0) return -1;
   if (sdw_make_map4(&maps.s, s_raw, C, Wo, Ho, NP, CC, Wo + 2, NR) != 0) return -1;
-  if (sdw_make_map4(&maps.e, e_raw, C, W, H, NP, CC, W, THI) != 0) return -1;
+  if (sdw_make_map4(&maps.e, e_raw, C, W, H, NP, CC, W, THI, S) != 0) return -1;
   const int nchunks = C / CC;
   dim3 grid(P * nchunks), block(256);
 #define LAUNCH(THI_, CC_)                                                                                       \
