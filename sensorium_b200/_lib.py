@@ -2,9 +2,12 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libdwn_b200.so"
+# DWN_LIB: another build of the same library (A/B timing of two revisions on one GPU box, tests/gpu_checks/run_ab.sh)
+_LIB_PATH = Path(os.environ["DWN_LIB"]).resolve() if os.environ.get("DWN_LIB") else \
+    Path(__file__).resolve().parent / "libdwn_b200.so"
 _lib = None
 
 

@@ -429,8 +429,9 @@ __global__ void __launch_bounds__(256) se_bwd_a1_kernel(const float* __restrict_
   }
 }
 
-// a2: one CTA (1024 threads) per sample: dh -> dhpre -> dmean.  All weight reads are coalesced (lanes run over the
-// contiguous index of w2 [C][RD] / w1 [RD][C]) and unrolled so that several loads are in flight per thread.
+// a2: one CTA (1024 threads) per sample: dh -> dhpre -> dmean.  Both weight passes issue their global loads in explicit
+// batches of 8 with select-predication (no early-exit branch between loads): the loops the compiler produced from a plain
+// `#pragma unroll 8` waited for every load before issuing the next (67 us at C = 1792 in the ncu launch list, all latency).
 __global__ void __launch_bounds__(1024) se_bwd_a2_kernel(const float* __restrict__ dpre2, const float* __restrict__ hpre,
                                                         const float* __restrict__ w1, const float* __restrict__ w2,
                                                         float* __restrict__ dhpre, float* __restrict__ dmean, int C,
@@ -443,14 +444,31 @@ __global__ void __launch_bounds__(1024) se_bwd_a2_kernel(const float* __restrict
   for (int k = tid; k < C; k += blockDim.x) s_dp2[k] = dpre2[(long)b * C + k];
   __syncthreads();
   const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-  for (int r0 = 0; r0 < RD; r0 += 32) {
-    const int r = r0 + lane;
-    float s = 0.f;
-    if (r < RD) {
-#pragma unroll 8
-      for (int k = wid; k < C; k += nw) s = fmaf(s_dp2[k], __ldg(&w2[(long)k * RD + r]), s);
-      s_part[wid * RD + r] = s;
+  // dh[r] = sum_k dpre2[k] * w2[k][r]: warp = a contiguous slice of k, lanes = r (two r per lane and pass)
+  const int kc = (C + nw - 1) / nw;
+  const int kbeg = min(C, wid * kc), kend = min(C, kbeg + kc);
+  for (int r0 = 0; r0 < RD; r0 += 64) {
+    const int ra = r0 + lane, rb = r0 + 32 + lane;
+    const bool oka = ra < RD, okb = rb < RD;
+    float sa = 0.f, sb = 0.f;
+    for (int k0 = kbeg; k0 < kend; k0 += 8) {
+      float wa[8], wb[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kk = min(k0 + j, kend - 1);
+        const bool okk = k0 + j < kend;
+        wa[j] = (oka && okk) ? __ldg(&w2[(long)kk * RD + ra]) : 0.f;
+        wb[j] = (okb && okk) ? __ldg(&w2[(long)kk * RD + rb]) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = s_dp2[min(k0 + j, kend - 1)];
+        sa = fmaf(d, wa[j], sa);
+        sb = fmaf(d, wb[j], sb);
+      }
     }
+    if (oka) s_part[wid * RD + ra] = sa;
+    if (okb) s_part[wid * RD + rb] = sb;
   }
   __syncthreads();
   for (int r = tid; r < RD; r += blockDim.x) {
@@ -463,10 +481,16 @@ __global__ void __launch_bounds__(1024) se_bwd_a2_kernel(const float* __restrict
     dhpre[(long)b * RD + r] = d;
   }
   __syncthreads();
+  // dmean[k] = sum_r dhp[r] * w1[r][k]: thread = k (coalesced rows of w1), r in batches of 8
   for (int k = tid; k < C; k += blockDim.x) {
     float s = 0.f;
-#pragma unroll 8
-    for (int r = 0; r < RD; ++r) s = fmaf(s_dhp[r], __ldg(&w1[(long)r * C + k]), s);
+    for (int r0 = 0; r0 < RD; r0 += 8) {
+      float wv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = (r0 + j < RD) ? __ldg(&w1[(long)min(r0 + j, RD - 1) * C + k]) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s = fmaf(s_dhp[min(r0 + j, RD - 1)], wv[j], s);
+    }
     dmean[(long)b * C + k] = s;
   }
 }

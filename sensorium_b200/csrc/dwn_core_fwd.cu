@@ -780,18 +780,33 @@ __global__ void __launch_bounds__(1024) se_mlp_kernel(const float* __restrict__ 
   const int b = blockIdx.x, tid = threadIdx.x;
   for (int c = tid; c < C; c += blockDim.x) {
     float s = 0.f;
-#pragma unroll 8
-    for (int j = 0; j < J; ++j) s += partial[((long)b * J + j) * C + c];
+    for (int j0 = 0; j0 < J; j0 += 16) {  // 16 independent loads in flight, same summation order
+      float pv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pv[j] = (j0 + j < J) ? partial[((long)b * J + min(j0 + j, J - 1)) * C + c] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s += pv[j];
+    }
     s *= inv_n;
     s_mean[c] = s;
     mean_out[(long)b * C + c] = s;
   }
   __syncthreads();
   const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  // global loads in explicit batches of 8 with select-predication: the plain unrolled loops waited for every load before
+  // issuing the next one (35 us at C = 1792, pure latency)
   for (int r = wid; r < RD; r += nw) {
     float s = 0.f;
-#pragma unroll 8
-    for (int c = lane; c < C; c += 32) s = fmaf(__ldg(&w1[(long)r * C + c]), s_mean[c], s);
+    for (int c0 = 0; c0 < C; c0 += 512) {
+      float wv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c = c0 + lane + 32 * j;
+        wv[j] = c < C ? __ldg(&w1[(long)r * C + c]) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s = fmaf(wv[j], s_mean[min(c0 + lane + 32 * j, C - 1)], s);
+    }
     s = warp_sum(s);
     if (lane == 0) {
       s += b1[r];
@@ -800,11 +815,31 @@ __global__ void __launch_bounds__(1024) se_mlp_kernel(const float* __restrict__ 
     }
   }
   __syncthreads();
-  for (int c = tid; c < C; c += blockDim.x) {
-    float s = b2[c];
-#pragma unroll 8
-    for (int r = 0; r < RD; ++r) s = fmaf(__ldg(&w2[(long)c * RD + r]), s_h[r], s);
-    gate_out[(long)b * C + c] = 1.0f / (1.0f + expf(-s));
+  // gate[c] = sigmoid(b2[c] + sum_r w2[c][r] h[r]): warp = 8 consecutive channels at a time (one contiguous 8 x RD block of
+  // w2), lanes = r
+  for (int cb = wid * 8; cb < C; cb += nw * 8) {
+    float s8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s8[j] = 0.f;
+    for (int r0 = 0; r0 < RD; r0 += 64) {
+      float wa[8], wb[8];
+      const int ra = r0 + lane, rb = r0 + 32 + lane;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool okc = cb + j < C;
+        wa[j] = (okc && ra < RD) ? __ldg(&w2[(long)(cb + j) * RD + ra]) : 0.f;
+        wb[j] = (okc && rb < RD) ? __ldg(&w2[(long)(cb + j) * RD + rb]) : 0.f;
+      }
+      const float ha = s_h[min(ra, RD - 1)], hb = s_h[min(rb, RD - 1)];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s8[j] = fmaf(wb[j], hb, fmaf(wa[j], ha, s8[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s8[j] = warp_sum(s8[j]);
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine = lane == j ? s8[j] : mine;
+    if (lane < 8 && cb + lane < C) gate_out[(long)b * C + cb + lane] = 1.0f / (1.0f + expf(-(mine + b2[cb + lane])));
   }
 }
 

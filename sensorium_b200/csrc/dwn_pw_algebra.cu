@@ -7,6 +7,7 @@
 //        dW = diag(a) (G^T X) - b (x) sx - diag(d) W Gx            -> the split-K wgrad GEMM on G + a tiny finalize
 // This removes colstats(E) and bn_bwd_apply (4 passes over the largest tensor of the network).
 #include "dwn_common.cuh"
+#include <cstdlib>
 
 // out[c] = sum_p partial[p][q][c]      (block = 32 channels x 32 slices of P)
 __global__ void __launch_bounds__(1024) partial_colsum_kernel(const float* __restrict__ partial, int P, int NQ, int q,
@@ -71,14 +72,18 @@ extern "C" int dwn_gram_finalize(const float* part, int Z, int ci, const float* 
   return 0;
 }
 
-// one warp per output channel c of conv_pw
+// one warp per output channel c of conv_pw.  var = w^T C w on the centred second moment C (gram_finalize_kernel): lane l
+// owns the columns k = l + 32 i of t = w^T C, rows of C are read coalesced in batches of 4 rows x 8 columns of independent
+// loads (the former row-slice loop issued one dependent L2 round trip per row group: 100 us at ci = 256); fp32 partial sums
+// over 16 rows are flushed into fp64.  A variant that staged C through shared memory measured slower inside the replayed
+// step (C is L2-resident there): tests/gpu_checks/run_ab.sh
 __global__ void __launch_bounds__(256) pw_stats_kernel(const float* __restrict__ cgram, const float* __restrict__ sx,
-                                                      const bf16* __restrict__ w, double count,
-                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                      float* __restrict__ rmean, float* __restrict__ rvar,
-                                                      long long* __restrict__ nbt, float momentum, float eps,
-                                                      float* __restrict__ coef, int mid, int ci) {
-  extern __shared__ float sw[];  // [8][ci]
+                                                             const bf16* __restrict__ w, double count,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float* __restrict__ rmean, float* __restrict__ rvar,
+                                                             long long* __restrict__ nbt, float momentum, float eps,
+                                                             float* __restrict__ coef, int mid, int ci) {
+  extern __shared__ __align__(16) float sw[];  // [8][ci]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int c = blockIdx.x * 8 + wid;
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
@@ -90,26 +95,46 @@ __global__ void __launch_bounds__(256) pw_stats_kernel(const float* __restrict__
   double m1 = 0;
   for (int k = lane; k < ci; k += 32) m1 += (double)wc[k] * (double)sx[k];
   m1 = warp_sum_d(m1);
-  // var = w^T C w on the centred second moment C (gram_finalize_kernel): every lane accumulates its column slice of each
-  // row, four rows in flight to hide L2 latency; rows are combined in fp64
   double q = 0;
-  for (int j0 = 0; j0 < ci; j0 += 4) {
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = lane; k < ci; k += 32) {
-      const float wk = wc[k];
+  for (int kb = 0; kb < ci; kb += 256) {
+    double td[8];
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj)
-        if (j0 + jj < ci) v[jj] = fmaf(cgram[(long)(j0 + jj) * ci + k], wk, v[jj]);
+    for (int i = 0; i < 8; ++i) td[i] = 0.0;
+    for (int j0 = 0; j0 < ci; j0 += 16) {
+      float t[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = 0.f;
+#pragma unroll
+      for (int jb = 0; jb < 16; jb += 4) {
+        float cv[4][8];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int j = j0 + jb + jj, k = kb + lane + 32 * i;
+            cv[jj][i] = (j < ci && k < ci) ? cgram[(long)j * ci + k] : 0.f;
+          }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float wj = wc[min(j0 + jb + jj, ci - 1)];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = fmaf(cv[jj][i], wj, t[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) td[i] += (double)t[i];
     }
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
-      if (j0 + jj < ci) q += (double)wc[j0 + jj] * (double)v[jj];
+    for (int i = 0; i < 8; ++i) {
+      const int k = kb + lane + 32 * i;
+      if (k < ci) q += td[i] * (double)wc[k];
+    }
   }
   q = warp_sum_d(q);
   if (lane != 0) return;
   const double mean = m1 * inv_m;
   double var = q;
-  if (var < 0) var = 0;  // guard only: C is positive semi-definite up to rounding
+  if (var < 0) var = 0;
   const double rstd = 1.0 / sqrt(var + (double)eps);
   const double g = gamma[c], b = beta[c];
   coef[c] = (float)(g * rstd);
@@ -166,7 +191,13 @@ __global__ void pw_q_partial_kernel(const float* __restrict__ abd, const bf16* _
   const int cnt = max(cend - cbeg, 0);
   float* scf = reinterpret_cast<float*>(pwq_sm);                       // [cper][PWQ_JT]
   bf16* sw = reinterpret_cast<bf16*>(pwq_sm + (size_t)cper * PWQ_JT * sizeof(float));  // [cper][ci]
-  for (int i = k; i < cnt * ci; i += blockDim.x) sw[i] = w[(long)cbeg * ci + i];
+  if ((ci & 7) == 0) {  // 16-byte copies, all independent (the scalar loop was 56 dependent-issue rounds at ci = 256)
+    const uint4* src = reinterpret_cast<const uint4*>(w + (long)cbeg * ci);
+    uint4* dst = reinterpret_cast<uint4*>(sw);
+    for (int i = k; i < cnt * ci / 8; i += blockDim.x) dst[i] = src[i];
+  } else {
+    for (int i = k; i < cnt * ci; i += blockDim.x) sw[i] = w[(long)cbeg * ci + i];
+  }
   for (int i = k; i < cnt * PWQ_JT; i += blockDim.x) {
     const int cl = i / PWQ_JT, j = j0 + i % PWQ_JT, c = cbeg + cl;
     scf[i] = j < ci ? abd[2 * mid + c] * __bfloat162float(w[(long)c * ci + j]) : (j == ci ? abd[mid + c] : 0.f);
