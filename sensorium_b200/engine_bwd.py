@@ -239,7 +239,7 @@ def run_backward(mod, sv, grad_outs: Sequence[Optional[torch.Tensor]]) -> List[O
         grads[blk.temp_covn_dw[0].weight] = dwt                 # filled by the side chain below
         # spatial dw backward (da now holds d s_hat)
         dE = _empty((Mi, mid), adt, dev)
-        psdw = _p_sdw(Mi * mid) if bf else _P_SDW
+        psdw = 42 if bf else _P_SDW     # TMA-staged backward: 42 workers per channel chunk are best on every block (KB_PS sweep)
         part11 = _empty((psdw, 11, mid), torch.float32, dev)
         call("dwn_sdw_bwd", da, b.S, b.E, b.coef2, bcoef2, b.coef1, blk.spat_covn_dw[0].weight, dE, part11, psdw, B * T,
              b.Hi, b.Wi, mid, s, dcode, st, _tag="sdw_bwd", _bytes=(2 * Mo + 2 * Mi) * mid * es)
