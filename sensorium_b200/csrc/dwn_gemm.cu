@@ -8,6 +8,7 @@
 #include "dwn_common.cuh"
 #include "../../include/dwn_b200.h"
 #include <cuda.h>
+#include <mutex>
 #include <cudaTypedefs.h>
 #include <string.h>
 
@@ -395,8 +396,45 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // bf16 operand map.  mn_major=0: memory [Z][rows][K] (ld = row pitch) -> dims (K, rows, Z), box (64, box_rows, 1)
 //                    mn_major=1: memory [Z][K][rows] (ld = row pitch) -> dims (rows, K, Z), box (64, 64, 1)
+// Encoding is a pure function of (pointer, shape, strides, box): maps are memoised in a direct-mapped table, so an eager
+// step re-uses the ~120 maps of the previous step instead of calling the driver for each (SURVEY.md 8b "cached maps";
+// a replayed CUDA graph carries its maps as kernel parameters and never gets here).
+struct GemmMapKey {
+  const void* ptr;
+  long rows, K, ld, zstride;
+  int mn_major, zdim, box_rows;
+  bool operator==(const GemmMapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && K == o.K && ld == o.ld && zstride == o.zstride && mn_major == o.mn_major &&
+           zdim == o.zdim && box_rows == o.box_rows;
+  }
+};
+static int make_operand_map_uncached(CUtensorMap* map, const void* ptr, int mn_major, long rows, long K, long ld,
+                                     long zstride, int zdim, int box_rows);
 static int make_operand_map(CUtensorMap* map, const void* ptr, int mn_major, long rows, long K, long ld, long zstride,
                             int zdim, int box_rows) {
+  constexpr int NSLOT = 1024;
+  static GemmMapKey keys[NSLOT];
+  static CUtensorMap vals[NSLOT];
+  static bool used[NSLOT];
+  static std::mutex mu;
+  const GemmMapKey key{ptr, rows, K, ld, zstride, mn_major, zdim, box_rows};
+  size_t h = (size_t)((uintptr_t)ptr >> 8) * 1000003u;
+  h ^= (size_t)rows * 31 + (size_t)K * 8191 + (size_t)ld * 131071 + (size_t)zstride * 7 + (size_t)mn_major * 524287 +
+       (size_t)zdim * 65599 + (size_t)box_rows * 2654435761u;
+  const int slot = (int)(h % NSLOT);
+  std::lock_guard<std::mutex> lock(mu);
+  if (used[slot] && keys[slot] == key) {
+    *map = vals[slot];
+    return 0;
+  }
+  if (make_operand_map_uncached(map, ptr, mn_major, rows, K, ld, zstride, zdim, box_rows)) return -1;
+  keys[slot] = key;
+  vals[slot] = *map;
+  used[slot] = true;
+  return 0;
+}
+static int make_operand_map_uncached(CUtensorMap* map, const void* ptr, int mn_major, long rows, long K, long ld,
+                                     long zstride, int zdim, int box_rows) {
   auto enc = get_encode_fn();
   if (!enc) return dwn_fail("cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[3];
