@@ -297,6 +297,29 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
     rng_dev = getattr(mod, "_rng_device", None)        # test hooks: where / in which dtype the masks are drawn
     mdt = getattr(mod, "_mask_dtype", None) or adt
 
+    # drop-path masks of the blocks and the cortex layers, drawn up front in the reference's call order (drop_path,
+    # dwiseneuro.py:46-54 - the RNG stream only sees the order of the calls, not when they run) on a side stream: three tiny
+    # torch kernels per mask no longer sit between a block's projection and its residual epilogue
+    dp_blocks: List[Optional[torch.Tensor]] = [None] * nb
+    dp_cortex: List[Optional[torch.Tensor]] = [None] * len(mod.cortex.layers)
+    mask_side = []
+    if training:
+        mask_side = [_stats_stream(dev)] if (rng_dev is None and dev.type == "cuda" and not SERIALIZE) else []
+        _fork(mask_side, dev)
+        with torch.cuda.stream(mask_side[0]) if mask_side else _nullctx():
+            for i in range(nb):
+                blk_ = mod.core.blocks[2 * i + 1]
+                if blk_.drop_path_rate > 0.0:
+                    dp_blocks[i] = _drop_mask((B, 1, 1, 1, 1), 1.0 - blk_.drop_path_rate, mdt, dev, rng_dev)
+            for li, layer_ in enumerate(mod.cortex.layers):
+                if layer_.drop_path_rate > 0.0:
+                    dp_cortex[li] = _drop_mask((B, 1, 1), 1.0 - layer_.drop_path_rate, mdt, dev, rng_dev)
+    masks_joined = not mask_side
+    if mask_side:
+        for t_ in dp_blocks + dp_cortex:
+            if t_ is not None:
+                t_.record_stream(torch.cuda.current_stream(dev))  # allocated under the side stream, consumed on this one
+
     # ---------------- stem (dwiseneuro.py:306-309) + PE of block 0 -------------------------------
     stem_conv, stem_bn = mod.core.stem[0], mod.core.stem[1].bn
     C0 = feats[0]
@@ -410,9 +433,10 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         coef_sc = coef_sc_early if coef_sc_early is not None else _bn_coef(blk.bn_sc.bn, sc_part, _P, Mo, co, ci, training,
                                                                               st, dev, NQ=3)
         # 6. residual epilogue (+ drop-path, + PE of the next block, + stats of the next shortcut)
-        dp = None
-        if training and blk.drop_path_rate > 0.0:
-            dp = _drop_mask((B, 1, 1, 1, 1), 1.0 - blk.drop_path_rate, mdt, dev, rng_dev)
+        if not masks_joined:
+            _join(mask_side, dev)
+            masks_joined = True
+        dp = dp_blocks[i]
         last = i == nb - 1
         pe = (None, None, None) if last else pe_tables(mod.core.blocks[2 * i + 2], co, T, Ho, Wo, dev)
         Xn = _empty((Mo, co), torch.float32, dev)
@@ -438,7 +462,7 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
         sv.pool = SimpleNamespace(HW=Hi * Wi, C=CL)
 
     # ---------------- cortex (dwiseneuro.py:195-263) ---------------------------------------------
-    for layer in mod.cortex.layers:
+    for li, layer in enumerate(mod.cortex.layers):
         I, O = layer.in_features, layer.out_features
         wc = layer.conv.weight
         Yc = _empty((Mbt, O), adt, dev)
@@ -450,9 +474,10 @@ def run_forward(mod, x: torch.Tensor, index: Optional[int], mode: str, training:
                         training, st, dev)
         coef_sc = _bn_coef(layer.bn_sc.bn, _colstats(cx, Mbt, I, I, F32, st, dev) if training else None, _P, Mbt, O, I,
                            training, st, dev)
-        dp = None
-        if training and layer.drop_path_rate > 0.0:
-            dp = _drop_mask((B, 1, 1), 1.0 - layer.drop_path_rate, mdt, dev, rng_dev)
+        if not masks_joined:
+            _join(mask_side, dev)
+            masks_joined = True
+        dp = dp_cortex[li]
         out = _empty((Mbt, O), torch.float32, dev)
         outb = _empty((Mbt, O), torch.bfloat16, dev) if bf else None
         call("dwn_cortex_out", Yc, coef, dp, cx, coef_sc, out, outb, Mbt, T, I, O, G, dcode, st)
