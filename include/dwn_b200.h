@@ -223,6 +223,22 @@ int dwn_adamw(const void* tab, const int* chunk_tensor, const long* chunk_off, i
 int dwn_ema(const void* tab, const int* chunk_tensor, const long* chunk_off, int nchunks, float decay, void* stream);
 int dwn_scale(float* x, long n, float s, void* stream);
 
+/* ==== data-parallel gradient exchange behind the C ABI (the reference has no distributed path at all:
+ * scripts/train.py:173-189 trains one fold on one GPU).  NCCL is bound at run time (dlopen of the libnccl.so.2 the
+ * process already holds, e.g. torch's), so the library loads on machines without NCCL and these calls then fail loudly.
+ * One communicator per process, one process per GPU; the Python host of this repo keeps using torch.distributed's
+ * communicator (sensorium_b200/parallel.py) - these entry points are for hosts without torch.distributed.
+ *   dwn_comm_unique_id: 128-byte rendezvous token created on rank 0 and handed to the other ranks by the host;
+ *   dwn_allreduce_bucket: in place, asynchronous on comm_stream; dtype 0 = fp32, 1 = bf16, 2 = int32; avg != 0 -> mean
+ *   over ranks (DDP semantics), op_max != 0 -> maximum (per-mouse has-grad flags); several buckets between
+ *   dwn_comm_group_begin / dwn_comm_group_end are issued as one NCCL group. */
+int dwn_comm_unique_id(void* out128);
+int dwn_comm_init(int rank, int nranks, const void* unique_id128);
+int dwn_allreduce_bucket(void* ptr, long count, int dtype, int avg, int op_max, void* comm_stream);
+int dwn_comm_group_begin(void);
+int dwn_comm_group_end(void);
+int dwn_comm_destroy(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,13 @@ SIGNATURES = {
     "dwn_adamw": "ppp" + "i" + "pp" + "i" + "ffffff" + "ppp",
     "dwn_ema": "ppp" + "i" + "f" + "p",
     "dwn_scale": "plfp",
+    # NCCL behind the C ABI (hosts without torch.distributed)
+    "dwn_comm_unique_id": "p",
+    "dwn_comm_init": "iip",
+    "dwn_allreduce_bucket": "pliiip",
+    "dwn_comm_group_begin": "",
+    "dwn_comm_group_end": "",
+    "dwn_comm_destroy": "",
 }
 
 

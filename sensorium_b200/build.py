@@ -13,7 +13,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = Path(__file__).resolve().parent / "libdwn_b200.so"
 SOURCES = ["dwn_api.cu", "dwn_gemm.cu", "dwn_core_fwd.cu", "dwn_core_bwd.cu", "dwn_head.cu", "dwn_optim.cu",
-           "dwn_pw_algebra.cu", "dwn_io.cu"]
+           "dwn_pw_algebra.cu", "dwn_io.cu", "dwn_comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
     if force or _stale(LIB, objs):
-        cmd = [_nvcc(), "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static", "-Wno-deprecated-gpu-targets"]
+        cmd = [_nvcc(), "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static", "-Wno-deprecated-gpu-targets", "-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)

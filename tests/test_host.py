@@ -189,3 +189,14 @@ def test_synthetic_generators_match_the_oracle():
         assert torch.equal(comp[i, :a[m].shape[1]], a[m][i]) and float(comp[i, a[m].shape[1]:].abs().sum()) == 0.0
     v, bh, pc = S.synthetic_trial(50, seed=1)
     assert v.shape == (36, 64, 50) and v.dtype.name == "uint8" and bh.shape == (2, 50) and pc.shape == (2, 50)
+
+
+def test_comm_entry_points_fail_loudly_before_init():
+    """The NCCL entry points behind the C ABI (include/dwn_b200.h) refuse to run without a communicator -
+    no silent no-op (checked without a GPU: the call fails before anything touches the device)."""
+    import ctypes
+    with pytest.raises(_lib.DwnError, match="dwn_comm_init has not been called"):
+        _lib.call("dwn_allreduce_bucket", ctypes.c_void_p(0), 16, 0, 1, 0, ctypes.c_void_p(0))
+    with pytest.raises(_lib.DwnError, match="dwn_comm_init has not been called"):
+        _lib.call("dwn_comm_group_begin")
+    _lib.call("dwn_comm_destroy")   # nothing to destroy: succeeds

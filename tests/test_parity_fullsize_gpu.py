@@ -461,3 +461,16 @@ def test_data_parallel_exchange_two_gpus():
                        capture_output=True, text=True, timeout=900, env=env, cwd=str(ROOT))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "check_dp: PASS" in r.stdout
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_nccl_entry_points_behind_the_c_abi_two_gpus():
+    """tests/gpu_checks/check_comm_cabi.py under torchrun: dwn_comm_init / dwn_allreduce_bucket (include/dwn_b200.h,
+    SURVEY.md 8b) - fp32 mean, bf16 sum, int32 max, grouped buckets - against closed-form expectations."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29641",
+                        str(ROOT / "tests/gpu_checks/check_comm_cabi.py")],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=str(ROOT))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "check_comm_cabi: PASS" in r.stdout
