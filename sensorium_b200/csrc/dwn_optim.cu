@@ -28,7 +28,10 @@ __global__ void adamw_step_kernel(int* __restrict__ steps, const int* __restrict
   bc[2 * t + 1] = (float)sqrt(1.0 - pow((double)b2, (double)st));
 }
 
-__global__ void __launch_bounds__(256) adamw_kernel(const DwnTensorEntry* __restrict__ tab,
+// Occupancy, not bytes in flight per thread, is what this 7-stream pass wants: 6 CTAs per SM (<= 40 registers) and one
+// 16-byte vector per array and iteration run at 82 % of the HBM copy peak; the former unroll-2 body (80 registers, 3 CTAs)
+// ran at 67 %, unroll 4 at 54 %, streaming (evict-first) hints changed nothing (tests/gpu_checks/bench_adamw.py)
+__global__ void __launch_bounds__(256, 6) adamw_kernel(const DwnTensorEntry* __restrict__ tab,
                                                     const int* __restrict__ chunk_tensor,
                                                     const long* __restrict__ chunk_off, const float* __restrict__ bc,
                                                     const int* __restrict__ active, float lr, float wd, float b1, float b2,
@@ -56,7 +59,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const DwnTensorEntry* __rest
   const uintptr_t bits = (uintptr_t)e.p | (uintptr_t)e.g | (uintptr_t)e.m | (uintptr_t)e.v | (uintptr_t)e.ema |
                          ((uintptr_t)e.shadow << 1);
   const long nvec = (bits & 15) == 0 ? (end - off) / 4 : 0;
-#pragma unroll 2
+#pragma unroll 1
   for (long q = threadIdx.x; q < nvec; q += blockDim.x) {
     const long i = off + 4 * q;
     const float4 g4 = *reinterpret_cast<const float4*>(e.g + i);
